@@ -1,0 +1,59 @@
+// C-ABI glue of libb200parse.so: error string, launch counter, and the dense-contraction entry points.
+// Declarations + the reference call sites each entry point replaces: include/b200parse.h.
+#include "b2p_internal.h"
+#include <atomic>
+#include <mutex>
+#include <string>
+
+namespace b2p {
+static std::mutex g_err_mu;
+static std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+int set_error(const char* msg) {
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  g_err = msg ? msg : "unknown error";
+  return -1;
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace b2p
+
+using namespace b2p;
+
+extern "C" {
+
+const char* b2p_last_error(void) {
+  static thread_local std::string copy;
+  std::lock_guard<std::mutex> lk(g_err_mu);
+  copy = g_err;
+  return copy.c_str();
+}
+
+long long b2p_launch_count(void) { return g_launches.load(); }
+
+int b2p_abi_version(void) { return 1; }
+
+// C[M,N] = act(A[M,K] * B[N,K]^T + bias) (+ residual); A, B fp16 (bf16 if flags&1); out fp16 or fp32 (flags&2).
+int b2p_gemm(const void* A, long long lda, const void* B, int M, int N, int K, void* out, long long ldc,
+             const float* bias, const void* residual, long long ldr, int act, int flags, cudaStream_t st) {
+  ConvGemm d{};
+  d.mode = 0; d.bf16 = flags & 1; d.A = A; d.lda = lda; d.B = B; d.M = M; d.N = N; d.K = K;
+  d.out = out; d.ldc = ldc; d.out_f32 = (flags >> 1) & 1; d.bias = bias; d.res = residual; d.ldr = ldr; d.act = act;
+  d.bn_max = (flags >> 8) & 0x1ff;
+  return gemm_launch(d, st);
+}
+
+// 3x3 pad-1 convolution (stride 1 or 2) on an NHWC fp16 channel slice; weights [Cout][9*Cin] ordered (ky,kx,c).
+int b2p_conv3x3(const void* in, long long ld_in, int batch, int H, int W, int Cin, int stride, const void* weight,
+                int Cout, void* out, long long ldc, const float* bias, const void* residual, long long ldr, int act,
+                int flags, cudaStream_t st) {
+  if (stride != 1 && stride != 2) return set_error("conv3x3: stride must be 1 or 2");
+  ConvGemm d{};
+  d.mode = stride; d.bf16 = flags & 1; d.A = in; d.lda = ld_in; d.B = weight; d.N = Cout;
+  d.batch = batch; d.H = H; d.W = W; d.Cin = Cin;
+  d.out = out; d.ldc = ldc; d.out_f32 = (flags >> 1) & 1; d.bias = bias; d.res = residual; d.ldr = ldr; d.act = act;
+  d.bn_max = (flags >> 8) & 0x1ff;
+  return gemm_launch(d, st);
+}
+
+}  // extern "C"

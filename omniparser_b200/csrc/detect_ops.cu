@@ -1,0 +1,230 @@
+// HBM-bound NHWC fp16 helpers of the YOLOv9-E graph (ref:util/yolov9.py:120-121 runs them inside the
+// TorchScript archive): ADown pooling, SPPELAN max-pool, nearest upsample, CBFuse multi-scale sum.
+// Every tensor is a channel slice (pointer + pixel stride `ld`) so concats are never materialised.
+// 8 channels (one 16-byte vector) per thread, channels fastest => fully coalesced.
+#include "b2p_internal.h"
+#include <cuda_fp16.h>
+
+namespace b2p {
+
+struct H8 { uint4 v; };
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+__device__ __forceinline__ uint4 ld8(const __half* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void st8(__half* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+
+// ADown front half (common.py::ADown.forward): a = avg_pool2d(x, 2, 1) (size (H-1)x(W-1)); x1 = a[:, :C/2],
+// x2 = max_pool2d(a[:, C/2:], 3, 2, 1).  x1 is stored as an HxW map whose last row/column are zero, which is
+// exactly the zero padding the following 3x3 stride-2 pad-1 conv would see (keeps H, W even for the TMA view).
+__global__ void adown_pool_kernel(const __half* __restrict__ x, long long ldx, int B, int H, int W, int C,
+                                  __half* __restrict__ x1, long long ld1, __half* __restrict__ x2, long long ld2) {
+  const int c8n = C / 16;   // vectors per half
+  const long long n1 = (long long)B * H * W * c8n;
+  const int Ho = H / 2, Wo = W / 2;
+  const long long n2 = (long long)B * Ho * Wo * c8n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n1 + n2; i += (long long)gridDim.x * blockDim.x) {
+    if (i < n1) {
+      const int cv = int(i % c8n);
+      long long p = i / c8n;
+      const int xx = int(p % W); p /= W;
+      const int yy = int(p % H);
+      const int b = int(p / H);
+      float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (yy < H - 1 && xx < W - 1) {
+        const __half* s = x + (((long long)b * H + yy) * W + xx) * ldx + cv * 8;
+        float a[8], bq[8], c[8], d[8];
+        unpack8(ld8(s), a); unpack8(ld8(s + ldx), bq); unpack8(ld8(s + (long long)W * ldx), c); unpack8(ld8(s + (long long)(W + 1) * ldx), d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = ((a[k] + bq[k]) + (c[k] + d[k])) * 0.25f;
+      }
+      st8(x1 + (((long long)b * H + yy) * W + xx) * ld1 + cv * 8, pack8(o));
+    } else {
+      const long long j = i - n1;
+      const int cv = int(j % c8n);
+      long long p = j / c8n;
+      const int ox = int(p % Wo); p /= Wo;
+      const int oy = int(p % Ho);
+      const int b = int(p / Ho);
+      float m[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int yy = 2 * oy + dy;
+        if (yy < 0 || yy >= H - 1) continue;
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int xx = 2 * ox + dx;
+          if (xx < 0 || xx >= W - 1) continue;
+          const __half* s = x + (((long long)b * H + yy) * W + xx) * ldx + C / 2 + cv * 8;
+          float a[8], bq[8], c[8], d[8];
+          unpack8(ld8(s), a); unpack8(ld8(s + ldx), bq); unpack8(ld8(s + (long long)W * ldx), c); unpack8(ld8(s + (long long)(W + 1) * ldx), d);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], ((a[k] + bq[k]) + (c[k] + d[k])) * 0.25f);
+        }
+      }
+      st8(x2 + (((long long)b * Ho + oy) * Wo + ox) * ld2 + cv * 8, pack8(m));
+    }
+  }
+}
+
+// MaxPool2d(k, stride 1, pad k/2) on a channel slice (SPPELAN, k = 5).
+__global__ void maxpool_s1_kernel(const __half* __restrict__ x, long long ldx, int B, int H, int W, int C, int k,
+                                  __half* __restrict__ y, long long ldy) {
+  const int cvn = C / 8;
+  const long long n = (long long)B * H * W * cvn;
+  const int r = k / 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = int(i % cvn);
+    long long p = i / cvn;
+    const int xx = int(p % W); p /= W;
+    const int yy = int(p % H);
+    const int b = int(p / H);
+    __half2 m[4];
+    const __half2 ninf = __float2half2_rn(-INFINITY);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) m[q] = ninf;
+    for (int dy = -r; dy <= r; ++dy) {
+      const int sy = yy + dy;
+      if (sy < 0 || sy >= H) continue;
+      for (int dx = -r; dx <= r; ++dx) {
+        const int sx = xx + dx;
+        if (sx < 0 || sx >= W) continue;
+        const uint4 v = ld8(x + (((long long)b * H + sy) * W + sx) * ldx + cv * 8);
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) m[q] = __hmax2(m[q], h[q]);
+      }
+    }
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) oh[q] = m[q];
+    st8(y + (((long long)b * H + yy) * W + xx) * ldy + cv * 8, o);
+  }
+}
+
+// nn.Upsample(scale_factor=2, mode='nearest') into a channel slice.
+__global__ void upsample2x_kernel(const __half* __restrict__ x, long long ldx, int B, int H, int W, int C,
+                                  __half* __restrict__ y, long long ldy) {
+  const int cvn = C / 8;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const long long n = (long long)B * Ho * Wo * cvn;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = int(i % cvn);
+    long long p = i / cvn;
+    const int xx = int(p % Wo); p /= Wo;
+    const int yy = int(p % Ho);
+    const int b = int(p / Ho);
+    st8(y + (((long long)b * Ho + yy) * Wo + xx) * ldy + cv * 8,
+        ld8(x + (((long long)b * H + (yy >> 1)) * W + (xx >> 1)) * ldx + cv * 8));
+  }
+}
+
+struct FuseSrc { const __half* p; long long ld; int shift; int H, W; };
+struct FuseArgs { FuseSrc s[5]; int n; };
+
+// CBFuse (common.py::CBFuse): out = sum_i nearest_upsample(src_i) + last, summed in that order in fp32.
+__global__ void cbfuse_kernel(FuseArgs a, const __half* __restrict__ last, long long ldl, int B, int H, int W, int C,
+                              __half* __restrict__ y, long long ldy) {
+  const int cvn = C / 8;
+  const long long n = (long long)B * H * W * cvn;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = int(i % cvn);
+    long long p = i / cvn;
+    const int xx = int(p % W); p /= W;
+    const int yy = int(p % H);
+    const int b = int(p / H);
+    float acc[8], t[8];
+    bool first = true;
+    for (int s = 0; s < a.n; ++s) {
+      const FuseSrc& f = a.s[s];
+      unpack8(ld8(f.p + (((long long)b * f.H + (yy >> f.shift)) * f.W + (xx >> f.shift)) * f.ld + cv * 8), t);
+      if (first) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = t[k];
+        first = false;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += t[k];
+      }
+    }
+    unpack8(ld8(last + (((long long)b * H + yy) * W + xx) * ldl + cv * 8), t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = first ? t[k] : acc[k] + t[k];
+    st8(y + (((long long)b * H + yy) * W + xx) * ldy + cv * 8, pack8(acc));
+  }
+}
+
+static inline int grid_for(long long n, int threads) {
+  long long b = (n + threads - 1) / threads;
+  const long long cap = 148LL * 16;
+  return int(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace b2p
+
+using namespace b2p;
+
+extern "C" {
+
+int b2p_adown_pool(const void* x, long long ldx, int B, int H, int W, int C, void* x1, long long ld1, void* x2,
+                   long long ld2, cudaStream_t st) {
+  if ((H & 1) || (W & 1) || (C % 16)) return set_error("adown_pool: H, W must be even and C a multiple of 16");
+  const long long n = (long long)B * H * W * (C / 16) + (long long)B * (H / 2) * (W / 2) * (C / 16);
+  adown_pool_kernel<<<grid_for(n, 256), 256, 0, st>>>((const __half*)x, ldx, B, H, W, C, (__half*)x1, ld1, (__half*)x2, ld2);
+  B2P_CHECK_LAUNCH();
+  return 0;
+}
+
+int b2p_maxpool_s1(const void* x, long long ldx, int B, int H, int W, int C, int k, void* y, long long ldy, cudaStream_t st) {
+  if (C % 8) return set_error("maxpool_s1: C must be a multiple of 8");
+  const long long n = (long long)B * H * W * (C / 8);
+  maxpool_s1_kernel<<<grid_for(n, 256), 256, 0, st>>>((const __half*)x, ldx, B, H, W, C, k, (__half*)y, ldy);
+  B2P_CHECK_LAUNCH();
+  return 0;
+}
+
+int b2p_upsample2x(const void* x, long long ldx, int B, int H, int W, int C, void* y, long long ldy, cudaStream_t st) {
+  if (C % 8) return set_error("upsample2x: C must be a multiple of 8");
+  const long long n = (long long)B * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<grid_for(n, 256), 256, 0, st>>>((const __half*)x, ldx, B, H, W, C, (__half*)y, ldy);
+  B2P_CHECK_LAUNCH();
+  return 0;
+}
+
+// srcs[i]: pointer to the selected CBLinear split (already offset to its first channel), lds[i] its pixel stride,
+// shifts[i] = log2(target size / source size).
+int b2p_cbfuse(int nsrc, const void* const* srcs, const long long* lds, const int* shifts, const void* last,
+               long long ldl, int B, int H, int W, int C, void* y, long long ldy, cudaStream_t st) {
+  if (nsrc < 0 || nsrc > 5) return set_error("cbfuse: at most 5 upsampled sources");
+  if (C % 8) return set_error("cbfuse: C must be a multiple of 8");
+  FuseArgs a{};
+  a.n = nsrc;
+  for (int i = 0; i < nsrc; ++i) {
+    a.s[i].p = (const __half*)srcs[i];
+    a.s[i].ld = lds[i];
+    a.s[i].shift = shifts[i];
+    a.s[i].H = H >> shifts[i];
+    a.s[i].W = W >> shifts[i];
+  }
+  const long long n = (long long)B * H * W * (C / 8);
+  cbfuse_kernel<<<grid_for(n, 256), 256, 0, st>>>(a, (const __half*)last, ldl, B, H, W, C, (__half*)y, ldy);
+  B2P_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,478 @@
+// One persistent, warp-specialised tcgen05 kernel for every dense contraction on the parse hot path:
+//   mode 0  C[M,N] = A[M,K] * B[N,K]^T                 (1x1 convs on NHWC, all transformer linears, LM head)
+//   mode 1  3x3 stride-1 pad-1 convolution on NHWC      (implicit GEMM: 9 shifted TMA boxes per Cin block)
+//   mode 2  3x3 stride-2 pad-1 convolution on NHWC      (implicit GEMM through a 5-D even/odd "parity" view)
+// Operands fp16 (or bf16), accumulate fp32 in TMEM, fused epilogue: +bias, SiLU / exact GELU, +residual,
+// store fp16 or fp32 into a channel slice (row stride ldc) of the destination so concats are never
+// materialised.  Replaces the cuDNN/cuBLAS library kernels behind ref:util/yolov9.py:120-121 (TorchScript
+// YOLOv9-E forward) and ref:util/utils.py:125 (Florence-2 generate).
+//
+// Roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one elected lane),
+// warp 2 also owns TMEM alloc/dealloc, warps 2..5 = epilogue (TMEM lane group = warp % 4).
+// Pipelines: smem ring full/empty (TMA <-> MMA), TMEM accumulator double buffer full/empty (MMA <-> epilogue).
+#include "ptx.cuh"
+#include "b2p_internal.h"
+#include <cuda_fp16.h>
+#include <math.h>
+
+namespace b2p {
+
+static constexpr int kThreads = 192;
+static constexpr int kTileM = 128;
+static constexpr int kASlot = 16384;    // 128 rows x 128 B
+static constexpr int kMaxStages = 8;
+static constexpr int kTmemCols = 512;
+
+struct GemmArgs {
+  int mode, M, N, num_kb, bk, bn;
+  int cin_blocks, tw, th, tiles_x, tiles_y, Ho, Wo, batch;
+  int m_tiles, n_tiles, stages, ldpar;
+  uint32_t a_bytes, b_bytes, b_slot;
+  uint32_t idesc;
+  uint64_t desc_hi;   // high 32 bits of the smem matrix descriptor (SBO, version, layout), shifted in place
+  void* out;
+  long long ldc;
+  int out_f32;
+  const float* bias;
+  const void* res;
+  long long ldr;
+  int act, vec_ok;
+};
+
+// Shared-memory matrix descriptor (PTX ISA "tcgen05 matrix descriptor"), K-major operand, swizzled:
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (=1, unused for swizzled K-major) | [32,46) SBO >> 4
+//   [46,48) version = 1 (sm_100) | [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B.
+// SBO = byte distance between consecutive 8-row groups (8 rows x row pitch).
+__host__ __device__ inline uint64_t make_desc_hi(int bk) {
+  const uint64_t sbo = (bk == 64) ? 1024 : 512;
+  const uint64_t layout = (bk == 64) ? 2 : 4;
+  return (uint64_t(1) << 16) | ((sbo >> 4) << 32) | (uint64_t(1) << 46) | (layout << 61);
+}
+// Instruction descriptor for kind::f16: [4,6) D fmt (1 = f32) | [7,10) A fmt | [10,13) B fmt (0 = f16, 1 = bf16)
+//   | bit 15/16 A/B major (0 = K-major) | [17,23) N >> 3 | [24,29) M >> 4.
+__host__ inline uint32_t make_idesc(int bn, int bf16) {
+  uint32_t f = bf16 ? 1u : 0u;
+  return (1u << 4) | (f << 7) | (f << 10) | (uint32_t(bn >> 3) << 17) | (uint32_t(kTileM >> 4) << 24);
+}
+
+__device__ __forceinline__ float act_fn(float x, int act) {
+  if (act == 1) return x / (1.0f + __expf(-x));                        // SiLU
+  if (act == 2) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));  // exact GELU
+  return x;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t stage_bytes = kASlot + g.b_slot;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(g.stages) * stage_bytes);
+  const uint32_t bar_full = smem_u32(bars);
+  const uint32_t bar_empty = bar_full + 8 * g.stages;
+  const uint32_t bar_tfull = bar_empty + 8 * g.stages;
+  const uint32_t bar_tempty = bar_tfull + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * g.stages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < g.stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = g.m_tiles * g.n_tiles;
+  const uint32_t smem_base = smem_u32(smem);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % g.n_tiles;
+        const int mt = tile / g.n_tiles;
+        const int n0 = nt * g.bn;
+        int img = 0, y0 = 0, x0 = 0;
+        if (g.mode != 0) {
+          const int per_img = g.tiles_x * g.tiles_y;
+          img = mt / per_img;
+          const int r = mt - img * per_img;
+          y0 = (r / g.tiles_x) * g.th;
+          x0 = (r % g.tiles_x) * g.tw;
+        }
+        for (int kb = 0; kb < g.num_kb; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t fb = bar_full + 8 * stage;
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint32_t sb = sa + kASlot;
+          mbar_expect_tx(fb, g.a_bytes + g.b_bytes);
+          if (g.mode == 0) {
+            tma_load_2d(sa, &tmA, fb, kb * g.bk, mt * kTileM);
+          } else {
+            const int tap = kb / g.cin_blocks;
+            const int c0 = (kb - tap * g.cin_blocks) * g.bk;
+            const int ky = tap / 3, kx = tap - ky * 3;
+            if (g.mode == 1) {
+              tma_load_4d(sa, &tmA, fb, c0, x0 + kx - 1, y0 + ky - 1, img);
+            } else {
+              // input row 2*oy + (ky-1): ky=0 -> (oy-1, odd), ky=1 -> (oy, even), ky=2 -> (oy, odd); same in x.
+              const int py = (ky != 1), px = (kx != 1);
+              const int yo = y0 - (ky == 0), xo = x0 - (kx == 0);
+              tma_load_5d(sa, &tmA, fb, c0 + px * g.ldpar, xo, py, yo, img);
+            }
+          }
+          tma_load_2d(sb, &tmB, fb, kb * g.bk, n0);
+          if (++stage == g.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ MMA issuer
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const int ksteps = g.bk / 16;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * 256);
+        for (int kb = 0; kb < g.num_kb; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint32_t sb = sa + kASlot;
+          const uint64_t da = g.desc_hi | uint64_t((sa & 0x3FFFF) >> 4);
+          const uint64_t db = g.desc_hi | uint64_t((sb & 0x3FFFF) >> 4);
+          for (int k = 0; k < ksteps; ++k) {
+            // advancing K inside the swizzle span = +32 B on the start address (encoded >> 4)
+            umma_f16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), g.idesc, (kb | k) != 0);
+          }
+          umma_commit(bar_empty + 8 * stage);
+          if (++stage == g.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(bar_tfull + 8 * acc);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // -------------------------------------------------------------- epilogue (4 warps, 128 TMEM lanes)
+    const int grp = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    __half* outh = reinterpret_cast<__half*>(g.out);
+    float* outf = reinterpret_cast<float*>(g.out);
+    const __half* resh = reinterpret_cast<const __half*>(g.res);
+    const float* resf = reinterpret_cast<const float*>(g.res);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile % g.n_tiles;
+      const int mt = tile / g.n_tiles;
+      const int n0 = nt * g.bn;
+      const int r = grp * 32 + lane;
+      long long pix;
+      bool valid;
+      if (g.mode == 0) {
+        pix = (long long)mt * kTileM + r;
+        valid = pix < g.M;
+      } else {
+        const int per_img = g.tiles_x * g.tiles_y;
+        const int img = mt / per_img;
+        const int rr = mt - img * per_img;
+        const int ty = r / g.tw, tx = r - ty * g.tw;
+        const int oy = (rr / g.tiles_x) * g.th + ty;
+        const int ox = (rr % g.tiles_x) * g.tw + tx;
+        valid = (ty < g.th) && (oy < g.Ho) && (ox < g.Wo);
+        pix = ((long long)img * g.Ho + oy) * g.Wo + ox;
+      }
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (uint32_t(grp * 32) << 16) + uint32_t(acc * 256);
+      for (int c = 0; c < g.bn; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_row + c, v);
+        tmem_ld_wait();
+        const int nb = n0 + c;
+        if (nb >= g.N) continue;   // warp-uniform
+        float x[16];
+        const bool full = (nb + 16 <= g.N);
+        if (full && g.vec_ok) {
+          if (g.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(g.bias + nb);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 b = __ldg(bp + q);
+              x[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + b.x;
+              x[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + b.y;
+              x[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + b.z;
+              x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + b.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]);
+          }
+          if (g.act) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = act_fn(x[j], g.act);
+          }
+          if (valid) {
+            if (g.res) {
+              if (g.out_f32) {
+                const float4* rp = reinterpret_cast<const float4*>(resf + pix * g.ldr + nb);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float4 t = rp[q];
+                  x[4 * q] += t.x; x[4 * q + 1] += t.y; x[4 * q + 2] += t.z; x[4 * q + 3] += t.w;
+                }
+              } else {
+                const uint4* rp = reinterpret_cast<const uint4*>(resh + pix * g.ldr + nb);
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                  const uint4 t = rp[q];
+                  const __half2* hp = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __half22float2(hp[e]);
+                    x[8 * q + 2 * e] += f.x;
+                    x[8 * q + 2 * e + 1] += f.y;
+                  }
+                }
+              }
+            }
+            if (g.out_f32) {
+              float4* op = reinterpret_cast<float4*>(outf + pix * g.ldc + nb);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) op[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+            } else {
+              uint4 pk[2];
+              __half2* hp = reinterpret_cast<__half2*>(pk);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) hp[e] = __floats2half2_rn(x[2 * e], x[2 * e + 1]);
+              uint4* op = reinterpret_cast<uint4*>(outh + pix * g.ldc + nb);
+              op[0] = pk[0];
+              op[1] = pk[1];
+            }
+          }
+        } else {
+          // ragged tail / unaligned destination: scalar path
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = nb + j;
+            if (n < g.N) {
+              float t = __uint_as_float(v[j]);
+              if (g.bias) t += __ldg(g.bias + n);
+              t = act_fn(t, g.act);
+              if (valid) {
+                if (g.res) t += g.out_f32 ? resf[pix * g.ldr + n] : __half2float(resh[pix * g.ldr + n]);
+                if (g.out_f32) outf[pix * g.ldc + n] = t;
+                else outh[pix * g.ldc + n] = __float2half_rn(t);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int encode(CUtensorMap* m, int bf16, int rank, const void* base, const cuuint64_t* dims,
+                  const cuuint64_t* strides_bytes, const cuuint32_t* box, int bk) {
+  EncodeTiledFn fn = get_encode();
+  if (!fn) return set_error("cuTensorMapEncodeTiled entry point unavailable");
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank,
+                  const_cast<void*>(base), dims, strides_bytes, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed: CUresult %d (rank %d, dims %llu %llu, box %u %u)", int(r),
+             rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return set_error(buf);
+  }
+  return 0;
+}
+
+static int g_num_sms = 0;
+static int g_max_smem = 0;
+
+static int device_setup() {
+  if (g_num_sms) return 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return set_error("cudaGetDevice failed (no CUDA device?)");
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return set_error("cudaGetDeviceProperties failed");
+  if (p.major != 10) return set_error("libb200parse requires an sm_100 (Blackwell B200) device");
+  g_num_sms = p.multiProcessorCount;
+  g_max_smem = int(p.sharedMemPerBlockOptin);
+  if (cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem) != cudaSuccess)
+    return set_error("cudaFuncSetAttribute(max dynamic smem) failed");
+  return 0;
+}
+
+static int pick_bn(int N, int m_tiles, int num_kb, int bn_max) {
+  static const int cand[] = {256, 192, 128, 96, 64, 48, 32, 16};
+  const int n16 = (N + 15) / 16 * 16;
+  long best_cost = -1;
+  int best = 16;
+  for (int c : cand) {
+    if (c > bn_max) continue;
+    if (c > n16 && c != 16) {
+      // allow the smallest candidate that still covers N
+      bool smaller_covers = false;
+      for (int d : cand) if (d < c && d >= n16) smaller_covers = true;
+      if (smaller_covers) continue;
+    }
+    const long n_tiles = (N + c - 1) / c;
+    const long tiles = n_tiles * m_tiles;
+    const long waves = (tiles + g_num_sms - 1) / g_num_sms;
+    const long per_tile = long(num_kb) * (c > 64 ? c : 64) + 700;   // MMA issue floor ~ N/2 cyc per K16, + prologue/epilogue
+    const long cost = waves * per_tile;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = c; }
+  }
+  return best;
+}
+
+int gemm_launch(const ConvGemm& d, cudaStream_t st) {
+  if (int e = device_setup()) return e;
+  GemmArgs g{};
+  CUtensorMap tmA, tmB;
+  const int Ktot = (d.mode == 0) ? d.K : 9 * d.Cin;
+  const int kred = (d.mode == 0) ? d.K : d.Cin;
+  const int bk = (kred % 64 == 0) ? 64 : 32;
+  if (d.mode != 0 && kred % 32 != 0) return set_error("conv3x3: Cin must be a multiple of 32");
+  if (d.mode == 0 && (d.K % 8 != 0 || d.lda % 8 != 0)) return set_error("gemm: K and lda must be multiples of 8");
+  if ((reinterpret_cast<uintptr_t>(d.A) & 15) || (reinterpret_cast<uintptr_t>(d.B) & 15)) return set_error("gemm: operands must be 16-byte aligned");
+  g.mode = d.mode;
+  g.N = d.N;
+  g.bk = bk;
+  g.desc_hi = make_desc_hi(bk);
+  g.out = d.out; g.ldc = d.ldc; g.out_f32 = d.out_f32; g.bias = d.bias; g.res = d.res; g.ldr = d.ldr; g.act = d.act;
+
+  if (d.mode == 0) {
+    g.M = d.M;
+    g.num_kb = (d.K + bk - 1) / bk;
+    g.m_tiles = (d.M + kTileM - 1) / kTileM;
+    g.a_bytes = kTileM * bk * 2;
+    cuuint64_t dims[2] = {cuuint64_t(d.K), cuuint64_t(d.M)};
+    cuuint64_t str[1] = {cuuint64_t(d.lda) * 2};
+    cuuint32_t box[2] = {cuuint32_t(bk), cuuint32_t(kTileM)};
+    if (int e = encode(&tmA, d.bf16, 2, d.A, dims, str, box, bk)) return e;
+  } else {
+    const int s = (d.mode == 2) ? 2 : 1;
+    if (s == 2 && ((d.H & 1) || (d.W & 1))) return set_error("conv3x3 s2: H and W must be even");
+    if (d.lda % 8 != 0) return set_error("conv3x3: input pixel stride must be a multiple of 8 channels");
+    g.Ho = d.H / s; g.Wo = d.W / s; g.batch = d.batch;
+    g.cin_blocks = d.Cin / bk;
+    g.num_kb = 9 * g.cin_blocks;
+    // spatial tile tw x th <= 128 output pixels: maximise useful rows per 128-row MMA tile
+    int btw = 1, bth = 1; double bu = -1;
+    for (int tw = 1; tw <= g.Wo && tw <= 128; ++tw) {
+      int th = 128 / tw; if (th > g.Ho) th = g.Ho; if (th < 1) continue;
+      const long tiles = long((g.Wo + tw - 1) / tw) * ((g.Ho + th - 1) / th);
+      const double u = double(g.Ho) * g.Wo / (double(tiles) * 128.0);
+      if (u > bu + 1e-9 || (u > bu - 1e-9 && tw > btw)) { bu = u; btw = tw; bth = th; }
+    }
+    g.tw = btw; g.th = bth;
+    g.tiles_x = (g.Wo + btw - 1) / btw; g.tiles_y = (g.Ho + bth - 1) / bth;
+    g.m_tiles = g.tiles_x * g.tiles_y * d.batch;
+    g.a_bytes = uint32_t(btw) * bth * bk * 2;
+    const cuuint64_t ld = cuuint64_t(d.lda);
+    if (d.mode == 1) {
+      cuuint64_t dims[4] = {cuuint64_t(d.Cin), cuuint64_t(d.W), cuuint64_t(d.H), cuuint64_t(d.batch)};
+      cuuint64_t str[3] = {ld * 2, ld * 2 * d.W, ld * 2 * d.W * d.H};
+      cuuint32_t box[4] = {cuuint32_t(bk), cuuint32_t(btw), cuuint32_t(bth), 1};
+      if (int e = encode(&tmA, d.bf16, 4, d.A, dims, str, box, bk)) return e;
+    } else {
+      // (x parity, channel) merged in dim0: element (n, 2*yo+py, 2*xo+px, c) at c + px*ld  (+ xo*2ld + py*W*ld + yo*2W*ld)
+      g.ldpar = int(d.lda);   // producer adds px * ldA to the channel coordinate
+      cuuint64_t dims[5] = {ld + cuuint64_t(d.Cin), cuuint64_t(d.W / 2), 2, cuuint64_t(d.H / 2), cuuint64_t(d.batch)};
+      cuuint64_t str[4] = {ld * 4, ld * 2 * d.W, ld * 4 * d.W, ld * 2 * d.W * d.H};
+      cuuint32_t box[5] = {cuuint32_t(bk), cuuint32_t(btw), 1, cuuint32_t(bth), 1};
+      if (int e = encode(&tmA, d.bf16, 5, d.A, dims, str, box, bk)) return e;
+    }
+  }
+  const int bn = pick_bn(d.N, g.m_tiles, g.num_kb, d.bn_max > 0 ? d.bn_max : 256);
+  g.bn = bn;
+  g.n_tiles = (d.N + bn - 1) / bn;
+  g.b_bytes = uint32_t(bn) * bk * 2;
+  g.b_slot = (g.b_bytes + 1023) & ~1023u;
+  g.idesc = make_idesc(bn, d.bf16);
+  {
+    cuuint64_t dims[2] = {cuuint64_t(Ktot), cuuint64_t(d.N)};
+    cuuint64_t str[1] = {cuuint64_t(Ktot) * 2};
+    cuuint32_t box[2] = {cuuint32_t(bk), cuuint32_t(bn)};
+    if (int e = encode(&tmB, d.bf16, 2, d.B, dims, str, box, bk)) return e;
+  }
+  const int stage_bytes = kASlot + int(g.b_slot);
+  int stages = (g_max_smem - 1024 - 256) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > g.num_kb && g.num_kb >= 2) stages = g.num_kb;
+  if (stages < 2) stages = 2;
+  g.stages = stages;
+  const size_t smem = size_t(stages) * stage_bytes + 1024 + 256;
+  // vector epilogue needs 16-byte aligned rows in out / residual and bias
+  const int esz = d.out_f32 ? 4 : 2;
+  g.vec_ok = ((reinterpret_cast<uintptr_t>(d.out) & 15) == 0) && ((d.ldc * esz) % 16 == 0) &&
+             (!d.res || (((reinterpret_cast<uintptr_t>(d.res) & 15) == 0) && ((d.ldr * esz) % 16 == 0))) &&
+             (!d.bias || ((reinterpret_cast<uintptr_t>(d.bias) & 15) == 0));
+  const int total = g.m_tiles * g.n_tiles;
+  const int grid = total < g_num_sms ? total : g_num_sms;
+  if (grid <= 0) return 0;
+  gemm_tcgen05_kernel<<<grid, kThreads, smem, st>>>(tmA, tmB, g);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return set_error(cudaGetErrorString(ce));
+  count_launch();
+  return 0;
+}
+
+}  // namespace b2p

@@ -1,0 +1,149 @@
+"""Torch-tensor front ends of the C-ABI ops (device memory and streams come from PyTorch; the math does not).
+
+A feature map is a :class:`Map`: an NHWC fp16 channel slice ``(ptr, B, H, W, C, ld)`` inside a larger buffer,
+so concatenations (``torch.cat`` in the reference graph) are never materialised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
+FLAG_BF16, FLAG_OUT_F32 = 1, 2
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    if t is None:
+        return C.c_void_p(0)
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    return C.c_void_p(t.data_ptr())
+
+
+@dataclass
+class Map:
+    """NHWC channel slice: element (b, y, x, c) lives at ptr + 2*(((b*H + y)*W + x)*ld + c) bytes (fp16)."""
+
+    buf: torch.Tensor   # owning buffer [B, H, W, ld]
+    c0: int
+    C: int
+
+    @property
+    def B(self): return self.buf.shape[0]
+    @property
+    def H(self): return self.buf.shape[1]
+    @property
+    def W(self): return self.buf.shape[2]
+    @property
+    def ld(self): return self.buf.shape[3]
+    @property
+    def ptr(self): return self.buf.data_ptr() + self.c0 * self.buf.element_size()
+
+    def slice(self, c0, C_):
+        assert 0 <= c0 and c0 + C_ <= self.C
+        return Map(self.buf, self.c0 + c0, C_)
+
+    def torch(self):
+        """NCHW float32 copy (tests / debugging only)."""
+        return self.buf[..., self.c0:self.c0 + self.C].permute(0, 3, 1, 2).float()
+
+
+def new_map(B, H, W, Ctot, device, dtype=torch.float16):
+    return Map(torch.empty((B, H, W, Ctot), device=device, dtype=dtype), 0, Ctot)
+
+
+def gemm(a_ptr, lda, w, M, N, K, out_ptr, ldc, bias=None, res_ptr=None, ldr=0, act=ACT_NONE, out_f32=False,
+         bf16=False, bn_max=0):
+    flags = (FLAG_BF16 if bf16 else 0) | (FLAG_OUT_F32 if out_f32 else 0) | (bn_max << 8)
+    _lib.check(_lib.lib().b2p_gemm(_p(a_ptr), lda, _p(w), M, N, K, _p(out_ptr), ldc, _p(bias), _p(res_ptr), ldr, act,
+                                   flags, _stream()))
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias=None, res=None, act=ACT_NONE, out_dtype=torch.float16, out=None,
+           bn_max=0):
+    """out[M,N] = act(x[M,K] @ w[N,K]^T + bias) + res ; x, w fp16 row-major (x may be a strided row view)."""
+    assert x.dim() == 2 and w.dim() == 2 and x.shape[1] == w.shape[1] and x.stride(1) == 1 and w.is_contiguous()
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=out_dtype)
+    assert out.stride(1) == 1
+    if res is not None:
+        assert res.dtype == out.dtype and res.stride(1) == 1
+    gemm(x, x.stride(0), w, M, N, K, out, out.stride(0), bias, res, res.stride(0) if res is not None else 0, act,
+         out_f32=(out.dtype == torch.float32), bf16=(x.dtype == torch.bfloat16), bn_max=bn_max)
+    return out
+
+
+def conv1x1(x: Map, w, out: Map, bias=None, res: Map | None = None, act=ACT_SILU, out_f32=False):
+    M = x.B * x.H * x.W
+    gemm(x.ptr, x.ld, w, M, out.C, x.C, out.ptr, out.ld, bias, res.ptr if res else None, res.ld if res else 0, act,
+         out_f32=out_f32)
+
+
+def conv3x3(x: Map, w, out: Map, stride=1, bias=None, res: Map | None = None, act=ACT_SILU, out_f32=False, bn_max=0):
+    flags = (FLAG_OUT_F32 if out_f32 else 0) | (bn_max << 8)
+    _lib.check(_lib.lib().b2p_conv3x3(_p(x.ptr), x.ld, x.B, x.H, x.W, x.C, stride, _p(w), out.C, _p(out.ptr), out.ld,
+                                      _p(bias), _p(res.ptr if res else None), res.ld if res else 0, act, flags,
+                                      _stream()))
+
+
+def adown_pool(x: Map, x1: Map, x2: Map):
+    _lib.check(_lib.lib().b2p_adown_pool(_p(x.ptr), x.ld, x.B, x.H, x.W, x.C, _p(x1.ptr), x1.ld, _p(x2.ptr), x2.ld,
+                                         _stream()))
+
+
+def maxpool_s1(x: Map, y: Map, k=5):
+    _lib.check(_lib.lib().b2p_maxpool_s1(_p(x.ptr), x.ld, x.B, x.H, x.W, x.C, k, _p(y.ptr), y.ld, _stream()))
+
+
+def upsample2x(x: Map, y: Map):
+    _lib.check(_lib.lib().b2p_upsample2x(_p(x.ptr), x.ld, x.B, x.H, x.W, x.C, _p(y.ptr), y.ld, _stream()))
+
+
+def cbfuse(srcs: list[Map], last: Map, out: Map):
+    n = len(srcs)
+    ptrs = (C.c_void_p * max(n, 1))(*[s.ptr for s in srcs])
+    lds = (C.c_longlong * max(n, 1))(*[s.ld for s in srcs])
+    shifts = (C.c_int * max(n, 1))(*[(last.H // s.H).bit_length() - 1 for s in srcs])
+    _lib.check(_lib.lib().b2p_cbfuse(n, ptrs, lds, shifts, _p(last.ptr), last.ld, last.B, last.H, last.W, last.C,
+                                     _p(out.ptr), out.ld, _stream()))
+
+
+def yolo_decode(cls, box, hw, nc, B, conf, pad_l, pad_t, scale, cap, cand_box, cand_score, cand_cls, cand_count,
+                dense_ltrb=None, dense_score=None):
+    cp = (C.c_void_p * 3)(*[t.data_ptr() for t in cls])
+    bp = (C.c_void_p * 3)(*[t.data_ptr() for t in box])
+    Hs = (C.c_int * 3)(*[h for h, _ in hw])
+    Ws = (C.c_int * 3)(*[w for _, w in hw])
+    _lib.check(_lib.lib().b2p_yolo_decode(cp, bp, Hs, Ws, nc, B, conf, _p(pad_l), _p(pad_t), _p(scale), cap,
+                                          _p(cand_box), _p(cand_score), _p(cand_cls), _p(cand_count),
+                                          _p(dense_ltrb), _p(dense_score), _stream()))
+
+
+def batched_nms(box, score, cls, count, B, cap, iou, max_det, img_w, img_h, keep_idx, out_box, out_score, out_count):
+    _lib.check(_lib.lib().b2p_batched_nms(_p(box), _p(score), _p(cls), _p(count), B, cap, float(iou), max_det,
+                                          _p(img_w), _p(img_h), _p(keep_idx), _p(out_box), _p(out_score),
+                                          _p(out_count), _stream()))
+
+
+def letterbox(src_u8, B, H, W, Wr, Hr, Tw, Th, pad_l, pad_t, tmp, canvas):
+    _lib.check(_lib.lib().b2p_letterbox(_p(src_u8), B, H, W, Wr, Hr, Tw, Th, pad_l, pad_t, _p(tmp), _p(canvas),
+                                        _stream()))
+
+
+def im2col_u8(img, B, H, W, k, s, p, Kpad, lut, out):
+    _lib.check(_lib.lib().b2p_im2col_u8(_p(img), B, H, W, k, s, p, Kpad, _p(lut), _p(out), _stream()))
+
+
+def crop_resize(imgs, img_hw, img_off, boxes, box_img, n_box, out_hw, out, status):
+    _lib.check(_lib.lib().b2p_crop_resize(_p(imgs), _p(img_hw), _p(img_off), _p(boxes), _p(box_img), n_box, out_hw,
+                                          _p(out), _p(status), _stream()))
