@@ -301,7 +301,7 @@ int b2p_batched_nms(const float* box, const float* score, const int* cls, const 
   if (cap > 16384) return set_error("batched_nms: candidate capacity > 16384 unsupported");
   NmsArgs a{};
   a.box = box; a.score = score; a.cls = cls; a.count = count; a.cap = cap; a.max_det = max_det;
-  int P = 1;
+  int P = 2;   // >= 2 keeps the float4 arrays carved after keys[] 16-byte aligned
   while (P < cap) P <<= 1;
   a.sort_cap = P;
   // torchvision compares (double)ovr > iou_threshold; for a float ovr that equals ovr > T with T the

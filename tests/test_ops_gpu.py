@@ -1,0 +1,235 @@
+"""GPU parity tests of the individual kernels, called through the C-ABI (ctypes) on cuda:0.
+
+Dense contractions are compared with a plain PyTorch fp32 reference on the same fp16-rounded operands
+(tolerance: fp32 accumulation order only); byte/index kernels are compared bit-exactly with the oracle
+(Pillow / OpenCV / torchvision / oracle.ref_restate)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from omniparser_b200 import ops  # noqa: E402
+from oracle import ref_restate as R  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def _act(x, act):
+    if act == ops.ACT_SILU:
+        return F.silu(x)
+    if act == ops.ACT_GELU:
+        return F.gelu(x)
+    return x
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 64, 128), (256, 256, 256), (300, 200, 192), (37, 24, 32),
+                                   (1000, 320, 160), (129, 1, 256), (4096, 768, 768), (60, 3072, 768),
+                                   (480, 1000, 3072), (25600, 128, 32), (13, 51289, 768)])
+@pytest.mark.parametrize("cfg", [dict(), dict(bias=True, act=ops.ACT_SILU), dict(bias=True, act=ops.ACT_GELU, res=True),
+                                 dict(bias=True, res=True, out_f32=True)])
+def test_gemm(M, N, K, cfg):
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    a = (torch.randn(M, K, generator=g) * 0.5).half().to(DEV)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).half().to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV) if cfg.get("bias") else None
+    odt = torch.float32 if cfg.get("out_f32") else torch.float16
+    res = torch.randn(M, N, generator=g).to(DEV).to(odt) if cfg.get("res") else None
+    out = ops.linear(a, w, bias, res, cfg.get("act", 0), odt)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t()
+    if bias is not None:
+        ref = ref + bias
+    ref = _act(ref, cfg.get("act", 0))
+    if res is not None:
+        ref = ref + res.float()
+    tol = 2e-3 if odt == torch.float32 else 1e-2
+    err = (out.float() - ref).abs().max().item()
+    assert err < tol * max(1.0, ref.abs().max().item()), f"max abs err {err}"
+
+
+def test_gemm_strided_views():
+    """A is a column slice of a wider buffer, out/res are channel slices (concat elimination)."""
+    g = torch.Generator(device="cpu").manual_seed(5)
+    big = (torch.randn(500, 384, generator=g) * 0.5).half().to(DEV)
+    a = big[:, 128:256]
+    w = (torch.randn(96, 128, generator=g) / 11).half().to(DEV)
+    outbuf = torch.zeros(500, 256, device=DEV, dtype=torch.float16)
+    resbuf = torch.randn(500, 160, generator=g).half().to(DEV)
+    ops.linear(a, w, None, resbuf[:, 32:128], ops.ACT_SILU, out=outbuf[:, 64:160])
+    torch.cuda.synchronize()
+    ref = F.silu(a.float() @ w.float().t()) + resbuf[:, 32:128].float()
+    assert (outbuf[:, 64:160].float() - ref).abs().max().item() < 1e-2
+    assert outbuf[:, :64].abs().max().item() == 0 and outbuf[:, 160:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,stride", [(1, 20, 20, 64, 128, 1), (2, 20, 20, 512, 256, 1),
+                                                    (1, 80, 80, 32, 32, 1), (1, 40, 40, 128, 64, 1),
+                                                    (3, 34, 60, 64, 64, 1), (1, 160, 160, 64, 64, 1),
+                                                    (1, 40, 40, 256, 64, 2), (2, 80, 80, 128, 128, 2),
+                                                    (1, 320, 320, 64, 128, 2), (1, 22, 38, 32, 48, 2)])
+def test_conv3x3(B, H, W, Cin, Cout, stride):
+    g = torch.Generator(device="cpu").manual_seed(B + H + Cin + Cout + stride)
+    ld = Cin + 64
+    buf = (torch.randn(B, H, W, ld, generator=g) * 0.5).half().to(DEV)
+    x = ops.Map(buf, 32, Cin)
+    wt = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).half()
+    wpk = wt.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous().to(DEV)
+    bias = torch.randn(Cout, generator=g).to(DEV)
+    Ho, Wo = H // stride, W // stride
+    out = ops.new_map(B, Ho, Wo, Cout + 32, DEV)
+    out.buf.zero_()
+    o = out.slice(16, Cout)
+    res = None
+    if stride == 1 and Cin == Cout:
+        res = x
+    ops.conv3x3(x, wpk, o, stride=stride, bias=bias, res=res, act=ops.ACT_SILU)
+    torch.cuda.synchronize()
+    xin = buf[..., 32:32 + Cin].permute(0, 3, 1, 2).float()
+    ref = F.silu(F.conv2d(xin, wt.float().to(DEV), bias, stride=stride, padding=1))
+    if res is not None:
+        ref = ref + xin
+    err = (o.torch() - ref).abs().max().item()
+    assert err < 1e-2 * max(1.0, ref.abs().max().item()), f"max abs err {err}"
+    assert out.buf[..., :16].abs().max().item() == 0 and out.buf[..., 16 + Cout:].abs().max().item() == 0
+
+
+def test_detect_elementwise_ops():
+    g = torch.Generator(device="cpu").manual_seed(11)
+    B, H, W, C = 2, 40, 40, 256
+    x = ops.Map(torch.randn(B, H, W, C + 32, generator=g).half().to(DEV), 16, C)
+    xin = x.torch()
+    # ADown pooling
+    x1 = ops.new_map(B, H, W, C // 2, DEV)
+    x2 = ops.new_map(B, H // 2, W // 2, C // 2, DEV)
+    ops.adown_pool(x, x1, x2)
+    a = F.avg_pool2d(xin, 2, 1, 0, False, True)
+    r1 = F.pad(a[:, :C // 2], (0, 1, 0, 1))
+    r2 = F.max_pool2d(a[:, C // 2:], 3, 2, 1)
+    assert (x1.torch() - r1).abs().max().item() < 2e-3
+    assert (x2.torch() - r2).abs().max().item() < 2e-3
+    # maxpool 5
+    y = ops.new_map(B, H, W, C, DEV)
+    ops.maxpool_s1(x, y, 5)
+    assert torch.equal(y.torch(), F.max_pool2d(xin, 5, 1, 2))
+    # upsample
+    u = ops.new_map(B, 2 * H, 2 * W, C + 8, DEV)
+    ops.upsample2x(x, u.slice(8, C))
+    assert torch.equal(u.slice(8, C).torch(), F.interpolate(xin, scale_factor=2.0, mode="nearest"))
+    # cbfuse: two coarser sources + last
+    s1 = ops.Map(torch.randn(B, H // 2, W // 2, 3 * C, generator=g).half().to(DEV), C, C)
+    s2 = ops.Map(torch.randn(B, H // 4, W // 4, 2 * C, generator=g).half().to(DEV), 0, C)
+    out = ops.new_map(B, H, W, C, DEV)
+    ops.cbfuse([s1, s2], x, out)
+    ref = F.interpolate(s1.torch(), size=(H, W), mode="nearest") + F.interpolate(s2.torch(), size=(H, W), mode="nearest") + xin
+    assert (out.torch() - ref).abs().max().item() < 4e-3
+    torch.cuda.synchronize()
+
+
+def _nms_gpu(boxes, scores, cls, iou, max_det=300, W=1920.0, H=1080.0):
+    n = len(boxes)
+    cap = max(n, 1)
+    d = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(DEV)
+    b, s, c = d(boxes.reshape(-1, 4), torch.float32), d(scores, torch.float32), d(cls, torch.int32)
+    cnt = torch.tensor([n], dtype=torch.int32, device=DEV)
+    keep = torch.full((max_det,), -1, dtype=torch.int32, device=DEV)
+    ob = torch.zeros(max_det, 4, device=DEV)
+    os_ = torch.zeros(max_det, device=DEV)
+    oc = torch.zeros(1, dtype=torch.int32, device=DEV)
+    iw, ih = torch.tensor([W], device=DEV), torch.tensor([H], device=DEV)
+    ops.batched_nms(b, s, c, cnt, 1, cap, iou, max_det, iw, ih, keep, ob, os_, oc)
+    torch.cuda.synchronize()
+    k = int(oc.item())
+    return keep[:k].cpu().numpy().astype(np.int64), ob[:k].cpu(), os_[:k].cpu()
+
+
+@pytest.mark.parametrize("n,nc", [(0, 1), (1, 1), (7, 1), (300, 1), (513, 1), (999, 3), (1000, 3), (1001, 3), (2500, 1), (8400, 1)])
+def test_nms_bit_exact(n, nc):
+    from torchvision.ops import batched_nms
+    rng = np.random.default_rng(n + nc)
+    xy = rng.uniform(0, 1800, size=(n, 2)).astype(np.float32)
+    wh = rng.uniform(0, 200, size=(n, 2)).astype(np.float32)
+    boxes = np.concatenate([xy, xy + wh], 1)
+    scores = rng.uniform(0.05, 1, size=n).astype(np.float32)
+    if 4 < n <= 1000:
+        scores[rng.integers(0, n, size=n // 3)] = np.float32(0.5)
+        boxes[1] = boxes[0]
+        boxes[3, 2:] = boxes[3, :2]
+    cls = rng.integers(0, nc, size=n).astype(np.int64)
+    for iou in (0.1, 0.7):
+        tb, ts, tc = torch.from_numpy(boxes), torch.from_numpy(scores), torch.from_numpy(cls)
+        ref = batched_nms(tb, ts, tc, iou)[:300]
+        got, ob, os_ = _nms_gpu(boxes, scores, cls, iou)
+        assert np.array_equal(ref.numpy(), got), (n, nc, iou)
+        rb = tb[ref].clone()
+        rb[:, [0, 2]] = rb[:, [0, 2]].clamp(0, 1920)
+        rb[:, [1, 3]] = rb[:, [1, 3]].clamp(0, 1080)
+        assert torch.equal(rb, ob) and torch.equal(ts[ref], os_)
+
+
+@pytest.mark.parametrize("size,imgsz", [((1920, 1080), 640), ((1919, 1079), 640), ((3240, 2160), 640),
+                                        ((300, 200), 640), ((1920, 1080), (1080, 1920))])
+def test_letterbox_bit_exact(size, imgsz):
+    rng = np.random.default_rng(3)
+    B = 2
+    imgs = rng.integers(0, 256, size=(B, size[1], size[0], 3), dtype=np.uint8)
+    tw, th, scale, rw, rh, pl, pt = R.letterbox_geometry(size[0], size[1], imgsz)
+    src = torch.from_numpy(imgs).to(DEV)
+    tmp = torch.empty(B, size[1], rw, 3, dtype=torch.uint8, device=DEV)
+    canvas = torch.empty(B, th, tw, 3, dtype=torch.uint8, device=DEV)
+    ops.letterbox(src, B, size[1], size[0], rw, rh, tw, th, pl, pt, tmp, canvas)
+    torch.cuda.synchronize()
+    for b in range(B):
+        ref, *_ = R.letterbox_pil(imgs[b], imgsz)
+        assert np.array_equal(ref, canvas[b].cpu().numpy())
+
+
+def test_crop_resize_bit_exact():
+    import cv2
+    rng = np.random.default_rng(4)
+    H, W = 1080, 1920
+    imgs = rng.integers(0, 256, size=(2, H, W, 3), dtype=np.uint8)
+    n = 200
+    x0 = rng.uniform(0, 0.9, size=n); y0 = rng.uniform(0, 0.9, size=n)
+    bw = rng.uniform(0.001, 0.1, size=n); bh = rng.uniform(0.002, 0.15, size=n)
+    boxes = np.stack([x0, y0, np.minimum(x0 + bw, 1.0), np.minimum(y0 + bh, 1.0)], 1).astype(np.float32)
+    boxes[0] = (np.float32(100 / W), np.float32(100 / H), np.float32(228.5 / W), np.float32(228.5 / H))   # 128x128 -> area path
+    boxes[1] = (np.float32(10 / W), np.float32(10 / H), np.float32(74.5 / W), np.float32(74.5 / H))      # 64x64 identity
+    boxes[2] = (0.5, 0.5, 0.5, 0.6)   # empty crop
+    bimg = rng.integers(0, 2, size=n).astype(np.int32)
+    d_img = torch.from_numpy(imgs).to(DEV)
+    hw = torch.tensor([[H, W], [H, W]], dtype=torch.int32, device=DEV)
+    off = torch.tensor([0, H * W * 3], dtype=torch.int64, device=DEV)
+    out = torch.empty(n, 64, 64, 3, dtype=torch.uint8, device=DEV)
+    status = torch.empty(n, dtype=torch.int32, device=DEV)
+    ops.crop_resize(d_img, hw, off, torch.from_numpy(boxes).to(DEV), torch.from_numpy(bimg).to(DEV), n, 64, out, status)
+    torch.cuda.synchronize()
+    tb = torch.from_numpy(boxes)
+    ints = R.crop_boxes_int(tb, W, H)
+    st = status.cpu().numpy()
+    for i, (xa, ya, xb, yb) in enumerate(ints):
+        crop = imgs[bimg[i]][ya:yb, xa:xb, :]
+        if crop.shape[0] == 0 or crop.shape[1] == 0:
+            assert st[i] == 1
+            continue
+        assert st[i] == 0
+        assert np.array_equal(cv2.resize(crop, (64, 64)), out[i].cpu().numpy()), (i, crop.shape)
+
+
+def test_im2col_stem():
+    rng = np.random.default_rng(6)
+    B, H, W = 2, 64, 96
+    img = rng.integers(0, 256, size=(B, H, W, 3), dtype=np.uint8)
+    lut = (np.arange(256, dtype=np.float32) / np.float32(255.0))[None].repeat(3, 0).copy()
+    for (k, s, p, Kpad) in [(3, 2, 1, 32), (7, 4, 3, 160)]:
+        Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+        out = torch.empty(B * Ho * Wo, Kpad, dtype=torch.float16, device=DEV)
+        ops.im2col_u8(torch.from_numpy(img).to(DEV), B, H, W, k, s, p, Kpad, torch.from_numpy(lut).to(DEV), out)
+        torch.cuda.synchronize()
+        x = torch.from_numpy(img.astype(np.float32) / np.float32(255.0)).permute(0, 3, 1, 2)
+        cols = F.unfold(x, k, padding=p, stride=s)   # [B, 3*k*k, L] ordered (c, ky, kx)
+        cols = cols.view(B, 3, k * k, Ho * Wo).permute(0, 3, 2, 1).reshape(B * Ho * Wo, k * k * 3)
+        got = out.cpu().float()
+        assert torch.equal(got[:, :k * k * 3], cols.half().float())
+        assert got[:, k * k * 3:].abs().max().item() == 0
