@@ -32,6 +32,7 @@ struct ConvGemm {
   long long ldr;
   int act;             // 0 none, 1 SiLU, 2 GELU(erf)
   int bn_max;          // 0 = auto
+  int split_out;       // fp16 output written as [hi | hi | lo] (row stride ldc >= 3N): operand of a fp16x3 GEMM
 };
 
 int gemm_launch(const ConvGemm& d, cudaStream_t st);

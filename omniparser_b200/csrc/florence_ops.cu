@@ -1,2 +1,493 @@
-// placeholder translation unit (Florence-2 kernels land here)
+// Non-GEMM kernels of the Florence-2 caption path (ref:util/utils.py:125 -> HF generate): LayerNorm, DaViT
+// depthwise conv / window attention / channel attention, BART multi-head attention with KV cache, embedding +
+// position + LayerNorm, image-token projector prep, and the greedy token pick with HF logits processors.
+// All are HBM/latency-bound SIMT kernels in fp32; the dense contractions run in gemm_tcgen05.cu.
+// Residual streams are fp32, GEMM operands fp16.
 #include "b2p_internal.h"
+#include <cuda_fp16.h>
+#include <math.h>
+
+namespace b2p {
+
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// fp16 activation store.  split == 0: plain.  split == K > 0: "fp16x3" operand layout [hi | hi | lo] (row stride 3K)
+// so that a K-concatenated GEMM against [W_hi | W_lo | W_hi] accumulates hi*hi + hi*lo + lo*hi in fp32
+// (2^-22-class products instead of 2^-11): the parity-grade precision mode of the caption path.
+__device__ __forceinline__ void store_act(__half* row, int c, int split, float v) {
+  const __half h = __float2half_rn(v);
+  row[c] = h;
+  if (split) {
+    row[split + c] = h;
+    row[2 * split + c] = __float2half_rn(v - __half2float(h));
+  }
+}
+
+// ---------------------------------------------------------------------------------------- LayerNorm
+// one warp per row; x fp32 [T][ldx]; writes fp16 and/or fp32 (nn.LayerNorm, biased variance, eps inside sqrt)
+__global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ g,
+                                 const float* __restrict__ b, float eps, int T, int C, __half* __restrict__ o16,
+                                 long long ld16, float* __restrict__ o32, long long ld32, int split) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= T) return;
+  const float* xr = x + (long long)row * ldx;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += xr[c];
+  const float mean = warp_sum(s) / float(C);
+  float v = 0.f;
+  for (int c = lane; c < C; c += 32) { const float d = xr[c] - mean; v += d * d; }
+  const float rstd = rsqrtf(warp_sum(v) / float(C) + eps);
+  for (int c = lane; c < C; c += 32) {
+    const float y = (xr[c] - mean) * rstd * g[c] + b[c];
+    if (o16) store_act(o16 + (long long)row * ld16, c, split, y);
+    if (o32) o32[(long long)row * ld32 + c] = y;
+  }
+}
+
+// ---------------------------------------------------------------------------------------- depthwise 3x3 + residual
+// y = dwconv3x3(x) + bias + x   (hf:models/florence2/modeling_florence2.py:281,293 and :431,443)
+__global__ void dwconv3x3_res_kernel(const float* __restrict__ x, int B, int H, int W, int C,
+                                     const float* __restrict__ w /*[9][C]*/, const float* __restrict__ bias,
+                                     float* __restrict__ y) {
+  const long long n = (long long)B * H * W * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % C);
+    long long p = i / C;
+    const int xx = int(p % W); p /= W;
+    const int yy = int(p % H);
+    const int b = int(p / H);
+    float acc = bias[c];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int sy = yy + ky - 1;
+      if (sy < 0 || sy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int sx = xx + kx - 1;
+        if (sx < 0 || sx >= W) continue;
+        acc += x[(((long long)b * H + sy) * W + sx) * C + c] * w[(ky * 3 + kx) * C + c];
+      }
+    }
+    y[i] = acc + x[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------- window attention
+// qkv fp16 [B*H*W][3C] for REAL tokens only.  The reference zero-pads the normed map to a multiple of the 12x12
+// window; padded tokens have qkv = bias and take part as keys/values unmasked
+// (hf:models/florence2/modeling_florence2.py:346-350,377-383).  Exact shortcut: one "pad key" (k = bias_k,
+// v = bias_v) with multiplicity n_pad = 144 - n_real.  One CTA per (batch, window, head); one thread per query.
+template <int D>
+__global__ void window_attn_kernel(const float* __restrict__ qkv, const float* __restrict__ qkv_bias, int B, int H,
+                                   int W, int C, int heads, int win, __half* __restrict__ out, int split) {
+  extern __shared__ float sm[];
+  const int nwx = (W + win - 1) / win, nwy = (H + win - 1) / win;
+  int bid = blockIdx.x;
+  const int head = bid % heads; bid /= heads;
+  const int wx = bid % nwx; bid /= nwx;
+  const int wy = bid % nwy;
+  const int b = bid / nwy;
+  const int y0 = wy * win, x0 = wx * win;
+  const int ny = min(win, H - y0), nx = min(win, W - x0);
+  const int nreal = ny * nx, npad = win * win - nreal;
+  float* Ks = sm;                       // [nreal][D]
+  float* Vs = sm + win * win * D;       // [nreal][D]
+  for (int i = threadIdx.x; i < nreal * D; i += blockDim.x) {
+    const int t = i / D, d = i - t * D;
+    const long long tok = ((long long)b * H + y0 + t / nx) * W + x0 + t % nx;
+    Ks[i] = qkv[tok * 3 * C + C + head * D + d];
+    Vs[i] = qkv[tok * 3 * C + 2 * C + head * D + d];
+  }
+  __syncthreads();
+  const float scale = rsqrtf(float(D));
+  for (int t = threadIdx.x; t < nreal; t += blockDim.x) {
+    const long long tok = ((long long)b * H + y0 + t / nx) * W + x0 + t % nx;
+    float q[D], acc[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) { q[d] = qkv[tok * 3 * C + head * D + d] * scale; acc[d] = 0.f; }
+    float m = -INFINITY, l = 0.f;
+    if (npad > 0) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) s += q[d] * qkv_bias[C + head * D + d];
+      m = s;
+      l = float(npad);
+#pragma unroll
+      for (int d = 0; d < D; ++d) acc[d] = float(npad) * qkv_bias[2 * C + head * D + d];
+    }
+    for (int j = 0; j < nreal; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) s += q[d] * Ks[j * D + d];
+      if (s > m) {
+        const float r = __expf(m - s);
+        l *= r;
+#pragma unroll
+        for (int d = 0; d < D; ++d) acc[d] *= r;
+        m = s;
+      }
+      const float p = __expf(s - m);
+      l += p;
+#pragma unroll
+      for (int d = 0; d < D; ++d) acc[d] += p * Vs[j * D + d];
+    }
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int d = 0; d < D; ++d) store_act(out + tok * (split ? 3 * C : C), head * D + d, split, acc[d] * inv);
+  }
+}
+
+// ---------------------------------------------------------------------------------------- channel attention
+// hf:models/florence2/modeling_florence2.py:228-264: per (batch, group) a d x d (d = 32) attention over channels:
+// S[i][j] = N^-0.5 * sum_n q[n][i] k[n][j]; P = softmax_j(S); out[n][i] = sum_j P[i][j] v[n][j].
+// One CTA (1024 threads = 32 x 32) per (batch, group); tokens streamed through shared memory in chunks.
+__global__ void __launch_bounds__(1024) channel_attn_kernel(const float* __restrict__ qkv, int N, int C, int groups,
+                                                            __half* __restrict__ out, int split) {
+  constexpr int D = 32, CH = 64;
+  __shared__ float qs[CH][D + 1], ks[CH][D + 1];
+  __shared__ float P[D][D + 1];
+  const int g = blockIdx.x % groups, b = blockIdx.x / groups;
+  const int i = threadIdx.x >> 5, j = threadIdx.x & 31;
+  const float* base = qkv + (long long)b * N * 3 * C;
+  float s = 0.f;
+  for (int n0 = 0; n0 < N; n0 += CH) {
+    const int cn = min(CH, N - n0);
+    for (int t = threadIdx.x; t < cn * D; t += blockDim.x) {
+      const int n = t / D, d = t - n * D;
+      qs[n][d] = base[(long long)(n0 + n) * 3 * C + g * D + d];
+      ks[n][d] = base[(long long)(n0 + n) * 3 * C + C + g * D + d];
+    }
+    __syncthreads();
+    for (int n = 0; n < cn; ++n) s += qs[n][i] * ks[n][j];
+    __syncthreads();
+  }
+  s *= rsqrtf(float(N));
+  const float m = warp_max(s);
+  const float e = __expf(s - m);
+  const float l = warp_sum(e);
+  P[i][j] = e / l;
+  __syncthreads();
+  // out[n][i]: thread (n_local = i, channel = j) over token chunks of 32
+  for (int n0 = 0; n0 < N; n0 += 32) {
+    const int n = n0 + i;
+    if (n < N) {
+      const float* vr = base + (long long)n * 3 * C + 2 * C + g * D;
+      float acc = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < D; ++jj) acc += P[j][jj] * vr[jj];
+      store_act(out + ((long long)b * N + n) * (split ? 3 * C : C), g * D + j, split, acc);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------- BART attention
+// One warp per (batch, head, query).  d_head = 64 (2 values per lane), scale applied to q (hf:models/bart/
+// modeling_bart.py:143-258).  K/V row b*Lk + j at k + (b*Lk + j)*ldk + h*64.  Decoder self-attention: the current
+// step's k, v (columns of the fused qkv GEMM output) are appended to the cache at position *step, and the
+// attention covers cache[0..*step].
+struct MhaArgs {
+  const float* q; long long ldq;
+  const float* k; const float* v; long long ldk;     // encoder / cross: [B*Lk][ldk]
+  float* kcache; float* vcache; int tmax;             // decoder self: cache [B][tmax][heads*64]
+  const float* knew; const float* vnew; long long ldnew;
+  const int* step;
+  int B, Lq, Lk, heads;
+  __half* out; long long ldo; int split;
+};
+
+__global__ void mha_kernel(MhaArgs a) {
+  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int total = a.B * a.heads * a.Lq;
+  if (wid >= total) return;
+  const int qi = wid % a.Lq;
+  const int h = (wid / a.Lq) % a.heads;
+  const int b = wid / (a.Lq * a.heads);
+  const int HD = a.heads * 64;
+  float2 q = *reinterpret_cast<const float2*>(a.q + ((long long)b * a.Lq + qi) * a.ldq + h * 64 + 2 * lane);
+  q.x *= 0.125f; q.y *= 0.125f;
+  int Lk = a.Lk;
+  const float *kb, *vb;
+  long long ldk;
+  if (a.kcache) {
+    const int t = *a.step;
+    // append this step's k, v
+    const float2 kn = *reinterpret_cast<const float2*>(a.knew + (long long)b * a.ldnew + h * 64 + 2 * lane);
+    const float2 vn = *reinterpret_cast<const float2*>(a.vnew + (long long)b * a.ldnew + h * 64 + 2 * lane);
+    *reinterpret_cast<float2*>(a.kcache + ((long long)b * a.tmax + t) * HD + h * 64 + 2 * lane) = kn;
+    *reinterpret_cast<float2*>(a.vcache + ((long long)b * a.tmax + t) * HD + h * 64 + 2 * lane) = vn;
+    __syncwarp();
+    Lk = t + 1;
+    kb = a.kcache + (long long)b * a.tmax * HD + h * 64;
+    vb = a.vcache + (long long)b * a.tmax * HD + h * 64;
+    ldk = HD;
+  } else {
+    kb = a.k + (long long)b * a.Lk * a.ldk + h * 64;
+    vb = a.v + (long long)b * a.Lk * a.ldk + h * 64;
+    ldk = a.ldk;
+  }
+  float m = -INFINITY, l = 0.f;
+  float2 acc = make_float2(0.f, 0.f);
+  for (int j = 0; j < Lk; ++j) {
+    const float2 kf = *reinterpret_cast<const float2*>(kb + j * ldk + 2 * lane);
+    const float s = warp_sum(q.x * kf.x + q.y * kf.y);
+    const float mn = fmaxf(m, s);
+    const float r = __expf(m - mn), p = __expf(s - mn);
+    const float2 vf = *reinterpret_cast<const float2*>(vb + j * ldk + 2 * lane);
+    l = l * r + p;
+    acc.x = acc.x * r + p * vf.x;
+    acc.y = acc.y * r + p * vf.y;
+    m = mn;
+  }
+  const float inv = 1.f / l;
+  __half* orow = a.out + ((long long)b * a.Lq + qi) * a.ldo;
+  store_act(orow, h * 64 + 2 * lane, a.split, acc.x * inv);
+  store_act(orow, h * 64 + 2 * lane + 1, a.split, acc.y * inv);
+}
+
+// ---------------------------------------------------------------------------------------- embeddings
+// Encoder input: row (b, i) = (i < n_img ? image_feat[b][i] : E[prompt[i - n_img]]) + P[i + 2]
+// (hf:models/florence2/modeling_florence2.py:742-761; learned positions with offset 2, hf:models/bart/
+// modeling_bart.py:74-98).  Decoder input: row b = E[token[b]] + P[*step + 2].  Output fp32 (LayerNorm follows).
+__global__ void encoder_embed_kernel(const float* __restrict__ img, int n_img, const float* __restrict__ E,
+                                     const int* __restrict__ prompt, int n_prompt, const float* __restrict__ P, int B,
+                                     int C, float* __restrict__ out) {
+  const int L = n_img + n_prompt;
+  const long long n = (long long)B * L * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % C);
+    const int t = int((i / C) % L);
+    const int b = int(i / ((long long)C * L));
+    const float e = (t < n_img) ? img[((long long)b * n_img + t) * C + c] : E[(long long)prompt[t - n_img] * C + c];
+    out[i] = e + P[(long long)(t + 2) * C + c];
+  }
+}
+
+__global__ void decoder_embed_kernel(const float* __restrict__ E, const int* __restrict__ seq, int seq_ld,
+                                     const int* __restrict__ step, const float* __restrict__ P, int B, int C,
+                                     float* __restrict__ out) {
+  const int t = *step;
+  const long long n = (long long)B * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % C);
+    const int b = int(i / C);
+    out[i] = E[(long long)seq[b * seq_ld + t] * C + c] + P[(long long)(t + 2) * C + c];
+  }
+}
+
+// Projector prep (hf:models/florence2/modeling_florence2.py:573-595): tokens = x + pos2d + temporal(0);
+// rows: [mean over HW] ++ [HW tokens]; fp16 out [B][1+HW][C] feeding the 1024->768 projection GEMM.
+__global__ void projector_prep_kernel(const float* __restrict__ x /*[B][HW][C]*/, const float* __restrict__ pos /*[HW][C]*/,
+                                      int B, int HW, int C, __half* __restrict__ out, int split) {
+  const long long n = (long long)B * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % C);
+    const int b = int(i / C);
+    float s = 0.f;
+    for (int t = 0; t < HW; ++t) {
+      const float v = x[((long long)b * HW + t) * C + c] + pos[(long long)t * C + c];
+      s += v;
+      store_act(out + ((long long)b * (HW + 1) + 1 + t) * (split ? 3 * C : C), c, split, v);
+    }
+    store_act(out + (long long)b * (HW + 1) * (split ? 3 * C : C), c, split, s / float(HW));
+  }
+}
+
+// ---------------------------------------------------------------------------------------- greedy pick
+// HF greedy step (hf:generation/utils.py:2727-2805) with the processors Florence-2 configures, in HF order:
+// no_repeat_ngram (hf:generation/logits_process.py:1012-1079), forced BOS (:1552), forced EOS (:1597); then
+// argmax (first maximum), pad for finished rows, EOS bookkeeping.  seq[b][0] = decoder_start; this kernel writes
+// seq[b][*step + 1].  One CTA per row.
+struct PickArgs {
+  const float* logits; long long ld; int V;
+  int* seq; int seq_ld;
+  int* finished;        // [B]
+  const int* step;      // current decoder length - 1
+  int ngram, forced_bos, forced_eos, eos, pad, max_len;   // max_len = total sequence length incl. start token
+  float* dump;          // optional [B][V] processed scores of this step (parity checks)
+  int* n_unfinished;    // device counter, decremented when a row finishes
+};
+
+__global__ void __launch_bounds__(1024) greedy_pick_kernel(PickArgs a) {
+  const int b = blockIdx.x;
+  const int t = *a.step;            // tokens so far = t + 1
+  const int cur_len = t + 1;
+  const float* lg = a.logits + (long long)b * a.ld;
+  int* seq = a.seq + (long long)b * a.seq_ld;
+  __shared__ float bv[32];
+  __shared__ int bi[32];
+  __shared__ int banned[64];
+  __shared__ int nbanned;
+  if (threadIdx.x == 0) {
+    int nb = 0;
+    if (a.ngram > 0 && cur_len + 1 >= a.ngram) {
+      // ban every token that would complete an n-gram already present in seq[0..cur_len)
+      const int pre = a.ngram - 1;
+      for (int s = 0; s + a.ngram <= cur_len; ++s) {
+        bool eq = true;
+        for (int k = 0; k < pre; ++k) eq = eq && (seq[s + k] == seq[cur_len - pre + k]);
+        if (eq && nb < 64) banned[nb++] = seq[s + pre];
+      }
+    }
+    nbanned = nb;
+  }
+  __syncthreads();
+  int force = -1;
+  if (cur_len == 1 && a.forced_bos >= 0) force = a.forced_bos;
+  if (cur_len == a.max_len - 1 && a.forced_eos >= 0) force = a.forced_eos;
+  float best = -INFINITY;
+  int besti = 0x7fffffff;
+  for (int v = threadIdx.x; v < a.V; v += blockDim.x) {
+    float s = lg[v];
+    for (int k = 0; k < nbanned; ++k) if (banned[k] == v) s = -INFINITY;
+    if (force >= 0) s = (v == force) ? 0.f : -INFINITY;
+    if (a.dump) a.dump[(long long)b * a.V + v] = s;
+    if (s > best || (s == best && v < besti)) { best = s; besti = v; }
+  }
+  for (int o = 16; o; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { bv[threadIdx.x >> 5] = best; bi[threadIdx.x >> 5] = besti; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+      if (bv[w] > best || (bv[w] == best && bi[w] < besti)) { best = bv[w]; besti = bi[w]; }
+    int tok = besti;
+    if (a.finished[b]) tok = a.pad;
+    seq[cur_len] = tok;
+    if (!a.finished[b] && tok == a.eos) {
+      a.finished[b] = 1;
+      if (a.n_unfinished) atomicSub(a.n_unfinished, 1);
+    }
+  }
+}
+
+__global__ void step_advance_kernel(int* step) { *step += 1; }
+
+static inline int grid_for(long long n, int threads) {
+  long long b = (n + threads - 1) / threads;
+  const long long cap = 148LL * 16;
+  return int(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace b2p
+
+using namespace b2p;
+
+extern "C" {
+
+int b2p_layernorm(const float* x, long long ldx, const float* gamma, const float* beta, float eps, int T, int C,
+                  void* out16, long long ld16, float* out32, long long ld32, int split, cudaStream_t st) {
+  if (T <= 0) return 0;
+  const int wpb = 8;
+  layernorm_kernel<<<(T + wpb - 1) / wpb, wpb * 32, 0, st>>>(x, ldx, gamma, beta, eps, T, C, (__half*)out16, ld16, out32, ld32, split ? C : 0);
+  B2P_CHECK_LAUNCH();
+  return 0;
+}
+
+int b2p_dwconv3x3_res(const float* x, int B, int H, int W, int C, const float* w9c, const float* bias, float* y,
+                      cudaStream_t st) {
+  dwconv3x3_res_kernel<<<grid_for((long long)B * H * W * C, 256), 256, 0, st>>>(x, B, H, W, C, w9c, bias, y);
+  B2P_CHECK_LAUNCH();
+  return 0;
+}
+
+int b2p_window_attn(const float* qkv, const float* qkv_bias, int B, int H, int W, int C, int heads, int win, void* out,
+                    int split, cudaStream_t st) {
+  if (C / heads != 32) return set_error("window_attn: head_dim must be 32");
+  const int nw = ((W + win - 1) / win) * ((H + win - 1) / win);
+  const size_t smem = size_t(2) * win * win * 32 * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(window_attn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr = true;
+  }
+  if (smem > 64 * 1024) return set_error("window_attn: window too large");
+  window_attn_kernel<32><<<B * nw * heads, 160, smem, st>>>(qkv, qkv_bias, B, H, W, C, heads, win, (__half*)out, split ? C : 0);
+  B2P_CHECK_LAUNCH();
+  return 0;
+}
+
+int b2p_channel_attn(const float* qkv, int B, int N, int C, int groups, void* out, int split, cudaStream_t st) {
+  if (C / groups != 32) return set_error("channel_attn: channels per group must be 32");
+  channel_attn_kernel<<<B * groups, 1024, 0, st>>>(qkv, N, C, groups, (__half*)out, split ? C : 0);
+  B2P_CHECK_LAUNCH();
+  return 0;
+}
+
+// Encoder self-attention / decoder cross-attention: explicit K, V.
+int b2p_mha(const float* q, long long ldq, const float* k, const float* v, long long ldk, int B, int Lq, int Lk, int heads,
+            void* out, long long ldo, int split, cudaStream_t st) {
+  MhaArgs a{};
+  a.q = q; a.ldq = ldq; a.k = k; a.v = v; a.ldk = ldk;
+  a.B = B; a.Lq = Lq; a.Lk = Lk; a.heads = heads; a.out = (__half*)out; a.ldo = ldo; a.split = split ? heads * 64 : 0;
+  const int total = B * heads * Lq;
+  mha_kernel<<<(total + 7) / 8, 256, 0, st>>>(a);
+  B2P_CHECK_LAUNCH();
+  return 0;
+}
+
+// Decoder self-attention step with KV-cache append at position *step.
+int b2p_mha_cached(const float* q, long long ldq, const float* knew, const float* vnew, long long ldnew, float* kcache,
+                   float* vcache, int tmax, const int* step, int B, int heads, void* out, long long ldo, int split,
+                   cudaStream_t st) {
+  MhaArgs a{};
+  a.q = q; a.ldq = ldq; a.knew = knew; a.vnew = vnew; a.ldnew = ldnew;
+  a.kcache = kcache; a.vcache = vcache; a.tmax = tmax; a.step = step;
+  a.B = B; a.Lq = 1; a.Lk = 0; a.heads = heads; a.out = (__half*)out; a.ldo = ldo; a.split = split ? heads * 64 : 0;
+  const int total = B * heads;
+  mha_kernel<<<(total + 7) / 8, 256, 0, st>>>(a);
+  B2P_CHECK_LAUNCH();
+  return 0;
+}
+
+int b2p_encoder_embed(const float* img, int n_img, const float* E, const int* prompt, int n_prompt, const float* P,
+                      int B, int C, float* out, cudaStream_t st) {
+  encoder_embed_kernel<<<grid_for((long long)B * (n_img + n_prompt) * C, 256), 256, 0, st>>>(img, n_img, E, prompt,
+                                                                                            n_prompt, P, B, C, out);
+  B2P_CHECK_LAUNCH();
+  return 0;
+}
+
+int b2p_decoder_embed(const float* E, const int* seq, int seq_ld, const int* step, const float* P, int B, int C,
+                      float* out, cudaStream_t st) {
+  decoder_embed_kernel<<<grid_for((long long)B * C, 256), 256, 0, st>>>(E, seq, seq_ld, step, P, B, C, out);
+  B2P_CHECK_LAUNCH();
+  return 0;
+}
+
+int b2p_projector_prep(const float* x, const float* pos, int B, int HW, int C, void* out, int split, cudaStream_t st) {
+  projector_prep_kernel<<<grid_for((long long)B * C, 256), 256, 0, st>>>(x, pos, B, HW, C, (__half*)out, split ? C : 0);
+  B2P_CHECK_LAUNCH();
+  return 0;
+}
+
+int b2p_greedy_pick(const float* logits, long long ld, int V, int B, int* seq, int seq_ld, int* finished,
+                    const int* step, int ngram, int forced_bos, int forced_eos, int eos, int pad, int max_len,
+                    float* dump, int* n_unfinished, cudaStream_t st) {
+  PickArgs a{};
+  a.logits = logits; a.ld = ld; a.V = V; a.seq = seq; a.seq_ld = seq_ld; a.finished = finished; a.step = step;
+  a.ngram = ngram; a.forced_bos = forced_bos; a.forced_eos = forced_eos; a.eos = eos; a.pad = pad; a.max_len = max_len;
+  a.dump = dump; a.n_unfinished = n_unfinished;
+  greedy_pick_kernel<<<B, 1024, 0, st>>>(a);
+  B2P_CHECK_LAUNCH();
+  return 0;
+}
+
+int b2p_step_advance(int* step, cudaStream_t st) {
+  step_advance_kernel<<<1, 1, 0, st>>>(step);
+  B2P_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

@@ -7,17 +7,19 @@
 // materialised.  Replaces the cuDNN/cuBLAS library kernels behind ref:util/yolov9.py:120-121 (TorchScript
 // YOLOv9-E forward) and ref:util/utils.py:125 (Florence-2 generate).
 //
-// Roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one elected lane),
-// warp 2 also owns TMEM alloc/dealloc, warps 2..5 = epilogue (TMEM lane group = warp % 4).
+// Roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane), warp 2 also owns TMEM
+// alloc/dealloc, warps 2..9 = epilogue (TMEM lane group = warp % 4; the two warps of a group split the columns).
 // Pipelines: smem ring full/empty (TMA <-> MMA), TMEM accumulator double buffer full/empty (MMA <-> epilogue).
 #include "ptx.cuh"
 #include "b2p_internal.h"
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace b2p {
 
-static constexpr int kThreads = 192;
+static constexpr int kThreads = 320;      // 2 control warps + 8 epilogue warps
+static constexpr int kEpiWarps = 8;
 static constexpr int kTileM = 128;
 static constexpr int kASlot = 16384;    // 128 rows x 128 B
 static constexpr int kMaxStages = 8;
@@ -37,6 +39,7 @@ struct GemmArgs {
   const void* res;
   long long ldr;
   int act, vec_ok;
+  int split;   // > 0: fp16 output in the fp16x3 operand layout [hi | hi | lo] with logical width `split`
 };
 
 // Shared-memory matrix descriptor (PTX ISA "tcgen05 matrix descriptor"), K-major operand, swizzled:
@@ -56,7 +59,7 @@ __host__ inline uint32_t make_idesc(int bn, int bf16) {
 }
 
 __device__ __forceinline__ float act_fn(float x, int act) {
-  if (act == 1) return x / (1.0f + __expf(-x));                        // SiLU
+  if (act == 1) return __fdividef(x, 1.0f + __expf(-x));               // SiLU (MUFU ex2 + rcp; ~2 ulp)
   if (act == 2) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));  // exact GELU
   return x;
 }
@@ -87,7 +90,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 4);
+      mbar_init(bar_tempty + 8 * a, kEpiWarps);
     }
     mbar_fence_init();
   }
@@ -178,8 +181,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    // -------------------------------------------------------------- epilogue (4 warps, 128 TMEM lanes)
+    // -------------------------------------------------------------- epilogue (8 warps, 128 TMEM lanes x 2 column halves)
     const int grp = warp & 3;
+    const int chalf = (warp - 2) >> 2;   // which 16-column chunks this warp owns (even / odd)
     int acc = 0;
     uint32_t acc_phase = 0;
     __half* outh = reinterpret_cast<__half*>(g.out);
@@ -209,7 +213,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(grp * 32) << 16) + uint32_t(acc * 256);
-      for (int c = 0; c < g.bn; c += 16) {
+      for (int c = chalf * 16; c < g.bn; c += 32) {
         uint32_t v[16];
         tmem_ld16(t_row + c, v);
         tmem_ld_wait();
@@ -272,6 +276,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               uint4* op = reinterpret_cast<uint4*>(outh + pix * g.ldc + nb);
               op[0] = pk[0];
               op[1] = pk[1];
+              if (g.split) {
+                uint4* o2 = reinterpret_cast<uint4*>(outh + pix * g.ldc + g.split + nb);
+                o2[0] = pk[0];
+                o2[1] = pk[1];
+                uint4 lo[2];
+                __half2* lp = reinterpret_cast<__half2*>(lo);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float2 hf = __half22float2(hp[e]);
+                  lp[e] = __floats2half2_rn(x[2 * e] - hf.x, x[2 * e + 1] - hf.y);
+                }
+                uint4* o3 = reinterpret_cast<uint4*>(outh + pix * g.ldc + 2 * g.split + nb);
+                o3[0] = lo[0];
+                o3[1] = lo[1];
+              }
             }
           }
         } else {
@@ -286,7 +305,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if (valid) {
                 if (g.res) t += g.out_f32 ? resf[pix * g.ldr + n] : __half2float(resh[pix * g.ldr + n]);
                 if (g.out_f32) outf[pix * g.ldc + n] = t;
-                else outh[pix * g.ldc + n] = __float2half_rn(t);
+                else {
+                  const __half hh = __float2half_rn(t);
+                  outh[pix * g.ldc + n] = hh;
+                  if (g.split) {
+                    outh[pix * g.ldc + g.split + n] = hh;
+                    outh[pix * g.ldc + 2 * g.split + n] = __float2half_rn(t - __half2float(hh));
+                  }
+                }
               }
             }
           }
@@ -397,6 +423,8 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
   g.bk = bk;
   g.desc_hi = make_desc_hi(bk);
   g.out = d.out; g.ldc = d.ldc; g.out_f32 = d.out_f32; g.bias = d.bias; g.res = d.res; g.ldr = d.ldr; g.act = d.act;
+  g.split = (d.split_out && !d.out_f32) ? d.N : 0;
+  if (g.split && (d.N % 8)) return set_error("gemm: split (fp16x3) output needs N % 8 == 0");
 
   if (d.mode == 0) {
     g.M = d.M;
@@ -468,6 +496,11 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
   const int total = g.m_tiles * g.n_tiles;
   const int grid = total < g_num_sms ? total : g_num_sms;
   if (grid <= 0) return 0;
+  static const bool dbg = getenv("B2P_DEBUG") != nullptr;
+  if (dbg)
+    fprintf(stderr, "b2p_gemm mode=%d M=%d N=%d Ktot=%d bk=%d bn=%d tw=%d th=%d m_tiles=%d n_tiles=%d stages=%d grid=%d act=%d f32=%d res=%d\n",
+            d.mode, d.mode == 0 ? d.M : g.m_tiles * 128, d.N, Ktot, bk, bn, g.tw, g.th, g.m_tiles, g.n_tiles, stages, grid,
+            d.act, d.out_f32, d.res != nullptr);
   gemm_tcgen05_kernel<<<grid, kThreads, smem, st>>>(tmA, tmB, g);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return set_error(cudaGetErrorString(ce));

@@ -151,16 +151,17 @@ __global__ void lanczos_v_paste_kernel(const unsigned char* __restrict__ tmp, in
 // ----------------------------------------------------------------------------------------- im2col
 __global__ void im2col_u8_kernel(const unsigned char* __restrict__ img, int B, int H, int W, int k, int s, int p,
                                  int Ho, int Wo, int Kpad, const float* __restrict__ lut /*[3][256]*/,
-                                 __half* __restrict__ out) {
+                                 __half* __restrict__ out, int split) {
   const long long n = (long long)B * Ho * Wo;
   const int K = k * k * 3;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int ox = int(i % Wo);
     const int oy = int((i / Wo) % Ho);
     const int b = int(i / ((long long)Wo * Ho));
-    __half* o = out + i * Kpad;
+    __half* o = out + i * (split ? 3 * Kpad : Kpad);
     for (int k0 = 0; k0 < Kpad; k0 += 8) {
       __align__(16) __half v[8];
+      __align__(16) __half lo[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int kk = k0 + j;
@@ -173,8 +174,13 @@ __global__ void im2col_u8_kernel(const unsigned char* __restrict__ img, int B, i
           if (y >= 0 && y < H && x >= 0 && x < W) f = lut[c * 256 + img[(((long long)b * H + y) * W + x) * 3 + c]];
         }
         v[j] = __float2half_rn(f);
+        lo[j] = __float2half_rn(f - __half2float(v[j]));
       }
       *reinterpret_cast<uint4*>(o + k0) = *reinterpret_cast<const uint4*>(v);
+      if (split) {   // fp16x3 operand layout [hi | hi | lo], see florence_ops.cu::store_act
+        *reinterpret_cast<uint4*>(o + Kpad + k0) = *reinterpret_cast<const uint4*>(v);
+        *reinterpret_cast<uint4*>(o + 2 * Kpad + k0) = *reinterpret_cast<const uint4*>(lo);
+      }
     }
   }
 }
@@ -294,10 +300,10 @@ int b2p_letterbox(const unsigned char* src, int B, int H, int W, int Wr, int Hr,
 }
 
 int b2p_im2col_u8(const unsigned char* img, int B, int H, int W, int k, int s, int p, int Kpad, const float* lut,
-                  void* out, cudaStream_t st) {
+                  void* out, int split, cudaStream_t st) {
   if (Kpad % 8 || Kpad < k * k * 3) return set_error("im2col_u8: Kpad must be a multiple of 8 and >= 3*k*k");
   const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;
-  im2col_u8_kernel<<<grid_for((long long)B * Ho * Wo, 128), 128, 0, st>>>(img, B, H, W, k, s, p, Ho, Wo, Kpad, lut, (__half*)out);
+  im2col_u8_kernel<<<grid_for((long long)B * Ho * Wo, 128), 128, 0, st>>>(img, B, H, W, k, s, p, Ho, Wo, Kpad, lut, (__half*)out, split);
   B2P_CHECK_LAUNCH();
   return 0;
 }

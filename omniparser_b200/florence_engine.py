@@ -1,0 +1,391 @@
+"""Florence-2 icon captioner on the B200 kernels (replaces ``model.generate`` at ref:util/utils.py:125).
+
+DaViT tower -> projector -> BART encoder run once per batch of crops; the greedy decoder runs one fused step per
+token (KV cache, cross-attention over precomputed K/V, tied LM head, HF logits processors and argmax on device)
+replayed as a CUDA graph whose kernels read the step index from device memory.  GEMM operands are fp16, every
+residual stream / LayerNorm / softmax is fp32.  Weight names follow ``transformers`` 5.5 ``models/florence2``.
+
+Only the reference's CUDA-branch input mode is planned here: 64x64 crops, ``do_resize=False`` -> 2x2 final map ->
+5 image tokens (ref:util/utils.py:120-121; SURVEY.md finding 3).
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import numpy as np
+import torch
+
+from . import ops
+from .ops import ACT_GELU, ACT_NONE
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def _h(t, dev):
+    return t.detach().to(device=dev, dtype=torch.float16).contiguous()
+
+
+def _wpack(w2d, dev, x3):
+    """[N, K] fp32 -> fp16 GEMM operand.  x3: [W_hi | W_lo | W_hi] (pairs with activations [A_hi | A_hi | A_lo])."""
+    w2d = w2d.detach().float()
+    hi = w2d.half()
+    if not x3:
+        return hi.contiguous().to(dev)
+    lo = (w2d - hi.float()).half()
+    return torch.cat([hi, lo, hi], 1).contiguous().to(dev)
+
+
+def _f(t, dev):
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+class _Lin:
+    def __init__(self, sd, name, dev, cat: List[str] | None = None, x3=False):
+        if cat:
+            w = torch.cat([sd[f"{name}.{c}.weight"] for c in cat], 0)
+            b = torch.cat([sd[f"{name}.{c}.bias"] for c in cat], 0)
+        else:
+            w = sd[name + ".weight"]
+            b = sd.get(name + ".bias")
+        self.w = _wpack(w, dev, x3)
+        self.b = _f(b, dev) if b is not None else None
+        self.N, self.K = self.w.shape
+        self.Klog = w.shape[1]
+
+
+class _LN:
+    def __init__(self, sd, name, dev):
+        self.g, self.b = _f(sd[name + ".weight"], dev), _f(sd[name + ".bias"], dev)
+
+
+class FlorenceWeights:
+    def __init__(self, sd: Dict[str, torch.Tensor], device, gen_cfg: dict, precision: str = "fp16x3"):
+        """precision: "fp16x3" (parity grade: fp16 hi/lo operand split, three tensor-core products per term,
+        fp32 accumulate -> near-fp32 GEMMs) or "fp16" (single fp16 product; ~5e-3 logit drift)."""
+        assert precision in ("fp16", "fp16x3")
+        dev = device
+        self.device = dev
+        self.x3 = x3 = precision == "fp16x3"
+        self.precision = precision
+        self.gen = dict(gen_cfg)
+        V = "model.vision_tower."
+        self.dims = (128, 256, 512, 1024)
+        self.heads = (4, 8, 16, 32)
+        self.groups = (4, 8, 16, 32)
+        self.depths = tuple(sum(1 for k in sd if k.startswith(f"{V}blocks.{s}.") and k.endswith("spatial_block.norm1.weight")) for s in range(4))
+        self.conv_embed, self.conv_norm, self.blocks = [], [], []
+        for s in range(4):
+            w = sd[f"{V}convs.{s}.conv.weight"].float()
+            co = w.shape[0]
+            m = w.permute(0, 2, 3, 1).reshape(co, -1)   # (ky,kx,c)
+            if s == 0:
+                m = torch.cat([m, torch.zeros(co, 160 - m.shape[1])], 1)
+                wp = _wpack(m, dev, x3)
+            else:   # per tap [hi | lo | hi] over the tripled input channels
+                t = w.permute(0, 2, 3, 1)                      # [co, 3, 3, ci]
+                hi = t.half()
+                lo = (t - hi.float()).half()
+                wp = (torch.cat([hi, lo, hi], 3) if x3 else hi).reshape(co, -1).contiguous().to(dev)
+            lin = type("W", (), {})()
+            lin.w, lin.b, lin.N, lin.K, lin.Klog = wp, _f(sd[f"{V}convs.{s}.conv.bias"], dev), co, wp.shape[1], m.shape[1]
+            self.conv_embed.append(lin)
+            self.conv_norm.append(_LN(sd, f"{V}convs.{s}.norm", dev))
+            stage = []
+            for d in range(self.depths[s]):
+                blk = {}
+                for kind, attn in (("spatial_block", "window_attn"), ("channel_block", "channel_attn")):
+                    p = f"{V}blocks.{s}.{d}.{kind}."
+                    e = dict(
+                        dw1_w=_f(sd[p + "conv1.weight"].reshape(-1, 9).t(), dev), dw1_b=_f(sd[p + "conv1.bias"], dev),
+                        dw2_w=_f(sd[p + "conv2.weight"].reshape(-1, 9).t(), dev), dw2_b=_f(sd[p + "conv2.bias"], dev),
+                        n1=_LN(sd, p + "norm1", dev), n2=_LN(sd, p + "norm2", dev),
+                        qkv=_Lin(sd, p + attn + ".qkv", dev, x3=x3), proj=_Lin(sd, p + attn + ".proj", dev, x3=x3),
+                        fc1=_Lin(sd, p + "ffn.fc1", dev, x3=x3), fc2=_Lin(sd, p + "ffn.fc2", dev, x3=x3))
+                    blk[kind] = e
+                stage.append(blk)
+            self.blocks.append(stage)
+        P = "model.multi_modal_projector."
+        self.img_proj = _Lin(sd, P + "image_projection", dev, x3=x3)
+        self.img_norm = _LN(sd, P + "image_proj_norm", dev)
+        col, row = sd[P + "image_position_embed.column_embeddings.weight"].float(), sd[P + "image_position_embed.row_embeddings.weight"].float()
+        temporal = sd[P + "visual_temporal_embed.pos_idx_to_embed"].float()[0]
+        self._pos_tables = (col, row, temporal)
+        L = "model.language_model."
+        self.E32 = _f(sd[L + "shared.weight"], dev)
+        self.E16 = _wpack(sd[L + "shared.weight"], dev, x3)
+        self.vocab = self.E16.shape[0]
+        self.enc_pos = _f(sd[L + "encoder.embed_positions.weight"], dev)
+        self.dec_pos = _f(sd[L + "decoder.embed_positions.weight"], dev)
+        self.enc_ln_emb = _LN(sd, L + "encoder.layernorm_embedding", dev)
+        self.dec_ln_emb = _LN(sd, L + "decoder.layernorm_embedding", dev)
+        self.enc_layers, self.dec_layers = [], []
+        n_enc = 1 + max(int(k.split(".")[4]) for k in sd if k.startswith(L + "encoder.layers."))
+        n_dec = 1 + max(int(k.split(".")[4]) for k in sd if k.startswith(L + "decoder.layers."))
+        for i in range(n_enc):
+            p = f"{L}encoder.layers.{i}."
+            self.enc_layers.append(dict(qkv=_Lin(sd, p + "self_attn", dev, ["q_proj", "k_proj", "v_proj"], x3=x3),
+                                        o=_Lin(sd, p + "self_attn.out_proj", dev, x3=x3), ln1=_LN(sd, p + "self_attn_layer_norm", dev),
+                                        fc1=_Lin(sd, p + "fc1", dev, x3=x3), fc2=_Lin(sd, p + "fc2", dev, x3=x3), ln2=_LN(sd, p + "final_layer_norm", dev)))
+        for i in range(n_dec):
+            p = f"{L}decoder.layers.{i}."
+            self.dec_layers.append(dict(qkv=_Lin(sd, p + "self_attn", dev, ["q_proj", "k_proj", "v_proj"], x3=x3),
+                                        o=_Lin(sd, p + "self_attn.out_proj", dev, x3=x3), ln1=_LN(sd, p + "self_attn_layer_norm", dev),
+                                        cq=_Lin(sd, p + "encoder_attn.q_proj", dev, x3=x3), ckv=_Lin(sd, p + "encoder_attn", dev, ["k_proj", "v_proj"], x3=x3),
+                                        co=_Lin(sd, p + "encoder_attn.out_proj", dev, x3=x3), ln2=_LN(sd, p + "encoder_attn_layer_norm", dev),
+                                        fc1=_Lin(sd, p + "fc1", dev, x3=x3), fc2=_Lin(sd, p + "fc2", dev, x3=x3), ln3=_LN(sd, p + "final_layer_norm", dev)))
+        # u8 -> normalised pixel table: rescale 1/255 then (x - mean) / std in fp32 (CLIP image processor order)
+        lut = np.empty((3, 256), np.float32)
+        for c in range(3):
+            lut[c] = (np.arange(256, dtype=np.float32) * np.float32(1.0 / 255.0) - np.float32(IMAGENET_MEAN[c])) / np.float32(IMAGENET_STD[c])
+        self.lut = torch.from_numpy(lut).to(dev)
+
+    def pos_table(self, h, w):
+        col, row, temporal = self._pos_tables
+        pos = torch.cat([col[:w].unsqueeze(0).repeat(h, 1, 1), row[:h].unsqueeze(1).repeat(1, w, 1)], -1)
+        return _f(pos.reshape(h * w, -1) + temporal[None], self.device)
+
+
+class FlorencePlan:
+    """Buffers + launch sequences for a fixed number of crop rows K (64x64 crops)."""
+
+    D = 768
+    HEADS = 12
+
+    def __init__(self, w: FlorenceWeights, K: int, max_new_tokens: int, prompt_ids: List[int], use_graph=True):
+        self.w, self.K, self.dev = w, K, w.device
+        self.x3 = w.x3
+        self.KX = 3 if w.x3 else 1
+        self.T = max_new_tokens
+        self.max_len = max_new_tokens + 1
+        dev = self.dev
+        self.use_graph = use_graph
+        self.crops = torch.zeros((K, 64, 64, 3), dtype=torch.uint8, device=dev)
+        self.prompt = torch.tensor(prompt_ids, dtype=torch.int32, device=dev)
+        self.n_prompt = len(prompt_ids)
+        self.n_img = 5
+        self.L = self.n_img + self.n_prompt
+        self.seq = torch.zeros((K, self.max_len + 1), dtype=torch.int32, device=dev)
+        self.finished = torch.zeros((K,), dtype=torch.int32, device=dev)
+        self.step = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.n_unfinished = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.logits = torch.empty((K, w.vocab), dtype=torch.float32, device=dev)
+        self.enc_ops, self.dec_ops = [], []
+        self.flops_enc = 0   # logical (useful) FLOPs; the fp16x3 mode executes 3x this on the tensor cores
+        self.flops_dec = 0
+        self._build_vision_encoder()
+        self._build_decoder()
+        self.g_enc = self.g_dec = None
+
+    # ------------------------------------------------------------------ helpers
+    def _e(self, *shape, dt=torch.float32):
+        return torch.empty(shape, dtype=dt, device=self.dev)
+
+    def _act(self, T, C):
+        """fp16 GEMM-operand buffer for T rows of logical width C ([hi | hi | lo] in fp16x3 mode)."""
+        return torch.empty((T, self.KX * C), dtype=torch.float16, device=self.dev)
+
+    def _gemm(self, lst, a, lin, out, act=ACT_NONE, res=None, enc=True, split=False):
+        M = a.shape[0]
+        assert a.shape[1] == lin.K, (a.shape, lin.K)
+        f = 2 * M * lin.N * lin.Klog
+        if enc:
+            self.flops_enc += f
+        else:
+            self.flops_dec += f
+        lst.append(lambda: ops.gemm(a, a.stride(0), lin.w, M, lin.N, lin.K, out, out.stride(0), lin.b, res,
+                                    res.stride(0) if res is not None else 0, act, out_f32=(out.dtype == torch.float32),
+                                    split=split))
+
+    def _ln(self, lst, x, ln, T, C, o16=None, o32=None):
+        lst.append(lambda: ops.layernorm(x, ln.g, ln.b, T, C, o16, o32, split=self.x3))
+
+    # ------------------------------------------------------------------ DaViT + projector + BART encoder
+    def _build_vision_encoder(self):
+        w, K, ops_, x3 = self.w, self.K, self.enc_ops, self.x3
+        H = 16
+        T = K * H * H
+        A0 = self._act(T, 160)
+        ops_.append(lambda: ops.im2col_u8(self.crops, K, 64, 64, 7, 4, 3, 160, w.lut, A0, split=x3))
+        y = self._e(T, 128)
+        self._gemm(ops_, A0, w.conv_embed[0], y)
+        x = self._e(T, 128)
+        self._ln(ops_, y, w.conv_norm[0], T, 128, None, x)
+        for s in range(4):
+            C = w.dims[s]
+            if s > 0:
+                Cp = w.dims[s - 1]
+                hmap = ops.new_map(K, H, H, self.KX * Cp, self.dev)
+                self._ln(ops_, x, w.conv_norm[s], T, Cp, hmap.buf, None)
+                H //= 2
+                T = K * H * H
+                xo = ops.new_map(K, H, H, C, self.dev, torch.float32)
+                ce = w.conv_embed[s]
+                self.flops_enc += 2 * T * C * 9 * Cp
+                ops_.append(lambda hmap=hmap, xo=xo, ce=ce: ops.conv3x3(hmap, ce.w, xo, 2, ce.b, None, ACT_NONE, out_f32=True))
+                x = xo.buf.view(T, C)
+            for blk in w.blocks[s]:
+                for kind in ("spatial_block", "channel_block"):
+                    e = blk[kind]
+                    x1 = self._e(T, C)
+                    ops_.append(lambda x=x, x1=x1, e=e, H=H, C=C: ops.dwconv3x3_res(x, K, H, H, C, e["dw1_w"], e["dw1_b"], x1))
+                    h = self._act(T, C)
+                    self._ln(ops_, x1, e["n1"], T, C, h)
+                    qkv = self._e(T, 3 * C)
+                    self._gemm(ops_, h, e["qkv"], qkv)
+                    a = self._act(T, C)
+                    if kind == "spatial_block":
+                        hd = w.heads[s]
+                        ops_.append(lambda qkv=qkv, a=a, e=e, H=H, C=C, hd=hd: ops.window_attn(qkv, e["qkv"].b, K, H, H, C, hd, a, split=x3))
+                    else:
+                        gr = w.groups[s]
+                        ops_.append(lambda qkv=qkv, a=a, H=H, C=C, gr=gr: ops.channel_attn(qkv, K, H * H, C, gr, a, split=x3))
+                    x2 = self._e(T, C)
+                    self._gemm(ops_, a, e["proj"], x2, res=x1)
+                    x3_ = self._e(T, C)
+                    ops_.append(lambda x2=x2, x3_=x3_, e=e, H=H, C=C: ops.dwconv3x3_res(x2, K, H, H, C, e["dw2_w"], e["dw2_b"], x3_))
+                    h2 = self._act(T, C)
+                    self._ln(ops_, x3_, e["n2"], T, C, h2)
+                    f = self._act(T, 4 * C)
+                    self._gemm(ops_, h2, e["fc1"], f, act=ACT_GELU, split=x3)
+                    x4 = self._e(T, C)
+                    self._gemm(ops_, f, e["fc2"], x4, res=x3_)
+                    x = x4
+        self.vision_out = x                     # [K*HW, 1024] fp32, H = 2
+        HW = H * H
+        pos = w.pos_table(H, H)
+        pp = self._act(K * (HW + 1), 1024)
+        ops_.append(lambda x=x: ops.projector_prep(x, pos, K, HW, 1024, pp, split=x3))
+        pf = self._e(K * (HW + 1), self.D)
+        self._gemm(ops_, pp, w.img_proj, pf)
+        self.img_feat = self._e(K * (HW + 1), self.D)
+        self._ln(ops_, pf, w.img_norm, K * (HW + 1), self.D, None, self.img_feat)
+        assert HW + 1 == self.n_img
+        # BART encoder
+        L, D = self.L, self.D
+        TE = K * L
+        e0 = self._e(TE, D)
+        ops_.append(lambda: ops.encoder_embed(self.img_feat, self.n_img, w.E32, self.prompt, self.n_prompt, w.enc_pos, K, D, e0))
+        x = self._e(TE, D)
+        h = self._act(TE, D)
+        self._ln(ops_, e0, w.enc_ln_emb, TE, D, h, x)
+        for lay in w.enc_layers:
+            qkv = self._e(TE, 3 * D)
+            self._gemm(ops_, h, lay["qkv"], qkv)
+            a = self._act(TE, D)
+            ops_.append(lambda qkv=qkv, a=a: ops.mha(qkv, 3 * D, qkv[:, D:], qkv[:, 2 * D:], 3 * D, K, L, L, self.HEADS, a, a.stride(0), split=x3))
+            y = self._e(TE, D)
+            self._gemm(ops_, a, lay["o"], y, res=x)
+            x = self._e(TE, D); h = self._act(TE, D)
+            self._ln(ops_, y, lay["ln1"], TE, D, h, x)
+            f = self._act(TE, 4 * D)
+            self._gemm(ops_, h, lay["fc1"], f, act=ACT_GELU, split=x3)
+            y = self._e(TE, D)
+            self._gemm(ops_, f, lay["fc2"], y, res=x)
+            x = self._e(TE, D); h = self._act(TE, D)
+            self._ln(ops_, y, lay["ln2"], TE, D, h, x)
+        self.enc_out32, self.enc_out16 = x, h
+        # cross-attention K/V of every decoder layer, once per batch (fp32: read by the attention kernel)
+        self.cross_kv = []
+        for lay in w.dec_layers:
+            kv = self._e(TE, 2 * D)
+            self._gemm(ops_, h, lay["ckv"], kv)
+            self.cross_kv.append(kv)
+
+    # ------------------------------------------------------------------ one greedy decode step
+    def _build_decoder(self):
+        w, K, D, ops_, x3 = self.w, self.K, self.D, self.dec_ops, self.x3
+        g = w.gen
+        tmax = self.max_len
+        e0 = self._e(K, D)
+        ops_.append(lambda: ops.decoder_embed(w.E32, self.seq, self.seq.stride(0), self.step, w.dec_pos, K, D, e0))
+        x = self._e(K, D); h = self._act(K, D)
+        self._ln(ops_, e0, w.dec_ln_emb, K, D, h, x)
+        self.kcache, self.vcache = [], []
+        for li, lay in enumerate(w.dec_layers):
+            qkv = self._e(K, 3 * D)
+            self._gemm(ops_, h, lay["qkv"], qkv, enc=False)
+            kc = torch.zeros((K, tmax, D), dtype=torch.float32, device=self.dev)
+            vc = torch.zeros((K, tmax, D), dtype=torch.float32, device=self.dev)
+            self.kcache.append(kc); self.vcache.append(vc)
+            a = self._act(K, D)
+            ops_.append(lambda qkv=qkv, kc=kc, vc=vc, a=a: ops.mha_cached(qkv, 3 * D, qkv[:, D:], qkv[:, 2 * D:], 3 * D, kc, vc, tmax,
+                                                                       self.step, K, self.HEADS, a, a.stride(0), split=x3))
+            y = self._e(K, D)
+            self._gemm(ops_, a, lay["o"], y, res=x, enc=False)
+            x = self._e(K, D); h = self._act(K, D)
+            self._ln(ops_, y, lay["ln1"], K, D, h, x)
+            q = self._e(K, D)
+            self._gemm(ops_, h, lay["cq"], q, enc=False)
+            kv = self.cross_kv[li]
+            a2 = self._act(K, D)
+            ops_.append(lambda q=q, kv=kv, a2=a2: ops.mha(q, D, kv, kv[:, D:], 2 * D, K, 1, self.L, self.HEADS, a2, a2.stride(0), split=x3))
+            y = self._e(K, D)
+            self._gemm(ops_, a2, lay["co"], y, res=x, enc=False)
+            x = self._e(K, D); h = self._act(K, D)
+            self._ln(ops_, y, lay["ln2"], K, D, h, x)
+            f = self._act(K, 4 * D)
+            self._gemm(ops_, h, lay["fc1"], f, act=ACT_GELU, enc=False, split=x3)
+            y = self._e(K, D)
+            self._gemm(ops_, f, lay["fc2"], y, res=x, enc=False)
+            x = self._e(K, D); h = self._act(K, D)
+            self._ln(ops_, y, lay["ln3"], K, D, h, x)
+        self.dec_hidden16 = h
+        lm = type("W", (), {})()
+        lm.w, lm.b, lm.N, lm.K, lm.Klog = w.E16, None, w.vocab, w.E16.shape[1], D
+        self._gemm(ops_, h, lm, self.logits, enc=False)
+        fb = g.get("forced_bos_token_id")
+        fe = g.get("forced_eos_token_id")
+        self.pick = lambda dump=None: ops.greedy_pick(self.logits, self.logits.stride(0), w.vocab, K, self.seq, self.seq.stride(0),
+                                                      self.finished, self.step, g.get("no_repeat_ngram_size", 0) or 0,
+                                                      -1 if fb is None else fb, -1 if fe is None else fe,
+                                                      g["eos_token_id"], g["pad_token_id"], self.max_len, dump, self.n_unfinished)
+
+    # ------------------------------------------------------------------ running
+    def _run(self, lst, which):
+        if not self.use_graph:
+            for f in lst:
+                f()
+            return
+        g = getattr(self, which)
+        if g is None:
+            for f in lst:
+                f()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for f in lst:
+                    f()
+            setattr(self, which, g)
+            return
+        g.replay()
+
+    def encode(self):
+        self._run(self.enc_ops, "g_enc")
+
+    def reset_decode(self, n_active: int):
+        self.seq.zero_()
+        self.seq[:, 0] = self.w.gen["decoder_start_token_id"]
+        self.finished.zero_()
+        if n_active < self.K:
+            self.finished[n_active:] = 1     # padding rows never gate the stop test
+        self.step.zero_()
+        self.n_unfinished.fill_(n_active)
+
+    def decode_step(self, dump=None, force_tokens=None):
+        """one token for every row; ``force_tokens`` [K] (teacher forcing) overwrites the picked ids."""
+        if dump is None and force_tokens is None:
+            self._run(self.dec_ops_full(), "g_dec")
+            return
+        for f in self.dec_ops:
+            f()
+        self.pick(dump)
+        if force_tokens is not None:
+            t = int(self.step.item())
+            self.seq[:, t + 1] = force_tokens
+        ops.step_advance(self.step)
+
+    def dec_ops_full(self):
+        if not hasattr(self, "_dec_full"):
+            self._dec_full = self.dec_ops + [lambda: self.pick(None), lambda: ops.step_advance(self.step)]
+        return self._dec_full

@@ -13,7 +13,7 @@ import torch
 from . import _lib
 
 ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
-FLAG_BF16, FLAG_OUT_F32 = 1, 2
+FLAG_BF16, FLAG_OUT_F32, FLAG_SPLIT = 1, 2, 4
 
 
 def _stream():
@@ -61,8 +61,8 @@ def new_map(B, H, W, Ctot, device, dtype=torch.float16):
 
 
 def gemm(a_ptr, lda, w, M, N, K, out_ptr, ldc, bias=None, res_ptr=None, ldr=0, act=ACT_NONE, out_f32=False,
-         bf16=False, bn_max=0):
-    flags = (FLAG_BF16 if bf16 else 0) | (FLAG_OUT_F32 if out_f32 else 0) | (bn_max << 8)
+         bf16=False, bn_max=0, split=False):
+    flags = (FLAG_BF16 if bf16 else 0) | (FLAG_OUT_F32 if out_f32 else 0) | (FLAG_SPLIT if split else 0) | (bn_max << 8)
     _lib.check(_lib.lib().b2p_gemm(_p(a_ptr), lda, _p(w), M, N, K, _p(out_ptr), ldc, _p(bias), _p(res_ptr), ldr, act,
                                    flags, _stream()))
 
@@ -89,8 +89,9 @@ def conv1x1(x: Map, w, out: Map, bias=None, res: Map | None = None, act=ACT_SILU
          out_f32=out_f32)
 
 
-def conv3x3(x: Map, w, out: Map, stride=1, bias=None, res: Map | None = None, act=ACT_SILU, out_f32=False, bn_max=0):
-    flags = (FLAG_OUT_F32 if out_f32 else 0) | (bn_max << 8)
+def conv3x3(x: Map, w, out: Map, stride=1, bias=None, res: Map | None = None, act=ACT_SILU, out_f32=False, bn_max=0,
+            split=False):
+    flags = (FLAG_OUT_F32 if out_f32 else 0) | (FLAG_SPLIT if split else 0) | (bn_max << 8)
     _lib.check(_lib.lib().b2p_conv3x3(_p(x.ptr), x.ld, x.B, x.H, x.W, x.C, stride, _p(w), out.C, _p(out.ptr), out.ld,
                                       _p(bias), _p(res.ptr if res else None), res.ld if res else 0, act, flags,
                                       _stream()))
@@ -140,10 +141,61 @@ def letterbox(src_u8, B, H, W, Wr, Hr, Tw, Th, pad_l, pad_t, tmp, canvas):
                                         _stream()))
 
 
-def im2col_u8(img, B, H, W, k, s, p, Kpad, lut, out):
-    _lib.check(_lib.lib().b2p_im2col_u8(_p(img), B, H, W, k, s, p, Kpad, _p(lut), _p(out), _stream()))
+def im2col_u8(img, B, H, W, k, s, p, Kpad, lut, out, split=False):
+    _lib.check(_lib.lib().b2p_im2col_u8(_p(img), B, H, W, k, s, p, Kpad, _p(lut), _p(out), int(split), _stream()))
 
 
 def crop_resize(imgs, img_hw, img_off, boxes, box_img, n_box, out_hw, out, status):
     _lib.check(_lib.lib().b2p_crop_resize(_p(imgs), _p(img_hw), _p(img_off), _p(boxes), _p(box_img), n_box, out_hw,
                                           _p(out), _p(status), _stream()))
+
+
+# ------------------------------------------------------------------------------------------ Florence-2 ops
+# `split=True` writes fp16 activations in the fp16x3 operand layout [hi | hi | lo] (row stride 3*C).
+def layernorm(x, gamma, beta, T, C, out16=None, out32=None, eps=1e-5, split=False):
+    _lib.check(_lib.lib().b2p_layernorm(_p(x), C, _p(gamma), _p(beta), eps, T, C, _p(out16), 3 * C if split else C,
+                                        _p(out32), C, int(split), _stream()))
+
+
+def dwconv3x3_res(x, B, H, W, C, w9c, bias, y):
+    _lib.check(_lib.lib().b2p_dwconv3x3_res(_p(x), B, H, W, C, _p(w9c), _p(bias), _p(y), _stream()))
+
+
+def window_attn(qkv32, qkv_bias, B, H, W, C, heads, out, win=12, split=False):
+    _lib.check(_lib.lib().b2p_window_attn(_p(qkv32), _p(qkv_bias), B, H, W, C, heads, win, _p(out), int(split), _stream()))
+
+
+def channel_attn(qkv32, B, N, C, groups, out, split=False):
+    _lib.check(_lib.lib().b2p_channel_attn(_p(qkv32), B, N, C, groups, _p(out), int(split), _stream()))
+
+
+def mha(q, ldq, k, v, ldk, B, Lq, Lk, heads, out, ldo, split=False):
+    _lib.check(_lib.lib().b2p_mha(_p(q), ldq, _p(k), _p(v), ldk, B, Lq, Lk, heads, _p(out), ldo, int(split), _stream()))
+
+
+def mha_cached(q, ldq, knew, vnew, ldnew, kcache, vcache, tmax, step, B, heads, out, ldo, split=False):
+    _lib.check(_lib.lib().b2p_mha_cached(_p(q), ldq, _p(knew), _p(vnew), ldnew, _p(kcache), _p(vcache), tmax, _p(step),
+                                         B, heads, _p(out), ldo, int(split), _stream()))
+
+
+def encoder_embed(img, n_img, E32, prompt, n_prompt, P, B, C, out):
+    _lib.check(_lib.lib().b2p_encoder_embed(_p(img), n_img, _p(E32), _p(prompt), n_prompt, _p(P), B, C, _p(out), _stream()))
+
+
+def decoder_embed(E32, seq, seq_ld, step, P, B, C, out):
+    _lib.check(_lib.lib().b2p_decoder_embed(_p(E32), _p(seq), seq_ld, _p(step), _p(P), B, C, _p(out), _stream()))
+
+
+def projector_prep(x, pos, B, HW, C, out, split=False):
+    _lib.check(_lib.lib().b2p_projector_prep(_p(x), _p(pos), B, HW, C, _p(out), int(split), _stream()))
+
+
+def greedy_pick(logits, ld, V, B, seq, seq_ld, finished, step, ngram, forced_bos, forced_eos, eos, pad, max_len,
+                dump=None, n_unfinished=None):
+    _lib.check(_lib.lib().b2p_greedy_pick(_p(logits), ld, V, B, _p(seq), seq_ld, _p(finished), _p(step), ngram,
+                                          forced_bos, forced_eos, eos, pad, max_len, _p(dump), _p(n_unfinished),
+                                          _stream()))
+
+
+def step_advance(step):
+    _lib.check(_lib.lib().b2p_step_advance(_p(step), _stream()))

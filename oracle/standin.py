@@ -30,8 +30,8 @@ BN_CALIB = GOLDEN / "yolov9e_bn_calib_seed0.npz"
 # Head calibration constants of the stand-in (chosen once so that the synthetic
 # 1920x1080 screenshots give ~60 post-NMS boxes at BOX_TRESHOLD=0.05, iou=0.1).
 DFL_BIN_SLOPE = -0.5          # final box-conv bias = slope * bin  -> ~1.5 strides per side
-CLS_BIAS = (-4.4, -7.0, -9.0)  # per-scale class-logit bias (stride 8, 16, 32)
-CLS_GAIN = 0.8
+CLS_BIAS = (-5.6, -8.5, -10.5)  # per-scale class-logit bias (stride 8, 16, 32)
+CLS_GAIN = 3.0
 
 
 def _seed_weights(m: YOLOv9E, seed: int) -> None:
@@ -45,8 +45,11 @@ def _seed_weights(m: YOLOv9E, seed: int) -> None:
                     mod.bias.copy_(torch.randn(mod.bias.shape, generator=g) * 0.1)
             elif isinstance(mod, nn.BatchNorm2d):
                 n = mod.num_features
-                mod.weight.copy_(1.0 + 0.1 * torch.randn(n, generator=g))
-                mod.bias.copy_(0.2 * torch.randn(n, generator=g))
+                # gamma ~0.5, beta ~0.5 keeps SiLU in a mildly non-linear regime: a random deep net with unit-gain
+                # BN is chaotic (measured: fp16 rounding noise amplified ~1000x over the 100-layer depth, 50 % drift at
+                # the heads), which says nothing about kernel correctness; trained detectors are not in that regime.
+                mod.weight.copy_(0.5 + 0.05 * torch.randn(n, generator=g))
+                mod.bias.copy_(0.5 + 0.2 * torch.randn(n, generator=g))
         for i, seq in enumerate(m.detect.cv2):
             bins = torch.arange(16, dtype=torch.float32).repeat(4)
             seq[-1].bias.copy_(DFL_BIN_SLOPE * bins)
