@@ -1,0 +1,218 @@
+"""Drop-in ``{'model', 'processor'}`` pair for the Florence-2 caption branch of
+``get_caption_model_processor`` (ref:util/utils.py:48-69) on the B200 kernels.
+
+Contract kept: ``model.config.model_type`` / ``model.config.name_or_path`` (contains 'florence'),
+``model.device``, ``model.generate(input_ids=, pixel_values=, max_new_tokens=20, num_beams=1, do_sample=False)`` ->
+``LongTensor[K, T]``; ``processor(images=, text=, return_tensors="pt"[, do_resize=False])`` -> object with
+``.to(device=, dtype=)`` and keys ``input_ids`` / ``pixel_values``; ``processor.batch_decode(ids,
+skip_special_tokens=True)``.
+
+The processor hands the 64x64 crops to the model as raw u8 HWC (its ``.to(dtype=float16)`` leaves integer tensors
+alone, exactly like ``BatchFeature.to``); rescale + ImageNet normalisation is folded into the first kernel's lookup
+table.  Float ``pixel_values`` (K,3,64,64) are also accepted and mapped back to the u8 they came from.
+"""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+from types import SimpleNamespace
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .florence_engine import IMAGENET_MEAN, IMAGENET_STD, FlorencePlan, FlorenceWeights
+
+# "<s>What does the image describe?</s>" in the BART vocabulary (hf:models/florence2/processing_florence2.py:81 maps
+# "<CAPTION>" to this question, ref:util/utils.py:109-110)
+CAPTION_PROMPT_IDS = [0, 2264, 473, 5, 2274, 6190, 116, 2]
+DEFAULT_GEN = dict(forced_bos_token_id=0, forced_eos_token_id=2, no_repeat_ngram_size=3, eos_token_id=2, pad_token_id=1,
+                   bos_token_id=0, decoder_start_token_id=2)
+BUCKET = 32
+
+
+class _Batch(dict):
+    """Minimal BatchFeature: attribute access + ``.to`` that only casts floating tensors."""
+
+    def to(self, device=None, dtype=None, **_):
+        out = _Batch()
+        for k, v in self.items():
+            if torch.is_tensor(v):
+                v = v.to(device=device, dtype=dtype) if (dtype is not None and v.is_floating_point()) else v.to(device=device)
+            out[k] = v
+        return out
+
+    __getattr__ = dict.__getitem__
+
+
+class B200Florence2Processor:
+    def __init__(self, tokenizer=None, prompt_ids: Sequence[int] = CAPTION_PROMPT_IDS):
+        self.tokenizer = tokenizer
+        self.prompt_ids = list(prompt_ids)
+
+    def __call__(self, images=None, text=None, return_tensors="pt", do_resize=False, **kw):
+        if do_resize:
+            raise NotImplementedError("the B200 caption path implements the reference's CUDA branch (do_resize=False, "
+                                      "64x64 crops, ref:util/utils.py:121); the 768x768 CPU branch is not planned")
+        arr = []
+        for im in images:
+            a = np.asarray(im.convert("RGB") if hasattr(im, "convert") else im, dtype=np.uint8)
+            if a.shape != (64, 64, 3):
+                raise ValueError(f"expected 64x64 RGB crops, got {a.shape}")
+            arr.append(a)
+        px = torch.from_numpy(np.stack(arr)) if arr else torch.zeros((0, 64, 64, 3), dtype=torch.uint8)
+        ids = torch.tensor([self.prompt_ids] * len(arr), dtype=torch.long).reshape(len(arr), len(self.prompt_ids))
+        return _Batch(input_ids=ids, pixel_values=px)
+
+    def batch_decode(self, ids, skip_special_tokens=True, **kw) -> List[str]:
+        ids = ids.tolist() if torch.is_tensor(ids) else ids
+        if self.tokenizer is not None:
+            return self.tokenizer.batch_decode(ids, skip_special_tokens=skip_special_tokens, **kw)
+        special = {0, 1, 2} if skip_special_tokens else set()
+        # no BART vocab/merges in this environment: ids are the pinned parity target, strings are id tags
+        return [" ".join(f"<{t}>" for t in row if t not in special) for row in ids]
+
+
+class B200Florence2Model:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device, gen_cfg: Optional[dict] = None,
+                 precision: str = "fp16x3", name_or_path: str = "b200/florence2", use_graph: bool = True):
+        self.device = torch.device(device)
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            raise RuntimeError("B200 Florence-2 needs a CUDA device; there is no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.config = SimpleNamespace(model_type="florence2", name_or_path=name_or_path)
+        self.gen = dict(DEFAULT_GEN)
+        if gen_cfg:
+            self.gen.update({k: v for k, v in gen_cfg.items() if k in self.gen or k.endswith("_token_id") or k == "no_repeat_ngram_size"})
+        with torch.cuda.device(self.device):
+            self.weights = FlorenceWeights(state_dict, self.device, self.gen, precision)
+        self.use_graph = use_graph
+        self._plans: Dict[tuple, FlorencePlan] = {}
+        inv = np.zeros((3, 256), np.float32)
+        for c in range(3):
+            inv[c] = (np.arange(256, dtype=np.float32) * np.float32(1 / 255.0) - np.float32(IMAGENET_MEAN[c])) / np.float32(IMAGENET_STD[c])
+        self._lut_cpu = torch.from_numpy(inv)
+
+    def to(self, device):
+        return self
+
+    def eval(self):
+        return self
+
+    def plan_for(self, n: int, max_new_tokens: int, prompt_ids: Sequence[int]) -> FlorencePlan:
+        K = max(BUCKET, ((n + BUCKET - 1) // BUCKET) * BUCKET)
+        key = (K, max_new_tokens, tuple(prompt_ids))
+        if key not in self._plans:
+            with torch.cuda.device(self.device):
+                self._plans[key] = FlorencePlan(self.weights, K, max_new_tokens, list(prompt_ids), self.use_graph)
+        return self._plans[key]
+
+    def _to_u8(self, pixel_values: torch.Tensor) -> torch.Tensor:
+        if pixel_values.dtype == torch.uint8:
+            if pixel_values.dim() == 4 and pixel_values.shape[-1] == 3:
+                return pixel_values
+            raise ValueError("uint8 pixel_values must be [K,64,64,3]")
+        x = pixel_values.float().cpu()   # [K,3,64,64] normalised
+        mean = torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1)
+        std = torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)
+        return ((x * std + mean) * 255.0).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+
+    @torch.inference_mode()
+    def generate_from_device_crops(self, plan: FlorencePlan, n: int, sync_every: int = 4) -> torch.Tensor:
+        """Crops already in ``plan.crops[:n]`` (device).  Returns LongTensor [n, T] on the device, HF layout
+        ``[decoder_start, tokens..., eos, pad...]`` truncated where every row has finished."""
+        with torch.cuda.device(self.device):
+            if n < plan.K:
+                plan.crops[n:].zero_()
+            plan.encode()
+            plan.reset_decode(n)
+            steps = 0
+            while steps < plan.T:
+                plan.decode_step()
+                steps += 1
+                if steps % sync_every == 0 and steps < plan.T and int(plan.n_unfinished.item()) == 0:
+                    break
+            # exact stop length: first step after which no row was unfinished
+            seq = plan.seq[:n, :steps + 1]
+            if steps > 1:
+                done_at = self._first_all_finished(seq)
+                if done_at is not None:
+                    seq = seq[:, :done_at + 1]
+            return seq.long()
+
+    def _first_all_finished(self, seq: torch.Tensor):
+        """HF stops right after the first step at which every row has produced EOS (hf:generation/utils.py:2797-2805)."""
+        eos = self.gen["eos_token_id"]
+        if seq.shape[0] == 0:
+            return None
+        hit = (seq[:, 1:] == eos)
+        first = torch.where(hit.any(1), hit.float().argmax(1) + 1, torch.full((seq.shape[0],), seq.shape[1], device=seq.device))
+        last = int(first.max().item())
+        return last if last < seq.shape[1] else None
+
+    @torch.inference_mode()
+    def generate(self, input_ids=None, pixel_values=None, max_new_tokens=20, num_beams=1, do_sample=False, **kw):
+        """ref:util/utils.py:125."""
+        if num_beams != 1 or do_sample:
+            raise NotImplementedError("only greedy decoding (num_beams=1, do_sample=False) is on the hot path")
+        u8 = self._to_u8(pixel_values)
+        n = u8.shape[0]
+        if n == 0:
+            return torch.zeros((0, 1), dtype=torch.long, device=self.device)
+        prompt = input_ids[0].tolist() if input_ids is not None else CAPTION_PROMPT_IDS
+        if input_ids is not None and not bool((input_ids == input_ids[0:1]).all()):
+            raise NotImplementedError("all rows must share one prompt (the reference passes [prompt]*len(batch))")
+        plan = self.plan_for(n, max_new_tokens, prompt)
+        plan.crops[:n].copy_(u8.to(self.device, non_blocking=True))
+        return self.generate_from_device_crops(plan, n)
+
+
+def load_florence_state(path: str | Path):
+    """Read ``model.safetensors`` (+ ``generation_config.json``) from a local directory (ref:README.md:45-46)."""
+    from safetensors.torch import load_file
+
+    p = Path(path)
+    sd = load_file(str(p / "model.safetensors"))
+    gen = {}
+    for name in ("generation_config.json", "config.json"):
+        f = p / name
+        if f.is_file():
+            cfg = json.loads(f.read_text())
+            for k in DEFAULT_GEN:
+                if k in cfg and k not in gen:
+                    gen[k] = cfg[k]
+    return rename_remote_code(sd), gen
+
+
+def rename_remote_code(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """microsoft/Florence-2 remote-code parameter names -> transformers-native names.  Only prefix
+    and leaf renames; untestable offline (no real checkpoint here) and therefore conservative: native names pass
+    through unchanged."""
+    if any(k.startswith("model.vision_tower.") for k in sd):
+        return sd
+    out = {}
+    for k, v in sd.items():
+        nk = k
+        if k.startswith("vision_tower."):
+            nk = "model." + k
+            nk = nk.replace(".convs.", ".convs.").replace(".proj.weight", ".conv.weight").replace(".proj.bias", ".conv.bias") \
+                if ".convs." in nk else nk
+            nk = nk.replace(".window_attn.fn.", ".window_attn.").replace(".channel_attn.fn.", ".channel_attn.")
+            nk = nk.replace(".conv1.fn.dw.", ".conv1.").replace(".conv2.fn.dw.", ".conv2.")
+            nk = nk.replace(".ffn.fn.net.fc1.", ".ffn.fc1.").replace(".ffn.fn.net.fc2.", ".ffn.fc2.")
+            nk = nk.replace(".window_attn.norm.", ".norm1.").replace(".channel_attn.norm.", ".norm1.").replace(".ffn.norm.", ".norm2.")
+        elif k == "image_projection":
+            nk, v = "model.multi_modal_projector.image_projection.weight", v.t().contiguous()
+        elif k.startswith("image_proj_norm."):
+            nk = "model.multi_modal_projector." + k
+        elif k.startswith("image_pos_embed."):
+            nk = "model.multi_modal_projector.image_position_embed." + k[len("image_pos_embed."):]
+        elif k.startswith("visual_temporal_embed."):
+            nk = "model.multi_modal_projector." + k
+        elif k.startswith("language_model.model."):
+            nk = "model.language_model." + k[len("language_model.model."):]
+        elif k == "language_model.lm_head.weight":
+            nk = "lm_head.weight"
+        out[nk] = v
+    return out

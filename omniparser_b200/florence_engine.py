@@ -359,6 +359,7 @@ class FlorencePlan:
             setattr(self, which, g)
             return
         g.replay()
+        ops.GRAPH_LAUNCHES[0] += len(lst)
 
     def encode(self):
         self._run(self.enc_ops, "g_enc")

@@ -1,0 +1,108 @@
+"""Host-side list logic between detection and captioning, restated from ``ref:util/utils.py`` (it needs the OCR
+strings, so it stays on the host in this round; SURVEY.md §8a row P2, §8f-2 lists the device version as "next").
+
+Semantics kept exactly (Python floats on float32-rounded ratios, strict comparisons, list order):
+``int_box_area`` (ref:util/utils.py:411-415), ``remove_overlap_new`` (:241-319), element construction and the
+stable "content is None last" sort (:444-451), caption fill order (:467-469).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+
+def int_box_area(box: Sequence[float], w: int, h: int) -> int:
+    x1, y1, x2, y2 = box
+    return (int(x2 * w) - int(x1 * w)) * (int(y2 * h) - int(y1 * h))
+
+
+def _area(b):
+    return (b[2] - b[0]) * (b[3] - b[1])
+
+
+def _inter(b1, b2):
+    return max(0, min(b1[2], b2[2]) - max(b1[0], b2[0])) * max(0, min(b1[3], b2[3]) - max(b1[1], b2[1]))
+
+
+def _iou_star(b1, b2):
+    """max(IoU, inter/area1, inter/area2) with the +1e-6 union guard (ref:util/utils.py:259-267)."""
+    inter = _inter(b1, b2)
+    union = _area(b1) + _area(b2) - inter + 1e-6
+    if _area(b1) > 0 and _area(b2) > 0:
+        r1, r2 = inter / _area(b1), inter / _area(b2)
+    else:
+        r1, r2 = 0, 0
+    return max(inter / union, r1, r2)
+
+
+def _is_inside(b1, b2):
+    return _inter(b1, b2) / _area(b1) > 0.80   # ref:util/utils.py:269-273
+
+
+def remove_overlap_new(boxes: List[dict], iou_threshold: float, ocr_bbox: Optional[List[dict]] = None) -> List[dict]:
+    filtered: List = []
+    if ocr_bbox:
+        filtered.extend(ocr_bbox)
+    for i, e1 in enumerate(boxes):
+        b1 = e1["bbox"]
+        valid = True
+        for j, e2 in enumerate(boxes):
+            b2 = e2["bbox"]
+            if i != j and _iou_star(b1, b2) > iou_threshold and _area(b1) > _area(b2):   # keep the smaller box
+                valid = False
+                break
+        if not valid:
+            continue
+        if ocr_bbox:
+            added = False
+            labels = ""
+            for e3 in ocr_bbox:
+                if added:
+                    continue
+                b3 = e3["bbox"]
+                try:
+                    if _is_inside(b3, b1):         # OCR box inside the icon: its text labels the icon
+                        labels += e3["content"] + " "
+                        filtered.remove(e3)
+                    elif _is_inside(b1, b3):       # icon inside an OCR box: drop the icon
+                        added = True
+                        break
+                except Exception:                  # the reference swallows errors here (ref:util/utils.py:300-305)
+                    continue
+            if not added:
+                if labels:
+                    filtered.append({"type": "icon", "bbox": e1["bbox"], "interactivity": True, "content": labels,
+                                     "source": "box_yolo_content_ocr"})
+                else:
+                    filtered.append({"type": "icon", "bbox": e1["bbox"], "interactivity": True, "content": None,
+                                     "source": "box_yolo_content_yolo"})
+        else:
+            filtered.append(b1)   # reference quirk kept: bare list when there are no OCR boxes (:317-318)
+    return filtered
+
+
+def build_elements(xyxy_ratio: List[List[float]], ocr_ratio: Optional[List[List[float]]], ocr_text: Sequence[str],
+                   w: int, h: int, iou_threshold: float) -> Tuple[List[dict], int]:
+    """ref:util/utils.py:444-451 -> (filtered_boxes_elem sorted with content-None last, starting_idx)."""
+    if ocr_ratio is None:
+        # ref:util/utils.py:437-444 raises TypeError here (zip over None); the drop-in accepts "no OCR" as an empty list
+        ocr_ratio = []
+    ocr_elem = [{"type": "text", "bbox": box, "interactivity": False, "content": txt, "source": "box_ocr_content_ocr"}
+                for box, txt in zip(ocr_ratio, ocr_text) if int_box_area(box, w, h) > 0]
+    icon_elem = [{"type": "icon", "bbox": box, "interactivity": True, "content": None}
+                 for box in xyxy_ratio if int_box_area(box, w, h) > 0]
+    filtered = remove_overlap_new(icon_elem, iou_threshold, ocr_elem)
+    if not ocr_elem:
+        # normalise the bare-list quirk so downstream code sees dicts
+        filtered = [{"type": "icon", "bbox": b, "interactivity": True, "content": None, "source": "box_yolo_content_yolo"}
+                    if not isinstance(b, dict) else b for b in filtered]
+    elems = sorted(filtered, key=lambda x: x["content"] is None)
+    starting_idx = next((i for i, e in enumerate(elems) if e["content"] is None), -1)
+    return elems, starting_idx
+
+
+def fill_captions(elems: List[dict], captions: List[str]) -> None:
+    """ref:util/utils.py:467-469: captions are consumed in order by the content-None elements."""
+    it = iter(captions)
+    for e in elems:
+        if e["content"] is None:
+            e["content"] = next(it)

@@ -13,6 +13,7 @@ import torch
 from . import _lib
 
 ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
+GRAPH_LAUNCHES = [0]   # kernels replayed through CUDA graphs (the C-side counter only sees direct launches)
 FLAG_BF16, FLAG_OUT_F32, FLAG_SPLIT = 1, 2, 4
 
 

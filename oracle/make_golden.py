@@ -1,0 +1,90 @@
+"""ORACLE (test infrastructure): generate tests/golden/*.json by running the UNMODIFIED reference
+(``/root/reference/util/utils.py::get_som_labeled_img`` + ``util/yolov9.py::YOLOv9Detector``) on the seeded stand-ins.
+Runs only where /root/reference exists (this container): ``python -m oracle.make_golden``.
+
+The reference's caption branch depends on ``model.device.type`` (ref:util/utils.py:120-123).  The goldens pin the
+CUDA-branch semantics (64x64 crops, ``do_resize=False``), executed on the CPU in fp32: the stand-in caption model
+reports a ``device`` whose ``.type`` is 'cuda' so the unmodified reference code takes that branch, and the stand-in
+processor's ``.to(device, dtype)`` keeps fp32 (the reference's fp16 cast is a precision choice, not semantics).
+"""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+from PIL import Image
+
+from omniparser_b200 import synth
+
+from . import florence_standin as FS
+from .shims import import_reference
+from .standin import GOLDEN, yolo_standin
+from .yolov9e import export_torchscript
+
+CASES = [dict(name="synth_seed0", seed=0, size=(1920, 1080)), dict(name="synth_seed3_odd", seed=3, size=(1919, 1079))]
+BOX_TRESHOLD, IOU = 0.05, 0.7
+
+
+class _Batch(dict):
+    def to(self, device=None, dtype=None):
+        return self
+
+
+class _Processor:
+    """What AutoProcessor('microsoft/Florence-2-base') does for ``do_resize=False`` (needs the network, hence restated)."""
+
+    def __call__(self, images, text, return_tensors="pt", do_resize=True):
+        assert do_resize is False, "goldens pin the CUDA-branch (64x64) semantics"
+        u8 = torch.from_numpy(np.stack([np.asarray(im) for im in images]))
+        return _Batch(input_ids=FS.input_ids_for(len(images)), pixel_values=FS.pixel_values_from_u8(u8))
+
+    def batch_decode(self, ids, skip_special_tokens=True):
+        return [" ".join(f"<{t}>" for t in row if t not in (0, 1, 2)) for row in ids.tolist()]
+
+
+class _Model:
+    def __init__(self, hf):
+        self.hf = hf
+        self.config = SimpleNamespace(model_type="florence2", name_or_path="seeded/florence2-standin")
+        self.device = SimpleNamespace(type="cuda")
+        self.ids = []
+
+    def generate(self, **kw):
+        out = self.hf.generate(**kw)
+        self.ids.append(out)
+        return out
+
+
+def main():
+    ru, ry = import_reference()
+    m = yolo_standin(0)
+    path = Path("/tmp/b2p_golden/icon_detect_v3/model.pt")
+    export_torchscript(m, path, (640, 640))
+    det = ru.get_yolo_model(str(path), device="cpu")
+    assert type(det).__name__ == "YOLOv9Detector"
+    fl = FS.florence_standin(0)
+    for case in CASES:
+        w, h = case["size"]
+        img = synth.screenshot(case["seed"], w, h)
+        texts, boxes = synth.ocr_boxes(case["seed"], w, h)
+        raw = det.predict(Image.fromarray(img), conf=BOX_TRESHOLD, iou=0.1)[0].boxes
+        cm = _Model(fl)
+        _, coords, parsed = ru.get_som_labeled_img(Image.fromarray(img), det, BOX_TRESHOLD=BOX_TRESHOLD, output_coord_in_ratio=True,
+                                                   ocr_bbox=boxes, draw_bbox_config=None,
+                                                   caption_model_processor={"model": cm, "processor": _Processor()},
+                                                   ocr_text=texts, use_local_semantics=True, iou_threshold=IOU, scale_img=False,
+                                                   batch_size=128)
+        ids = torch.cat(cm.ids, 0) if cm.ids else torch.zeros((0, 1), dtype=torch.long)
+        gold = dict(case=case, box_threshold=BOX_TRESHOLD, iou_threshold=IOU, max_new_tokens=20,
+                    det_xyxy=[[float(np.float32(v)) for v in b] for b in raw.xyxy.tolist()], det_conf=[float(c) for c in raw.conf.tolist()],
+                    parsed_content_list=parsed, caption_ids=ids.tolist(), label_coordinates=coords)
+        out = GOLDEN / f"{case['name']}.json"
+        out.write_text(json.dumps(gold, default=lambda o: float(o) if isinstance(o, (np.floating,)) else o.tolist()))
+        print("wrote", out, len(raw.xyxy), "boxes,", ids.shape[0], "captions")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,39 @@
+"""CPU: the oracle pipeline (oracle/pipeline_cpu.py) reproduces the golden fixtures that the UNMODIFIED reference
+(`get_som_labeled_img` + `YOLOv9Detector`, run through oracle/make_golden.py where /root/reference exists) produced:
+detector boxes and scores bit-exact, parsed_content_list (order, sources, bboxes, OCR-derived content) identical,
+greedy caption token ids identical."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from omniparser_b200 import synth
+from oracle.pipeline_cpu import OraclePipeline
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def pipe():
+    return OraclePipeline()
+
+
+@pytest.mark.parametrize("name", ["synth_seed0", "synth_seed3_odd"])
+def test_oracle_pipeline_equals_reference_golden(pipe, name):
+    g = json.loads((GOLD / f"{name}.json").read_text())
+    w, h = g["case"]["size"]
+    img = synth.screenshot(g["case"]["seed"], w, h)
+    texts, boxes = synth.ocr_boxes(g["case"]["seed"], w, h)
+    kb, ks = pipe.detect(img, g["box_threshold"], 0.1)
+    assert np.array_equal(kb.numpy(), np.asarray(g["det_xyxy"], np.float32))
+    assert np.array_equal(ks.numpy(), np.asarray(g["det_conf"], np.float32))
+    elems, ids = pipe.parse(img, texts, boxes, BOX_TRESHOLD=g["box_threshold"], iou_threshold=g["iou_threshold"],
+                            max_new_tokens=g["max_new_tokens"])
+    assert ids.tolist() == g["caption_ids"]
+    assert len(elems) == len(g["parsed_content_list"])
+    for a, b in zip(elems, g["parsed_content_list"]):
+        assert a["type"] == b["type"] and a["source"] == b["source"] and a["interactivity"] == b["interactivity"]
+        assert a["bbox"] == b["bbox"]
+        assert a["content"].strip() == b["content"].strip()

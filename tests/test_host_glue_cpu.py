@@ -1,0 +1,67 @@
+"""CPU: host list logic (overlap filter, element construction) of the product vs the unmodified reference functions
+(when /root/reference exists) and vs the oracle's independent restatement."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from omniparser_b200 import host_glue
+from oracle import pipeline_cpu
+from oracle.shims import reference_available
+
+W, H = 1920, 1080
+
+
+def _case(seed, n_icon=70, n_ocr=20):
+    rng = np.random.default_rng(seed)
+    xy = rng.uniform(0, 0.9, size=(n_icon, 2))
+    wh = rng.uniform(0.0, 0.08, size=(n_icon, 2))
+    icons = torch.tensor(np.concatenate([xy, xy + wh], 1), dtype=torch.float32)
+    icons[1] = icons[0]                       # duplicate
+    icons[2, 2:] = icons[2, :2]               # zero area
+    icons[3, :2] = icons[4, :2] + 0.001       # nested
+    icons[3, 2:] = icons[4, 2:] - 0.001
+    ob = []
+    for i in range(n_ocr):
+        x, y = int(rng.integers(0, W - 70)), int(rng.integers(0, H - 30))
+        ob.append([x, y, x + 60, y + 20])
+    # an OCR box inside an icon and an icon inside an OCR box
+    ix = (icons[5] * torch.tensor([W, H, W, H])).tolist()
+    ob[0] = [int(ix[0]) + 1, int(ix[1]) + 1, max(int(ix[0]) + 3, int(ix[2]) - 1), max(int(ix[1]) + 3, int(ix[3]) - 1)]
+    ox = ob[1]
+    icons[6] = torch.tensor([(ox[0] + 5) / W, (ox[1] + 4) / H, (ox[0] + 25) / W, (ox[1] + 14) / H])
+    texts = [f"t{i}" for i in range(n_ocr)]
+    return icons, ob, texts
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("thr", [0.7, 0.9])
+def test_build_elements_matches_oracle_restatement(seed, thr):
+    icons, ob, texts = _case(seed)
+    whwh = torch.Tensor([W, H, W, H])
+    oratio = (torch.tensor(ob) / whwh).tolist()
+    a, start = host_glue.build_elements(icons.tolist(), oratio, texts, W, H, thr)
+    b = pipeline_cpu.build_elements(icons.tolist(), oratio, texts, W, H, thr)
+    assert a == b
+    assert start == next((i for i, e in enumerate(a) if e["content"] is None), -1)
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference not on this machine")
+@pytest.mark.parametrize("seed", range(6))
+def test_build_elements_matches_reference(seed):
+    from oracle.shims import import_reference
+    ru, _ = import_reference()
+    icons, ob, texts = _case(seed)
+    whwh = torch.Tensor([W, H, W, H])
+    for thr in (0.7, 0.9):
+        # ref:util/utils.py:437-451 verbatim call sequence
+        ocr_bbox = (torch.tensor(ob) / whwh).tolist()
+        ocr_elem = [{'type': 'text', 'bbox': box, 'interactivity': False, 'content': txt, 'source': 'box_ocr_content_ocr'}
+                    for box, txt in zip(ocr_bbox, texts) if ru.int_box_area(box, W, H) > 0]
+        xyxy_elem = [{'type': 'icon', 'bbox': box, 'interactivity': True, 'content': None} for box in icons.tolist()
+                     if ru.int_box_area(box, W, H) > 0]
+        ref = ru.remove_overlap_new(boxes=xyxy_elem, iou_threshold=thr, ocr_bbox=copy.deepcopy(ocr_elem))
+        ref = sorted(ref, key=lambda x: x['content'] is None)
+        got, _ = host_glue.build_elements(icons.tolist(), ocr_bbox, texts, W, H, thr)
+        assert got == ref

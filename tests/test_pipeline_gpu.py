@@ -1,0 +1,85 @@
+"""GPU: the integrated parse path (omniparser_b200.utils.parse_screenshots / get_som_labeled_img) against
+(a) the golden fixtures of the unmodified reference with the detector output injected (pins overlap filter, crop +
+resize and caption exactly: identical elements and greedy ids), and (b) the CPU oracle pipeline fed the GPU
+detector's own boxes on a batch of screenshots."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import __graft_entry__ as ge  # noqa: E402
+from omniparser_b200 import synth  # noqa: E402
+from omniparser_b200.utils import get_som_labeled_img, parse_screenshots  # noqa: E402
+from oracle.pipeline_cpu import OraclePipeline  # noqa: E402
+
+GOLD = Path(__file__).resolve().parent / "golden"
+DEV = torch.device("cuda", 0)
+
+
+def _same_elements(got, ref, ids_got, ids_ref):
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        assert a["type"] == b["type"] and a["source"] == b["source"] and a["bbox"] == b["bbox"]
+        assert a["content"].strip() == b["content"].strip()
+    assert ids_got.tolist() == (ids_ref.tolist() if torch.is_tensor(ids_ref) else ids_ref)
+
+
+@pytest.mark.parametrize("name", ["synth_seed0", "synth_seed3_odd"])
+def test_after_detection_equals_reference_golden(name):
+    det, cmp_ = ge.standin_models(DEV)
+    g = json.loads((GOLD / f"{name}.json").read_text())
+    w, h = g["case"]["size"]
+    img = synth.screenshot(g["case"]["seed"], w, h)
+    texts, boxes = synth.ocr_boxes(g["case"]["seed"], w, h)
+    (elems, ids), = parse_screenshots([img], det, cmp_, [(texts, boxes)], BOX_TRESHOLD=g["box_threshold"],
+                                      iou_threshold=g["iou_threshold"], max_new_tokens=g["max_new_tokens"],
+                                      _det_override=[g["det_xyxy"]])
+    _same_elements(elems, g["parsed_content_list"], ids, g["caption_ids"])
+
+
+def test_batch_equals_cpu_oracle_on_gpu_boxes():
+    det, cmp_ = ge.standin_models(DEV)
+    pipe = OraclePipeline(yolo=torch.nn.Identity())
+    seeds = [11, 12, 13]
+    imgs = [synth.screenshot(s) for s in seeds]
+    ocr = [synth.ocr_boxes(s) for s in seeds]
+    out = parse_screenshots(imgs, det, cmp_, ocr, BOX_TRESHOLD=0.05, iou_threshold=0.7, max_new_tokens=8)
+    res = det.predict_batch(imgs, conf=0.05, iou=0.1)
+    for i, (elems, ids) in enumerate(out):
+        ref_elems, ref_ids = pipe.parse(imgs[i], ocr[i][0], ocr[i][1], BOX_TRESHOLD=0.05, iou_threshold=0.7, max_new_tokens=8,
+                                        det_boxes=res[i].boxes.xyxy.cpu())
+        _same_elements(elems, ref_elems, ids, ref_ids)
+        assert ids.shape[0] > 10
+
+
+def test_get_som_labeled_img_api():
+    import base64, io
+    from PIL import Image
+    det, cmp_ = ge.standin_models(DEV)
+    img = Image.fromarray(synth.screenshot(0))
+    texts, boxes = synth.ocr_boxes(0)
+    enc, coords, elems = get_som_labeled_img(img, det, BOX_TRESHOLD=0.05, output_coord_in_ratio=True, ocr_bbox=boxes,
+                                             caption_model_processor=cmp_, ocr_text=texts, iou_threshold=0.7, batch_size=128)
+    png = Image.open(io.BytesIO(base64.b64decode(enc)))
+    assert png.size == img.size
+    assert set(coords) == {str(i) for i in range(len(elems))}
+    assert all(set(e) == {"type", "bbox", "interactivity", "content", "source"} for e in elems)
+    kinds = [e["content"] is None for e in elems]
+    assert not any(kinds)
+    srcs = [e["source"] for e in elems]
+    assert srcs == sorted(srcs, key=lambda s: s == "box_yolo_content_yolo")   # captioned icons last (ref:util/utils.py:449)
+    # the drop-in route: reference-style processor + model.generate on host crops gives the same ids as the fused route
+    import cv2
+    from oracle import ref_restate as R
+    H, W = 1080, 1920
+    cb = torch.tensor([e["bbox"] for e in elems if e["source"] == "box_yolo_content_yolo"], dtype=torch.float32)
+    crops = [Image.fromarray(cv2.resize(np.asarray(img)[ya:yb, xa:xb], (64, 64))) for (xa, ya, xb, yb) in R.crop_boxes_int(cb, W, H)]
+    model, proc = cmp_["model"], cmp_["processor"]
+    inputs = proc(images=crops, text=["<CAPTION>"] * len(crops), return_tensors="pt", do_resize=False).to(device=model.device, dtype=torch.float16)
+    ids = model.generate(input_ids=inputs["input_ids"], pixel_values=inputs["pixel_values"], max_new_tokens=20, num_beams=1, do_sample=False)
+    texts2 = [t.strip() for t in proc.batch_decode(ids, skip_special_tokens=True)]
+    assert texts2 == [e["content"] for e in elems if e["source"] == "box_yolo_content_yolo"]
