@@ -32,6 +32,31 @@ W, H = 1920, 1080
 N_SETS = 4            # distinct input batches rotated between steps (4 x 8 x 6.2 MB = 199 MB > 126 MB L2)
 
 
+_T0 = time.perf_counter()
+
+
+def log(msg):
+    if os.environ.get("B2P_BENCH_VERBOSE", "1") != "0":
+        print(f"[bench {time.perf_counter() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+def host_threads() -> int:
+    """Usable host cores: torch's default, capped by the affinity mask and the cgroup CPU quota (oversubscribing
+    OpenMP threads on a quota-limited container stalls for minutes)."""
+    n = torch.get_num_threads()
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        q, per = Path("/sys/fs/cgroup/cpu.max").read_text().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(per))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def _dist():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -95,7 +120,7 @@ def run_reference(args):
         return
     from omniparser_b200 import synth
     from oracle.pipeline_cpu import OraclePipeline
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_threads())
     pipe = OraclePipeline()
     times, nb = [], []
     for i in range(args.warmup + args.steps):
@@ -144,7 +169,9 @@ def run_b200(args):
     from omniparser_b200 import _lib, ops, shard
     from omniparser_b200.utils import ParseTimings, parse_screenshots
     _lib.lib()   # raises if the CUDA extension is missing: no fallback
+    log("building stand-in models")
     model, cmp_ = ge.standin_models(dev, args.precision)
+    log("models ready; generating inputs")
     B = args.batch
     sets = _inputs(rank, B)
     rec = torch.zeros((B, shard.record_width(args.max_new_tokens)), dtype=torch.float32, device=dev)
@@ -166,9 +193,11 @@ def run_b200(args):
         return tm
 
     dsets = [torch.from_numpy(np.stack(s[0])).to(dev) for s in sets]
+    log("inputs ready; warm-up")
     for i in range(args.warmup):
         step(i, True)
         step(i, False)
+        log(f"warm-up step {i} done")
     torch.cuda.synchronize()
 
     def timed(resident):
@@ -197,7 +226,9 @@ def run_b200(args):
         return float(t.item()), wall, launches, sampler.summary(), tms, dict(stats)
 
     ms_res, _, launches, clocks, tms, st = timed(True)
+    log(f"resident leg: {ms_res / args.steps:.1f} ms/step")
     ms_e2e, _, _, _, tms2, _ = timed(False)
+    log(f"e2e leg: {ms_e2e / args.steps:.1f} ms/step")
     value = world * B * args.steps / (ms_res / 1e3)
     e2e = world * B * args.steps / (ms_e2e / 1e3)
 
@@ -227,6 +258,7 @@ def run_b200(args):
         torch.cuda.synchronize()
         lat.append(1e3 * (time.perf_counter() - t0))
     lat = sorted(lat[2:])
+    log("latency leg done")
 
     if rank == 0:
         line = {"metric": "screenshots/sec", "value": value, "unit": "screenshots/s", "n_gpus": world, "steps": args.steps,
@@ -253,9 +285,11 @@ def run_b200(args):
 
 def cpu_baseline(args):
     """Oracle port on the host cores, bounded sample (2 screenshots after 1 warm-up, ~10-20 s)."""
+    log("cpu baseline (oracle port on the host cores)")
     from omniparser_b200 import synth
     from oracle.pipeline_cpu import OraclePipeline
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_threads())
+    log(f"host threads: {torch.get_num_threads()} (os.cpu_count {os.cpu_count()})")
     pipe = OraclePipeline()
     ts, crops = [], []
     for i in range(3):

@@ -10,6 +10,7 @@ Only the reference's CUDA-branch input mode is planned here: 64x64 crops, ``do_r
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List
 
 import numpy as np
@@ -159,7 +160,7 @@ class FlorencePlan:
         self.T = max_new_tokens
         self.max_len = max_new_tokens + 1
         dev = self.dev
-        self.use_graph = use_graph
+        self.use_graph = use_graph and os.environ.get("B2P_NO_GRAPH") is None   # eager launches for profiling
         self.crops = torch.zeros((K, 64, 64, 3), dtype=torch.uint8, device=dev)
         self.prompt = torch.tensor(prompt_ids, dtype=torch.int32, device=dev)
         self.n_prompt = len(prompt_ids)

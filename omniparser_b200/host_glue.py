@@ -80,8 +80,73 @@ def remove_overlap_new(boxes: List[dict], iou_threshold: float, ocr_bbox: Option
     return filtered
 
 
+def remove_overlap_fast(boxes: List[dict], iou_threshold: float, ocr_bbox: List[dict]) -> List[dict]:
+    """Vectorised ``remove_overlap_new`` (same float64 operations in the same order, so results are identical to the
+    Python loops above; tests/test_host_glue_cpu.py checks equality against them and against the reference).
+    Requires dict OCR elements (the normal case, ref:util/utils.py:444)."""
+    import numpy as np
+    n, m = len(boxes), len(ocr_bbox)
+    if n == 0:
+        return list(ocr_bbox)
+    b = np.asarray([e["bbox"] for e in boxes], np.float64).reshape(n, 4)
+    area = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+
+    def inter(p, q):   # p [P,4], q [Q,4] -> [P,Q]
+        iw = np.maximum(0, np.minimum(p[:, None, 2], q[None, :, 2]) - np.maximum(p[:, None, 0], q[None, :, 0]))
+        ih = np.maximum(0, np.minimum(p[:, None, 3], q[None, :, 3]) - np.maximum(p[:, None, 1], q[None, :, 1]))
+        return iw * ih
+
+    it = inter(b, b)
+    union = ((area[:, None] + area[None, :]) - it) + 1e-6
+    pos = (area[:, None] > 0) & (area[None, :] > 0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        r1 = np.where(pos, it / area[:, None], 0.0)
+        r2 = np.where(pos, it / area[None, :], 0.0)
+        iou = np.maximum(np.maximum(it / union, r1), r2)
+    bad = (iou > iou_threshold) & (area[:, None] > area[None, :])
+    np.fill_diagonal(bad, False)
+    valid = ~bad.any(1)
+    filtered: List = list(ocr_bbox)
+    if m:
+        o = np.asarray([e["bbox"] for e in ocr_bbox], np.float64).reshape(m, 4)
+        oarea = (o[:, 2] - o[:, 0]) * (o[:, 3] - o[:, 1])
+        io = inter(b, o)                                   # [n, m]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ocr_in_icon = io / oarea[None, :] > 0.80       # is_inside(ocr, icon)
+            icon_in_ocr = io / area[:, None] > 0.80        # is_inside(icon, ocr)
+    removed = [False] * m
+    for i in range(n):
+        if not valid[i]:
+            continue
+        labels, dropped = "", False
+        if m:
+            a, c = ocr_in_icon[i], icon_in_ocr[i]
+            stop = np.flatnonzero(~a & c)
+            kstop = int(stop[0]) if stop.size else m
+            dropped = kstop < m
+            for k in np.flatnonzero(a[:kstop]):
+                labels += ocr_bbox[k]["content"] + " "
+                if not removed[k]:
+                    removed[k] = True
+        if dropped:
+            continue
+        filtered.append({"type": "icon", "bbox": boxes[i]["bbox"], "interactivity": True, "content": labels or None,
+                         "source": "box_yolo_content_ocr" if labels else "box_yolo_content_yolo"})
+    if m and any(removed):
+        # list.remove() drops the FIRST equal element; OCR elements are distinct dicts in practice, handled exactly
+        out, pending = [], [ocr_bbox[k] for k in range(m) if removed[k]]
+        for e in filtered:
+            hit = next((j for j, p in enumerate(pending) if p == e), None) if (pending and e.get("type") == "text") else None
+            if hit is not None:
+                pending.pop(hit)
+                continue
+            out.append(e)
+        filtered = out
+    return filtered
+
+
 def build_elements(xyxy_ratio: List[List[float]], ocr_ratio: Optional[List[List[float]]], ocr_text: Sequence[str],
-                   w: int, h: int, iou_threshold: float) -> Tuple[List[dict], int]:
+                   w: int, h: int, iou_threshold: float, fast: bool = True) -> Tuple[List[dict], int]:
     """ref:util/utils.py:444-451 -> (filtered_boxes_elem sorted with content-None last, starting_idx)."""
     if ocr_ratio is None:
         # ref:util/utils.py:437-444 raises TypeError here (zip over None); the drop-in accepts "no OCR" as an empty list
@@ -90,7 +155,10 @@ def build_elements(xyxy_ratio: List[List[float]], ocr_ratio: Optional[List[List[
                 for box, txt in zip(ocr_ratio, ocr_text) if int_box_area(box, w, h) > 0]
     icon_elem = [{"type": "icon", "bbox": box, "interactivity": True, "content": None}
                  for box in xyxy_ratio if int_box_area(box, w, h) > 0]
-    filtered = remove_overlap_new(icon_elem, iou_threshold, ocr_elem)
+    if fast and ocr_elem:
+        filtered = remove_overlap_fast(icon_elem, iou_threshold, ocr_elem)
+    else:
+        filtered = remove_overlap_new(icon_elem, iou_threshold, ocr_elem)
     if not ocr_elem:
         # normalise the bare-list quirk so downstream code sees dicts
         filtered = [{"type": "icon", "bbox": b, "interactivity": True, "content": None, "source": "box_yolo_content_yolo"}

@@ -11,6 +11,7 @@ Topology: WongKinYiu/yolov9 ``yolov9-e.yaml`` (restated in oracle/yolov9e.py, SU
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List
 
 import numpy as np
@@ -164,7 +165,7 @@ class YoloPlan:
         self.lut = torch.from_numpy(lut.copy()).to(self.dev)
         self._build()
         self.graph = None
-        self.use_graph = use_graph
+        self.use_graph = use_graph and os.environ.get("B2P_NO_GRAPH") is None   # eager launches for profiling
 
     # -- helpers that append launches
     def _fm(self, C, H, W):

@@ -14,6 +14,7 @@ W, H = 1920, 1080
 
 
 def _case(seed, n_icon=70, n_ocr=20):
+    n_icon = n_icon + 30 * (seed % 3)
     rng = np.random.default_rng(seed)
     xy = rng.uniform(0, 0.9, size=(n_icon, 2))
     wh = rng.uniform(0.0, 0.08, size=(n_icon, 2))
@@ -42,8 +43,9 @@ def test_build_elements_matches_oracle_restatement(seed, thr):
     whwh = torch.Tensor([W, H, W, H])
     oratio = (torch.tensor(ob) / whwh).tolist()
     a, start = host_glue.build_elements(icons.tolist(), oratio, texts, W, H, thr)
+    slow, _ = host_glue.build_elements(icons.tolist(), oratio, texts, W, H, thr, fast=False)
     b = pipeline_cpu.build_elements(icons.tolist(), oratio, texts, W, H, thr)
-    assert a == b
+    assert a == b and a == slow
     assert start == next((i for i, e in enumerate(a) if e["content"] is None), -1)
 
 
