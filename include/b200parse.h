@@ -79,6 +79,8 @@ int b2p_layernorm(const float* x, long long ldx, const float* gamma, const float
                   void* out16, long long ld16, float* out32, long long ld32, int split, b2p_stream_t stream);
 int b2p_dwconv3x3_res(const float* x, int B, int H, int W, int C, const float* w9c, const float* bias, float* y,
                       b2p_stream_t stream);
+int b2p_dwconv_ln(const float* x, int B, int H, int W, int C, const float* w9c, const float* bias, float* y,
+                  const float* gamma, const float* beta, float eps, void* out16, int split, b2p_stream_t stream);
 int b2p_window_attn(const float* qkv, const float* qkv_bias, int B, int H, int W, int C, int heads, int win, void* out,
                     int split, b2p_stream_t stream);
 int b2p_channel_attn(const float* qkv, int B, int N, int C, int groups, void* out, int split, b2p_stream_t stream);

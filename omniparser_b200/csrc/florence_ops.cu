@@ -30,6 +30,18 @@ __device__ __forceinline__ void store_act(__half* row, int c, int split, float v
   }
 }
 
+// 4 consecutive channels (c % 4 == 0) as one 8-byte store per copy
+__device__ __forceinline__ void store_act4(__half* row, int c, int split, const float4& v) {
+  __align__(8) __half2 h[2] = {__floats2half2_rn(v.x, v.y), __floats2half2_rn(v.z, v.w)};
+  *reinterpret_cast<uint2*>(row + c) = *reinterpret_cast<const uint2*>(h);
+  if (split) {
+    *reinterpret_cast<uint2*>(row + split + c) = *reinterpret_cast<const uint2*>(h);
+    const float2 a = __half22float2(h[0]), b = __half22float2(h[1]);
+    __align__(8) __half2 l[2] = {__floats2half2_rn(v.x - a.x, v.y - a.y), __floats2half2_rn(v.z - b.x, v.w - b.y)};
+    *reinterpret_cast<uint2*>(row + 2 * split + c) = *reinterpret_cast<const uint2*>(l);
+  }
+}
+
 // ---------------------------------------------------------------------------------------- LayerNorm
 // one warp per row; x fp32 [T][ldx]; writes fp16 and/or fp32 (nn.LayerNorm, biased variance, eps inside sqrt)
 __global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ g,
@@ -38,17 +50,79 @@ __global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, con
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= T) return;
-  const float* xr = x + (long long)row * ldx;
+  const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * ldx);
+  const int C4 = C >> 2;
+  float4 v[8];   // C <= 1024
   float s = 0.f;
-  for (int c = lane; c < C; c += 32) s += xr[c];
+  int n = 0;
+  for (int c = lane; c < C4; c += 32, ++n) { v[n] = xr[c]; s += (v[n].x + v[n].y) + (v[n].z + v[n].w); }
   const float mean = warp_sum(s) / float(C);
-  float v = 0.f;
-  for (int c = lane; c < C; c += 32) { const float d = xr[c] - mean; v += d * d; }
-  const float rstd = rsqrtf(warp_sum(v) / float(C) + eps);
-  for (int c = lane; c < C; c += 32) {
-    const float y = (xr[c] - mean) * rstd * g[c] + b[c];
-    if (o16) store_act(o16 + (long long)row * ld16, c, split, y);
-    if (o32) o32[(long long)row * ld32 + c] = y;
+  float q = 0.f;
+  for (int i = 0; i < n; ++i) {
+    const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+    q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / float(C) + eps);
+  n = 0;
+  for (int c = lane; c < C4; c += 32, ++n) {
+    const float4 gg = reinterpret_cast<const float4*>(g)[c], bb = reinterpret_cast<const float4*>(b)[c];
+    float4 y;
+    y.x = (v[n].x - mean) * rstd * gg.x + bb.x; y.y = (v[n].y - mean) * rstd * gg.y + bb.y;
+    y.z = (v[n].z - mean) * rstd * gg.z + bb.z; y.w = (v[n].w - mean) * rstd * gg.w + bb.w;
+    if (o16) store_act4(o16 + (long long)row * ld16, 4 * c, split, y);
+    if (o32) reinterpret_cast<float4*>(o32 + (long long)row * ld32)[c] = y;
+  }
+}
+
+// Fused DaViT pre-block: y = dwconv3x3(x) + bias + x (fp32, the new residual stream) and h = LayerNorm(y) as the next
+// GEMM operand.  One warp per token; channels in float4 lanes (C <= 1024).
+__global__ void dwconv_ln_kernel(const float* __restrict__ x, int B, int H, int W, int C, const float* __restrict__ w9c,
+                                 const float* __restrict__ bias, float* __restrict__ y, const float* __restrict__ g,
+                                 const float* __restrict__ bt, float eps, __half* __restrict__ o16, int split) {
+  const long long tok = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (tok >= (long long)B * H * W) return;
+  const int xx = int(tok % W), yy = int((tok / W) % H);
+  const int C4 = C >> 2;
+  float4 v[8];
+  float s = 0.f;
+  int n = 0;
+  for (int c = lane; c < C4; c += 32, ++n) {
+    float4 acc = reinterpret_cast<const float4*>(bias)[c];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int sy = yy + ky - 1;
+      if (sy < 0 || sy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int sx = xx + kx - 1;
+        if (sx < 0 || sx >= W) continue;
+        const float4 xv = reinterpret_cast<const float4*>(x + (tok + (long long)(ky - 1) * W + (kx - 1)) * C)[c];
+        const float4 wv = reinterpret_cast<const float4*>(w9c + (ky * 3 + kx) * C)[c];
+        acc.x += xv.x * wv.x; acc.y += xv.y * wv.y; acc.z += xv.z * wv.z; acc.w += xv.w * wv.w;
+      }
+    }
+    const float4 xc = reinterpret_cast<const float4*>(x + tok * C)[c];
+    acc.x += xc.x; acc.y += xc.y; acc.z += xc.z; acc.w += xc.w;
+    reinterpret_cast<float4*>(y + tok * C)[c] = acc;
+    v[n] = acc;
+    s += (acc.x + acc.y) + (acc.z + acc.w);
+  }
+  const float mean = warp_sum(s) / float(C);
+  float q = 0.f;
+  for (int i = 0; i < n; ++i) {
+    const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+    q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / float(C) + eps);
+  n = 0;
+  __half* orow = o16 + tok * (split ? 3 * C : C);
+  for (int c = lane; c < C4; c += 32, ++n) {
+    const float4 gg = reinterpret_cast<const float4*>(g)[c], bb = reinterpret_cast<const float4*>(bt)[c];
+    float4 o;
+    o.x = (v[n].x - mean) * rstd * gg.x + bb.x; o.y = (v[n].y - mean) * rstd * gg.y + bb.y;
+    o.z = (v[n].z - mean) * rstd * gg.z + bb.z; o.w = (v[n].w - mean) * rstd * gg.w + bb.w;
+    store_act4(orow, 4 * c, split, o);
   }
 }
 
@@ -88,7 +162,8 @@ __global__ void dwconv3x3_res_kernel(const float* __restrict__ x, int B, int H, 
 template <int D>
 __global__ void window_attn_kernel(const float* __restrict__ qkv, const float* __restrict__ qkv_bias, int B, int H,
                                    int W, int C, int heads, int win, __half* __restrict__ out, int split) {
-  extern __shared__ float sm[];
+  extern __shared__ float4 sm4[];
+  constexpr int D4 = D / 4;
   const int nwx = (W + win - 1) / win, nwy = (H + win - 1) / win;
   int bid = blockIdx.x;
   const int head = bid % heads; bid /= heads;
@@ -98,50 +173,68 @@ __global__ void window_attn_kernel(const float* __restrict__ qkv, const float* _
   const int y0 = wy * win, x0 = wx * win;
   const int ny = min(win, H - y0), nx = min(win, W - x0);
   const int nreal = ny * nx, npad = win * win - nreal;
-  float* Ks = sm;                       // [nreal][D]
-  float* Vs = sm + win * win * D;       // [nreal][D]
-  for (int i = threadIdx.x; i < nreal * D; i += blockDim.x) {
-    const int t = i / D, d = i - t * D;
+  float4* Ks = sm4;                       // [nreal][D4]
+  float4* Vs = sm4 + win * win * D4;      // [nreal][D4]
+  for (int i = threadIdx.x; i < nreal * D4; i += blockDim.x) {
+    const int t = i / D4, d = i - t * D4;
     const long long tok = ((long long)b * H + y0 + t / nx) * W + x0 + t % nx;
-    Ks[i] = qkv[tok * 3 * C + C + head * D + d];
-    Vs[i] = qkv[tok * 3 * C + 2 * C + head * D + d];
+    Ks[i] = reinterpret_cast<const float4*>(qkv + tok * 3 * C + C + head * D)[d];
+    Vs[i] = reinterpret_cast<const float4*>(qkv + tok * 3 * C + 2 * C + head * D)[d];
   }
   __syncthreads();
   const float scale = rsqrtf(float(D));
   for (int t = threadIdx.x; t < nreal; t += blockDim.x) {
     const long long tok = ((long long)b * H + y0 + t / nx) * W + x0 + t % nx;
-    float q[D], acc[D];
+    float4 q[D4], acc[D4];
 #pragma unroll
-    for (int d = 0; d < D; ++d) { q[d] = qkv[tok * 3 * C + head * D + d] * scale; acc[d] = 0.f; }
+    for (int d = 0; d < D4; ++d) {
+      q[d] = reinterpret_cast<const float4*>(qkv + tok * 3 * C + head * D)[d];
+      q[d].x *= scale; q[d].y *= scale; q[d].z *= scale; q[d].w *= scale;
+      acc[d] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     float m = -INFINITY, l = 0.f;
     if (npad > 0) {
       float s = 0.f;
 #pragma unroll
-      for (int d = 0; d < D; ++d) s += q[d] * qkv_bias[C + head * D + d];
+      for (int d = 0; d < D4; ++d) {
+        const float4 kb = reinterpret_cast<const float4*>(qkv_bias + C + head * D)[d];
+        s += (q[d].x * kb.x + q[d].y * kb.y) + (q[d].z * kb.z + q[d].w * kb.w);
+      }
       m = s;
       l = float(npad);
 #pragma unroll
-      for (int d = 0; d < D; ++d) acc[d] = float(npad) * qkv_bias[2 * C + head * D + d];
+      for (int d = 0; d < D4; ++d) {
+        const float4 vb = reinterpret_cast<const float4*>(qkv_bias + 2 * C + head * D)[d];
+        acc[d] = make_float4(l * vb.x, l * vb.y, l * vb.z, l * vb.w);
+      }
     }
     for (int j = 0; j < nreal; ++j) {
       float s = 0.f;
 #pragma unroll
-      for (int d = 0; d < D; ++d) s += q[d] * Ks[j * D + d];
+      for (int d = 0; d < D4; ++d) {
+        const float4 kk = Ks[j * D4 + d];
+        s += (q[d].x * kk.x + q[d].y * kk.y) + (q[d].z * kk.z + q[d].w * kk.w);
+      }
       if (s > m) {
         const float r = __expf(m - s);
         l *= r;
 #pragma unroll
-        for (int d = 0; d < D; ++d) acc[d] *= r;
+        for (int d = 0; d < D4; ++d) { acc[d].x *= r; acc[d].y *= r; acc[d].z *= r; acc[d].w *= r; }
         m = s;
       }
       const float p = __expf(s - m);
       l += p;
 #pragma unroll
-      for (int d = 0; d < D; ++d) acc[d] += p * Vs[j * D + d];
+      for (int d = 0; d < D4; ++d) {
+        const float4 vv = Vs[j * D4 + d];
+        acc[d].x += p * vv.x; acc[d].y += p * vv.y; acc[d].z += p * vv.z; acc[d].w += p * vv.w;
+      }
     }
     const float inv = 1.f / l;
+    __half* orow = out + tok * (split ? 3 * C : C);
 #pragma unroll
-    for (int d = 0; d < D; ++d) store_act(out + tok * (split ? 3 * C : C), head * D + d, split, acc[d] * inv);
+    for (int d = 0; d < D4; ++d)
+      store_act4(orow, head * D + 4 * d, split, make_float4(acc[d].x * inv, acc[d].y * inv, acc[d].z * inv, acc[d].w * inv));
   }
 }
 
@@ -149,15 +242,15 @@ __global__ void window_attn_kernel(const float* __restrict__ qkv, const float* _
 // hf:models/florence2/modeling_florence2.py:228-264: per (batch, group) a d x d (d = 32) attention over channels:
 // S[i][j] = N^-0.5 * sum_n q[n][i] k[n][j]; P = softmax_j(S); out[n][i] = sum_j P[i][j] v[n][j].
 // One CTA (1024 threads = 32 x 32) per (batch, group); tokens streamed through shared memory in chunks.
-__global__ void __launch_bounds__(1024) channel_attn_kernel(const float* __restrict__ qkv, int N, int C, int groups,
-                                                            __half* __restrict__ out, int split) {
+__global__ void __launch_bounds__(256) channel_attn_kernel(const float* __restrict__ qkv, int N, int C, int groups,
+                                                           __half* __restrict__ out, int split) {
   constexpr int D = 32, CH = 64;
   __shared__ float qs[CH][D + 1], ks[CH][D + 1];
   __shared__ float P[D][D + 1];
   const int g = blockIdx.x % groups, b = blockIdx.x / groups;
-  const int i = threadIdx.x >> 5, j = threadIdx.x & 31;
+  const int w = threadIdx.x >> 5, j = threadIdx.x & 31;   // warp w owns rows i = 4w .. 4w+3, lane = column j
   const float* base = qkv + (long long)b * N * 3 * C;
-  float s = 0.f;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
   for (int n0 = 0; n0 < N; n0 += CH) {
     const int cn = min(CH, N - n0);
     for (int t = threadIdx.x; t < cn * D; t += blockDim.x) {
@@ -166,25 +259,33 @@ __global__ void __launch_bounds__(1024) channel_attn_kernel(const float* __restr
       ks[n][d] = base[(long long)(n0 + n) * 3 * C + C + g * D + d];
     }
     __syncthreads();
-    for (int n = 0; n < cn; ++n) s += qs[n][i] * ks[n][j];
+    for (int n = 0; n < cn; ++n) {
+      const float kv = ks[n][j];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) s[r] += qs[n][4 * w + r] * kv;
+    }
     __syncthreads();
   }
-  s *= rsqrtf(float(N));
-  const float m = warp_max(s);
-  const float e = __expf(s - m);
-  const float l = warp_sum(e);
-  P[i][j] = e / l;
-  __syncthreads();
-  // out[n][i]: thread (n_local = i, channel = j) over token chunks of 32
-  for (int n0 = 0; n0 < N; n0 += 32) {
-    const int n = n0 + i;
-    if (n < N) {
-      const float* vr = base + (long long)n * 3 * C + 2 * C + g * D;
-      float acc = 0.f;
+  const float sc = rsqrtf(float(N));
 #pragma unroll
-      for (int jj = 0; jj < D; ++jj) acc += P[j][jj] * vr[jj];
-      store_act(out + ((long long)b * N + n) * (split ? 3 * C : C), g * D + j, split, acc);
-    }
+  for (int r = 0; r < 4; ++r) {
+    const float v = s[r] * sc;
+    const float m = warp_max(v);
+    const float e = __expf(v - m);
+    P[4 * w + r][j] = e / warp_sum(e);
+  }
+  __syncthreads();
+  // out[n][g*32 + j] = sum_jj P[j][jj] v[n][jj]: 8 tokens per pass (one per warp), lane = output channel j
+  float pr[D];
+#pragma unroll
+  for (int jj = 0; jj < D; ++jj) pr[jj] = P[j][jj];
+  for (int n = w; n < N; n += 8) {
+    const float* vr = base + (long long)n * 3 * C + 2 * C + g * D;
+    const float vj = vr[j];
+    float acc = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < D; ++jj) acc += pr[jj] * __shfl_sync(0xffffffffu, vj, jj);
+    store_act(out + ((long long)b * N + n) * (split ? 3 * C : C), g * D + j, split, acc);
   }
 }
 
@@ -389,8 +490,19 @@ extern "C" {
 int b2p_layernorm(const float* x, long long ldx, const float* gamma, const float* beta, float eps, int T, int C,
                   void* out16, long long ld16, float* out32, long long ld32, int split, cudaStream_t st) {
   if (T <= 0) return 0;
+  if (C % 4 || C > 1024 || (ldx % 4) || (ld32 % 4) || (ld16 % 4)) return set_error("layernorm: C, ld must be multiples of 4, C <= 1024");
   const int wpb = 8;
   layernorm_kernel<<<(T + wpb - 1) / wpb, wpb * 32, 0, st>>>(x, ldx, gamma, beta, eps, T, C, (__half*)out16, ld16, out32, ld32, split ? C : 0);
+  B2P_CHECK_LAUNCH();
+  return 0;
+}
+
+int b2p_dwconv_ln(const float* x, int B, int H, int W, int C, const float* w9c, const float* bias, float* y,
+                  const float* gamma, const float* beta, float eps, void* out16, int split, cudaStream_t st) {
+  if (C % 4 || C > 1024) return set_error("dwconv_ln: C must be a multiple of 4 and <= 1024");
+  const long long T = (long long)B * H * W;
+  const int wpb = 8;
+  dwconv_ln_kernel<<<int((T + wpb - 1) / wpb), wpb * 32, 0, st>>>(x, B, H, W, C, w9c, bias, y, gamma, beta, eps, (__half*)out16, split ? C : 0);
   B2P_CHECK_LAUNCH();
   return 0;
 }
@@ -420,7 +532,7 @@ int b2p_window_attn(const float* qkv, const float* qkv_bias, int B, int H, int W
 
 int b2p_channel_attn(const float* qkv, int B, int N, int C, int groups, void* out, int split, cudaStream_t st) {
   if (C / groups != 32) return set_error("channel_attn: channels per group must be 32");
-  channel_attn_kernel<<<B * groups, 1024, 0, st>>>(qkv, N, C, groups, (__half*)out, split ? C : 0);
+  channel_attn_kernel<<<B * groups, 256, 0, st>>>(qkv, N, C, groups, (__half*)out, split ? C : 0);
   B2P_CHECK_LAUNCH();
   return 0;
 }

@@ -29,6 +29,7 @@ struct GemmArgs {
   int mode, M, N, num_kb, bk, bn;
   int cin_blocks, tw, th, tiles_x, tiles_y, Ho, Wo, batch;
   int m_tiles, n_tiles, stages, ldpar;
+  int ksplit, kb_per;    // split-K: work item = (m tile, n tile, k slice); the last CTA of a tile reduces + stores
   uint32_t a_bytes, b_bytes, b_slot;
   uint32_t idesc;
   uint64_t desc_hi;   // high 32 bits of the smem matrix descriptor (SBO, version, layout), shifted in place
@@ -40,6 +41,8 @@ struct GemmArgs {
   long long ldr;
   int act, vec_ok;
   int split;   // > 0: fp16 output in the fp16x3 operand layout [hi | hi | lo] with logical width `split`
+  float* ws;   // split-K partial tiles [tile][slice][128][bn] fp32
+  int* counters;   // split-K arrival counters per output tile (self-resetting)
 };
 
 // Shared-memory matrix descriptor (PTX ISA "tcgen05 matrix descriptor"), K-major operand, swizzled:
@@ -58,10 +61,118 @@ __host__ inline uint32_t make_idesc(int bn, int bf16) {
   return (1u << 4) | (f << 7) | (f << 10) | (uint32_t(bn >> 3) << 17) | (uint32_t(kTileM >> 4) << 24);
 }
 
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float act_fn(float x, int act) {
-  if (act == 1) return __fdividef(x, 1.0f + __expf(-x));               // SiLU (MUFU ex2 + rcp; ~2 ulp)
-  if (act == 2) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));  // exact GELU
+  if (act == 1) return x * fast_rcp(1.0f + fast_ex2(x * -1.4426950408889634f));   // SiLU: 2 MUFU + 3 FP32, ~2 ulp
+  if (act == 2) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));        // exact GELU (Florence-2 parity)
   return x;
+}
+
+struct EpiCtx {
+  __half* outh; float* outf; const __half* resh; const float* resf;
+};
+
+// bias + activation + residual + store of 16 consecutive output columns [nb, nb+16) of one row.
+__device__ __forceinline__ void epi_store16(const GemmArgs& g, const EpiCtx& e, float (&x)[16], int nb, long long pix, bool valid) {
+  const bool full = (nb + 16 <= g.N);
+  if (full && g.vec_ok) {
+    if (g.bias) {
+      const float4* bp = reinterpret_cast<const float4*>(g.bias + nb);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 b = __ldg(bp + q);
+        x[4 * q + 0] += b.x; x[4 * q + 1] += b.y; x[4 * q + 2] += b.z; x[4 * q + 3] += b.w;
+      }
+    }
+    if (g.act) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) x[j] = act_fn(x[j], g.act);
+    }
+    if (!valid) return;
+    if (g.res) {
+      if (g.out_f32) {
+        const float4* rp = reinterpret_cast<const float4*>(e.resf + pix * g.ldr + nb);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 t = rp[q];
+          x[4 * q] += t.x; x[4 * q + 1] += t.y; x[4 * q + 2] += t.z; x[4 * q + 3] += t.w;
+        }
+      } else {
+        const uint4* rp = reinterpret_cast<const uint4*>(e.resh + pix * g.ldr + nb);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const uint4 t = rp[q];
+          const __half2* hp = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = __half22float2(hp[k]);
+            x[8 * q + 2 * k] += f.x;
+            x[8 * q + 2 * k + 1] += f.y;
+          }
+        }
+      }
+    }
+    if (g.out_f32) {
+      float4* op = reinterpret_cast<float4*>(e.outf + pix * g.ldc + nb);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) op[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+    } else {
+      uint4 pk[2];
+      __half2* hp = reinterpret_cast<__half2*>(pk);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) hp[k] = __floats2half2_rn(x[2 * k], x[2 * k + 1]);
+      uint4* op = reinterpret_cast<uint4*>(e.outh + pix * g.ldc + nb);
+      op[0] = pk[0];
+      op[1] = pk[1];
+      if (g.split) {
+        uint4* o2 = reinterpret_cast<uint4*>(e.outh + pix * g.ldc + g.split + nb);
+        o2[0] = pk[0];
+        o2[1] = pk[1];
+        uint4 lo[2];
+        __half2* lp = reinterpret_cast<__half2*>(lo);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float2 hf = __half22float2(hp[k]);
+          lp[k] = __floats2half2_rn(x[2 * k] - hf.x, x[2 * k + 1] - hf.y);
+        }
+        uint4* o3 = reinterpret_cast<uint4*>(e.outh + pix * g.ldc + 2 * g.split + nb);
+        o3[0] = lo[0];
+        o3[1] = lo[1];
+      }
+    }
+  } else {
+    // ragged tail / unaligned destination: scalar path
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int n = nb + j;
+      if (n < g.N) {
+        float t = x[j];
+        if (g.bias) t += __ldg(g.bias + n);
+        t = act_fn(t, g.act);
+        if (valid) {
+          if (g.res) t += g.out_f32 ? e.resf[pix * g.ldr + n] : __half2float(e.resh[pix * g.ldr + n]);
+          if (g.out_f32) e.outf[pix * g.ldc + n] = t;
+          else {
+            const __half hh = __float2half_rn(t);
+            e.outh[pix * g.ldc + n] = hh;
+            if (g.split) {
+              e.outh[pix * g.ldc + g.split + n] = hh;
+              e.outh[pix * g.ldc + 2 * g.split + n] = __float2half_rn(t - __half2float(hh));
+            }
+          }
+        }
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -75,6 +186,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t bar_tfull = bar_empty + 8 * g.stages;
   const uint32_t bar_tempty = bar_tfull + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * g.stages + 4);
+  volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -103,7 +215,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = g.m_tiles * g.n_tiles;
+  const int total_items = g.m_tiles * g.n_tiles * g.ksplit;   // item = (mt * n_tiles + nt) * ksplit + ks
   const uint32_t smem_base = smem_u32(smem);
 
   if (warp == 0) {
@@ -111,7 +223,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // ------------------------------------------------------------ TMA producer
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int ks = item % g.ksplit;
+        const int tile = item / g.ksplit;
         const int nt = tile % g.n_tiles;
         const int mt = tile / g.n_tiles;
         const int n0 = nt * g.bn;
@@ -123,7 +237,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           y0 = (r / g.tiles_x) * g.th;
           x0 = (r % g.tiles_x) * g.tw;
         }
-        for (int kb = 0; kb < g.num_kb; ++kb) {
+        const int kb0 = ks * g.kb_per, kb1 = min(g.num_kb, kb0 + g.kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t fb = bar_full + 8 * stage;
           const uint32_t sa = smem_base + stage * stage_bytes;
@@ -157,11 +272,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int acc = 0;
       uint32_t acc_phase = 0;
       const int ksteps = g.bk / 16;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int ks = item % g.ksplit;
+        const int kb0 = ks * g.kb_per, kb1 = min(g.num_kb, kb0 + g.kb_per);
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(acc * 256);
-        for (int kb = 0; kb < g.num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * stage_bytes;
@@ -170,7 +287,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint64_t db = g.desc_hi | uint64_t((sb & 0x3FFFF) >> 4);
           for (int k = 0; k < ksteps; ++k) {
             // advancing K inside the swizzle span = +32 B on the start address (encoded >> 4)
-            umma_f16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), g.idesc, (kb | k) != 0);
+            umma_f16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), g.idesc, ((kb - kb0) | k) != 0);
           }
           umma_commit(bar_empty + 8 * stage);
           if (++stage == g.stages) { stage = 0; phase ^= 1; }
@@ -186,11 +303,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int chalf = (warp - 2) >> 2;   // which 16-column chunks this warp owns (even / odd)
     int acc = 0;
     uint32_t acc_phase = 0;
-    __half* outh = reinterpret_cast<__half*>(g.out);
-    float* outf = reinterpret_cast<float*>(g.out);
-    const __half* resh = reinterpret_cast<const __half*>(g.res);
-    const float* resf = reinterpret_cast<const float*>(g.res);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    EpiCtx e;
+    e.outh = reinterpret_cast<__half*>(g.out);
+    e.outf = reinterpret_cast<float*>(g.out);
+    e.resh = reinterpret_cast<const __half*>(g.res);
+    e.resf = reinterpret_cast<const float*>(g.res);
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int ks = item % g.ksplit;
+      const int tile = item / g.ksplit;
       const int nt = tile % g.n_tiles;
       const int mt = tile / g.n_tiles;
       const int n0 = nt * g.bn;
@@ -213,114 +333,65 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(grp * 32) << 16) + uint32_t(acc * 256);
-      for (int c = chalf * 16; c < g.bn; c += 32) {
-        uint32_t v[16];
-        tmem_ld16(t_row + c, v);
-        tmem_ld_wait();
-        const int nb = n0 + c;
-        if (nb >= g.N) continue;   // warp-uniform
-        float x[16];
-        const bool full = (nb + 16 <= g.N);
-        if (full && g.vec_ok) {
-          if (g.bias) {
-            const float4* bp = reinterpret_cast<const float4*>(g.bias + nb);
+      if (g.ksplit == 1) {
+        for (int c = chalf * 16; c < g.bn; c += 32) {
+          uint32_t v[16];
+          tmem_ld16(t_row + c, v);
+          tmem_ld_wait();
+          if (n0 + c >= g.N) continue;   // warp-uniform
+          float x[16];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 b = __ldg(bp + q);
-              x[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + b.x;
-              x[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + b.y;
-              x[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + b.z;
-              x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + b.w;
-            }
-          } else {
+          for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]);
+          epi_store16(g, e, x, n0 + c, pix, valid);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      } else {
+        // split-K: park the raw partial tile, the last-arriving CTA of this output tile reduces in slice order
+        float* wsp = g.ws + ((size_t(tile) * g.ksplit + ks) * kTileM + r) * g.bn;
+        for (int c = chalf * 16; c < g.bn; c += 32) {
+          uint32_t v[16];
+          tmem_ld16(t_row + c, v);
+          tmem_ld_wait();
+          float4* wp = reinterpret_cast<float4*>(wsp + c);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]);
-          }
-          if (g.act) {
+          for (int q = 0; q < 4; ++q)
+            wp[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 64) {
+          const int old = atomicAdd(g.counters + tile, 1);
+          const int last = (old == g.ksplit - 1);
+          if (last) g.counters[tile] = 0;   // self-reset for the next launch / graph replay
+          *last_flag = last;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (*last_flag) {
+          __threadfence();
+          const float* base = g.ws + (size_t(tile) * g.ksplit * kTileM + r) * g.bn;
+          for (int c = chalf * 16; c < g.bn; c += 32) {
+            if (n0 + c >= g.N) continue;
+            float x[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) x[j] = act_fn(x[j], g.act);
-          }
-          if (valid) {
-            if (g.res) {
-              if (g.out_f32) {
-                const float4* rp = reinterpret_cast<const float4*>(resf + pix * g.ldr + nb);
+            for (int j = 0; j < 16; ++j) x[j] = 0.f;
+            for (int s = 0; s < g.ksplit; ++s) {
+              const float4* pp = reinterpret_cast<const float4*>(base + size_t(s) * kTileM * g.bn + c);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float4 t = rp[q];
-                  x[4 * q] += t.x; x[4 * q + 1] += t.y; x[4 * q + 2] += t.z; x[4 * q + 3] += t.w;
-                }
-              } else {
-                const uint4* rp = reinterpret_cast<const uint4*>(resh + pix * g.ldr + nb);
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                  const uint4 t = rp[q];
-                  const __half2* hp = reinterpret_cast<const __half2*>(&t);
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 f = __half22float2(hp[e]);
-                    x[8 * q + 2 * e] += f.x;
-                    x[8 * q + 2 * e + 1] += f.y;
-                  }
-                }
+              for (int q = 0; q < 4; ++q) {
+                const float4 t = __ldcg(pp + q);
+                x[4 * q] += t.x; x[4 * q + 1] += t.y; x[4 * q + 2] += t.z; x[4 * q + 3] += t.w;
               }
             }
-            if (g.out_f32) {
-              float4* op = reinterpret_cast<float4*>(outf + pix * g.ldc + nb);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) op[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
-            } else {
-              uint4 pk[2];
-              __half2* hp = reinterpret_cast<__half2*>(pk);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) hp[e] = __floats2half2_rn(x[2 * e], x[2 * e + 1]);
-              uint4* op = reinterpret_cast<uint4*>(outh + pix * g.ldc + nb);
-              op[0] = pk[0];
-              op[1] = pk[1];
-              if (g.split) {
-                uint4* o2 = reinterpret_cast<uint4*>(outh + pix * g.ldc + g.split + nb);
-                o2[0] = pk[0];
-                o2[1] = pk[1];
-                uint4 lo[2];
-                __half2* lp = reinterpret_cast<__half2*>(lo);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const float2 hf = __half22float2(hp[e]);
-                  lp[e] = __floats2half2_rn(x[2 * e] - hf.x, x[2 * e + 1] - hf.y);
-                }
-                uint4* o3 = reinterpret_cast<uint4*>(outh + pix * g.ldc + 2 * g.split + nb);
-                o3[0] = lo[0];
-                o3[1] = lo[1];
-              }
-            }
-          }
-        } else {
-          // ragged tail / unaligned destination: scalar path
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = nb + j;
-            if (n < g.N) {
-              float t = __uint_as_float(v[j]);
-              if (g.bias) t += __ldg(g.bias + n);
-              t = act_fn(t, g.act);
-              if (valid) {
-                if (g.res) t += g.out_f32 ? resf[pix * g.ldr + n] : __half2float(resh[pix * g.ldr + n]);
-                if (g.out_f32) outf[pix * g.ldc + n] = t;
-                else {
-                  const __half hh = __float2half_rn(t);
-                  outh[pix * g.ldc + n] = hh;
-                  if (g.split) {
-                    outh[pix * g.ldc + g.split + n] = hh;
-                    outh[pix * g.ldc + 2 * g.split + n] = __float2half_rn(t - __half2float(hh));
-                  }
-                }
-              }
-            }
+            epi_store16(g, e, x, n0 + c, pix, valid);
           }
         }
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // last_flag is reused by the next item
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -369,6 +440,11 @@ static int encode(CUtensorMap* m, int bf16, int rank, const void* base, const cu
 }
 
 static int g_num_sms = 0;
+static float* g_ws = nullptr;
+static int* g_counters = nullptr;
+static constexpr size_t kWsBytes = size_t(96) << 20;     // split-K partial tiles
+static constexpr int kMaxCounterTiles = 1 << 16;
+
 static int g_max_smem = 0;
 
 static int device_setup() {
@@ -382,30 +458,52 @@ static int device_setup() {
   g_max_smem = int(p.sharedMemPerBlockOptin);
   if (cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem) != cudaSuccess)
     return set_error("cudaFuncSetAttribute(max dynamic smem) failed");
+  if (cudaMalloc(&g_ws, kWsBytes) != cudaSuccess || cudaMalloc(&g_counters, kMaxCounterTiles * sizeof(int)) != cudaSuccess)
+    return set_error("cudaMalloc for the split-K workspace failed");
+  cudaMemset(g_counters, 0, kMaxCounterTiles * sizeof(int));
   return 0;
 }
 
-static int pick_bn(int N, int m_tiles, int num_kb, int bn_max) {
+
+// Choose the N tile and the split-K factor with a small time model (microseconds per CTA):
+//   per k-block  max(MMA issue, smem fill): MMA = bn*bk/32 cycles at ~1.9 GHz; fill = (A + B bytes) / ~70 GB/s per SM
+//   (measured: L2 -> SM delivery tops out near 12 TB/s chip-wide, profiles/r1_gemm_notes.md)
+//   per item     ~2.5 us pipeline fill/drain + epilogue (~0.012 us per output column) + split-K park/reduce.
+static void pick_tiling(int N, int m_tiles, int num_kb, int bk, uint32_t a_bytes, int bn_max, bool allow_split, int* bn_out,
+                        int* ksplit_out) {
   static const int cand[] = {256, 192, 128, 96, 64, 48, 32, 16};
   const int n16 = (N + 15) / 16 * 16;
-  long best_cost = -1;
-  int best = 16;
+  double best_cost = -1;
+  int best = 16, best_ks = 1;
   for (int c : cand) {
     if (c > bn_max) continue;
     if (c > n16 && c != 16) {
-      // allow the smallest candidate that still covers N
       bool smaller_covers = false;
       for (int d : cand) if (d < c && d >= n16) smaller_covers = true;
       if (smaller_covers) continue;
     }
     const long n_tiles = (N + c - 1) / c;
     const long tiles = n_tiles * m_tiles;
-    const long waves = (tiles + g_num_sms - 1) / g_num_sms;
-    const long per_tile = long(num_kb) * (c > 64 ? c : 64) + 700;   // MMA issue floor ~ N/2 cyc per K16, + prologue/epilogue
-    const long cost = waves * per_tile;
-    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = c; }
+    const double t_mma = double(c) * bk / 32.0 / 1900.0;
+    const double t_fill = (double(a_bytes) + double(c) * bk * 2.0) / 70000.0;
+    const double t_kb = t_mma > t_fill ? t_mma : t_fill;
+    int max_ks = 1;
+    if (allow_split && tiles < g_num_sms && tiles <= kMaxCounterTiles) max_ks = num_kb / 2 > 1 ? num_kb / 2 : 1;
+    if (max_ks > 32) max_ks = 32;
+    for (int ks = 1; ks <= max_ks; ++ks) {
+      const int kb_per = (num_kb + ks - 1) / ks;
+      const int ks_eff = (num_kb + kb_per - 1) / kb_per;
+      if (ks_eff != ks) continue;
+      if (size_t(tiles) * ks * 128 * c * 4 > kWsBytes) continue;
+      const long items = tiles * ks;
+      const long waves = (items + g_num_sms - 1) / g_num_sms;
+      const double per_item = 2.5 + kb_per * t_kb + 0.012 * c + (ks > 1 ? 1.5 + 0.02 * ks : 0.0);
+      const double cost = waves * per_item;
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = c; best_ks = ks; }
+    }
   }
-  return best;
+  *bn_out = best;
+  *ksplit_out = best_ks;
 }
 
 int gemm_launch(const ConvGemm& d, cudaStream_t st) {
@@ -469,8 +567,14 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
       if (int e = encode(&tmA, d.bf16, 5, d.A, dims, str, box, bk)) return e;
     }
   }
-  const int bn = pick_bn(d.N, g.m_tiles, g.num_kb, d.bn_max > 0 ? d.bn_max : 256);
+  int bn = 16, ksplit = 1;
+  static const bool no_split = getenv("B2P_NO_SPLITK") != nullptr;
+  pick_tiling(d.N, g.m_tiles, g.num_kb, bk, g.a_bytes, d.bn_max > 0 ? d.bn_max : 256, !no_split, &bn, &ksplit);
   g.bn = bn;
+  g.ksplit = ksplit;
+  g.kb_per = (g.num_kb + ksplit - 1) / ksplit;
+  g.ws = g_ws;
+  g.counters = g_counters;
   g.n_tiles = (d.N + bn - 1) / bn;
   g.b_bytes = uint32_t(bn) * bk * 2;
   g.b_slot = (g.b_bytes + 1023) & ~1023u;
@@ -484,7 +588,7 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
   const int stage_bytes = kASlot + int(g.b_slot);
   int stages = (g_max_smem - 1024 - 256) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages > g.num_kb && g.num_kb >= 2) stages = g.num_kb;
+  if (stages > g.kb_per && g.kb_per >= 2 && g.ksplit == 1) stages = g.kb_per;
   if (stages < 2) stages = 2;
   g.stages = stages;
   const size_t smem = size_t(stages) * stage_bytes + 1024 + 256;
@@ -493,14 +597,14 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
   g.vec_ok = ((reinterpret_cast<uintptr_t>(d.out) & 15) == 0) && ((d.ldc * esz) % 16 == 0) &&
              (!d.res || (((reinterpret_cast<uintptr_t>(d.res) & 15) == 0) && ((d.ldr * esz) % 16 == 0))) &&
              (!d.bias || ((reinterpret_cast<uintptr_t>(d.bias) & 15) == 0));
-  const int total = g.m_tiles * g.n_tiles;
+  const int total = g.m_tiles * g.n_tiles * g.ksplit;
   const int grid = total < g_num_sms ? total : g_num_sms;
   if (grid <= 0) return 0;
   static const bool dbg = getenv("B2P_DEBUG") != nullptr;
   if (dbg)
-    fprintf(stderr, "b2p_gemm mode=%d M=%d N=%d Ktot=%d bk=%d bn=%d tw=%d th=%d m_tiles=%d n_tiles=%d stages=%d grid=%d act=%d f32=%d res=%d\n",
+    fprintf(stderr, "b2p_gemm mode=%d M=%d N=%d Ktot=%d bk=%d bn=%d tw=%d th=%d m_tiles=%d n_tiles=%d stages=%d grid=%d act=%d f32=%d res=%d ksplit=%d\n",
             d.mode, d.mode == 0 ? d.M : g.m_tiles * 128, d.N, Ktot, bk, bn, g.tw, g.th, g.m_tiles, g.n_tiles, stages, grid,
-            d.act, d.out_f32, d.res != nullptr);
+            d.act, d.out_f32, d.res != nullptr, ksplit);
   gemm_tcgen05_kernel<<<grid, kThreads, smem, st>>>(tmA, tmB, g);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return set_error(cudaGetErrorString(ce));

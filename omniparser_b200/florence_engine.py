@@ -229,9 +229,9 @@ class FlorencePlan:
                 for kind in ("spatial_block", "channel_block"):
                     e = blk[kind]
                     x1 = self._e(T, C)
-                    ops_.append(lambda x=x, x1=x1, e=e, H=H, C=C: ops.dwconv3x3_res(x, K, H, H, C, e["dw1_w"], e["dw1_b"], x1))
                     h = self._act(T, C)
-                    self._ln(ops_, x1, e["n1"], T, C, h)
+                    ops_.append(lambda x=x, x1=x1, h=h, e=e, H=H, C=C: ops.dwconv_ln(x, K, H, H, C, e["dw1_w"], e["dw1_b"], x1,
+                                                                                 e["n1"].g, e["n1"].b, h, split=x3))
                     qkv = self._e(T, 3 * C)
                     self._gemm(ops_, h, e["qkv"], qkv)
                     a = self._act(T, C)
@@ -244,9 +244,9 @@ class FlorencePlan:
                     x2 = self._e(T, C)
                     self._gemm(ops_, a, e["proj"], x2, res=x1)
                     x3_ = self._e(T, C)
-                    ops_.append(lambda x2=x2, x3_=x3_, e=e, H=H, C=C: ops.dwconv3x3_res(x2, K, H, H, C, e["dw2_w"], e["dw2_b"], x3_))
                     h2 = self._act(T, C)
-                    self._ln(ops_, x3_, e["n2"], T, C, h2)
+                    ops_.append(lambda x2=x2, x3_=x3_, h2=h2, e=e, H=H, C=C: ops.dwconv_ln(x2, K, H, H, C, e["dw2_w"], e["dw2_b"], x3_,
+                                                                                      e["n2"].g, e["n2"].b, h2, split=x3))
                     f = self._act(T, 4 * C)
                     self._gemm(ops_, h2, e["fc1"], f, act=ACT_GELU, split=x3)
                     x4 = self._e(T, C)

@@ -162,6 +162,12 @@ def dwconv3x3_res(x, B, H, W, C, w9c, bias, y):
     _lib.check(_lib.lib().b2p_dwconv3x3_res(_p(x), B, H, W, C, _p(w9c), _p(bias), _p(y), _stream()))
 
 
+def dwconv_ln(x, B, H, W, C, w9c, bias, y, gamma, beta, out16, eps=1e-5, split=False):
+    """y = dwconv3x3(x) + bias + x (fp32) and out16 = LayerNorm(y) as the next GEMM operand, one kernel."""
+    _lib.check(_lib.lib().b2p_dwconv_ln(_p(x), B, H, W, C, _p(w9c), _p(bias), _p(y), _p(gamma), _p(beta), eps, _p(out16),
+                                        int(split), _stream()))
+
+
 def window_attn(qkv32, qkv_bias, B, H, W, C, heads, out, win=12, split=False):
     _lib.check(_lib.lib().b2p_window_attn(_p(qkv32), _p(qkv_bias), B, H, W, C, heads, win, _p(out), int(split), _stream()))
 

@@ -26,7 +26,8 @@ def _act(x, act):
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 64, 128), (256, 256, 256), (300, 200, 192), (37, 24, 32),
                                    (1000, 320, 160), (129, 1, 256), (4096, 768, 768), (60, 3072, 768),
-                                   (480, 1000, 3072), (25600, 128, 32), (13, 51289, 768)])
+                                   (480, 1000, 3072), (25600, 128, 32), (13, 51289, 768),
+                                   (416, 768, 9216), (416, 2304, 2304), (100, 64, 4608)])
 @pytest.mark.parametrize("cfg", [dict(), dict(bias=True, act=ops.ACT_SILU), dict(bias=True, act=ops.ACT_GELU, res=True),
                                  dict(bias=True, res=True, out_f32=True)])
 def test_gemm(M, N, K, cfg):
@@ -233,3 +234,23 @@ def test_im2col_stem():
         got = out.cpu().float()
         assert torch.equal(got[:, :k * k * 3], cols.half().float())
         assert got[:, k * k * 3:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("M,N,K", [(416, 3072, 768), (300, 256, 2048), (1000, 128, 64)])
+def test_gemm_fp16x3_layout(M, N, K):
+    """fp16x3 precision mode: A = [hi | hi | lo], W = [hi | lo | hi] (K-concatenated) gives near-fp32 products, and the
+    split epilogue writes the next operand in the same layout (covers the split-K path for the small-M cases)."""
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    a_hi, w_hi = a.half(), w.half()
+    a3 = torch.cat([a_hi, a_hi, (a - a_hi.float()).half()], 1).to(DEV)
+    w3 = torch.cat([w_hi, (w - w_hi.float()).half(), w_hi], 1).contiguous().to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    out = torch.empty(M, 3 * N, dtype=torch.float16, device=DEV)
+    ops.gemm(a3, 3 * K, w3, M, N, 3 * K, out, 3 * N, bias, None, 0, ops.ACT_GELU, split=True)
+    torch.cuda.synchronize()
+    ref = F.gelu(a.double() @ w.double().t() + bias.cpu().double())
+    got = (out[:, :N].float() + out[:, 2 * N:].float()).cpu().double()
+    assert torch.equal(out[:, :N], out[:, N:2 * N])
+    assert (got - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
