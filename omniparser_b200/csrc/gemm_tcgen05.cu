@@ -42,7 +42,7 @@ struct GemmArgs {
   int act, vec_ok;
   int split;   // > 0: fp16 output in the fp16x3 operand layout [hi | hi | lo] with logical width `split`
   float* ws;   // split-K partial tiles [tile][slice][128][bn] fp32
-  int* counters;   // split-K arrival counters per output tile (self-resetting)
+  int* counters;   // split-K {arrived, finished} counters per output tile (self-resetting)
 };
 
 // Shared-memory matrix descriptor (PTX ISA "tcgen05 matrix descriptor"), K-major operand, swizzled:
@@ -186,7 +186,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t bar_tfull = bar_empty + 8 * g.stages;
   const uint32_t bar_tempty = bar_tfull + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * g.stages + 4);
-  volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -348,7 +347,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
       } else {
-        // split-K: park the raw partial tile, the last-arriving CTA of this output tile reduces in slice order
+        // split-K (only launched when every work item owns a resident CTA, so spinning on the arrival counter is
+        // safe): park the raw partial tile; when all ksplit slices of this output tile have landed, each of the
+        // ksplit CTAs reduces its share of the 128 rows (slice order => deterministic sums) and runs the epilogue.
         float* wsp = g.ws + ((size_t(tile) * g.ksplit + ks) * kTileM + r) * g.bn;
         for (int c = chalf * 16; c < g.bn; c += 32) {
           uint32_t v[16];
@@ -364,33 +365,56 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
         __threadfence();
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        int* cnt = g.counters + 2 * tile;
         if (threadIdx.x == 64) {
-          const int old = atomicAdd(g.counters + tile, 1);
-          const int last = (old == g.ksplit - 1);
-          if (last) g.counters[tile] = 0;   // self-reset for the next launch / graph replay
-          *last_flag = last;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (*last_flag) {
-          __threadfence();
-          const float* base = g.ws + (size_t(tile) * g.ksplit * kTileM + r) * g.bn;
-          for (int c = chalf * 16; c < g.bn; c += 32) {
-            if (n0 + c >= g.N) continue;
-            float x[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) x[j] = 0.f;
-            for (int s = 0; s < g.ksplit; ++s) {
-              const float4* pp = reinterpret_cast<const float4*>(base + size_t(s) * kTileM * g.bn + c);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 t = __ldcg(pp + q);
-                x[4 * q] += t.x; x[4 * q + 1] += t.y; x[4 * q + 2] += t.z; x[4 * q + 3] += t.w;
-              }
-            }
-            epi_store16(g, e, x, n0 + c, pix, valid);
+          atomicAdd(cnt, 1);
+          long long t0 = clock64();
+          while (*reinterpret_cast<volatile int*>(cnt) < g.ksplit) {
+            if (clock64() - t0 > 4000000000LL) { printf("b2p: split-K arrival timeout (tile %d)\n", tile); __trap(); }
           }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // last_flag is reused by the next item
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        __threadfence();
+        const int rows_per = (kTileM + g.ksplit - 1) / g.ksplit;
+        const int row0 = ks * rows_per, row1 = min(kTileM, row0 + rows_per);
+        const int chunks = g.bn >> 4;
+        const float* base = g.ws + size_t(tile) * g.ksplit * kTileM * g.bn;
+        for (int w = (threadIdx.x - 64); w < (row1 - row0) * chunks; w += 256) {
+          const int rr_ = row0 + w / chunks, c = (w % chunks) << 4;
+          if (n0 + c >= g.N) continue;
+          long long pix2;
+          bool valid2;
+          if (g.mode == 0) {
+            pix2 = (long long)mt * kTileM + rr_;
+            valid2 = pix2 < g.M;
+          } else {
+            const int per_img = g.tiles_x * g.tiles_y;
+            const int img = mt / per_img;
+            const int rr = mt - img * per_img;
+            const int ty = rr_ / g.tw, tx = rr_ - ty * g.tw;
+            const int oy = (rr / g.tiles_x) * g.th + ty;
+            const int ox = (rr % g.tiles_x) * g.tw + tx;
+            valid2 = (ty < g.th) && (oy < g.Ho) && (ox < g.Wo);
+            pix2 = ((long long)img * g.Ho + oy) * g.Wo + ox;
+          }
+          float x[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) x[j] = 0.f;
+          for (int sidx = 0; sidx < g.ksplit; ++sidx) {
+            const float4* pp = reinterpret_cast<const float4*>(base + (size_t(sidx) * kTileM + rr_) * g.bn + c);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 t = __ldcg(pp + q);
+              x[4 * q] += t.x; x[4 * q + 1] += t.y; x[4 * q + 2] += t.z; x[4 * q + 3] += t.w;
+            }
+          }
+          epi_store16(g, e, x, n0 + c, pix2, valid2);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 64) {
+          // the last CTA to finish its share resets both counters for the next launch / graph replay
+          if (atomicAdd(cnt + 1, 1) == g.ksplit - 1) { cnt[1] = 0; cnt[0] = 0; __threadfence(); }
+        }
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -443,7 +467,7 @@ static int g_num_sms = 0;
 static float* g_ws = nullptr;
 static int* g_counters = nullptr;
 static constexpr size_t kWsBytes = size_t(96) << 20;     // split-K partial tiles
-static constexpr int kMaxCounterTiles = 1 << 16;
+static constexpr int kMaxCounterTiles = 1 << 12;   // split-K only ever covers < #SMs tiles
 
 static int g_max_smem = 0;
 
@@ -458,9 +482,9 @@ static int device_setup() {
   g_max_smem = int(p.sharedMemPerBlockOptin);
   if (cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem) != cudaSuccess)
     return set_error("cudaFuncSetAttribute(max dynamic smem) failed");
-  if (cudaMalloc(&g_ws, kWsBytes) != cudaSuccess || cudaMalloc(&g_counters, kMaxCounterTiles * sizeof(int)) != cudaSuccess)
+  if (cudaMalloc(&g_ws, kWsBytes) != cudaSuccess || cudaMalloc(&g_counters, 2 * kMaxCounterTiles * sizeof(int)) != cudaSuccess)
     return set_error("cudaMalloc for the split-K workspace failed");
-  cudaMemset(g_counters, 0, kMaxCounterTiles * sizeof(int));
+  cudaMemset(g_counters, 0, 2 * kMaxCounterTiles * sizeof(int));
   return 0;
 }
 
@@ -488,16 +512,22 @@ static void pick_tiling(int N, int m_tiles, int num_kb, int bk, uint32_t a_bytes
     const double t_fill = (double(a_bytes) + double(c) * bk * 2.0) / 70000.0;
     const double t_kb = t_mma > t_fill ? t_mma : t_fill;
     int max_ks = 1;
-    if (allow_split && tiles < g_num_sms && tiles <= kMaxCounterTiles) max_ks = num_kb / 2 > 1 ? num_kb / 2 : 1;
-    if (max_ks > 32) max_ks = 32;
+    if (allow_split && tiles * 2 <= g_num_sms && tiles * 2 <= kMaxCounterTiles) {
+      max_ks = int(g_num_sms / tiles);          // every (tile, slice) item must own a resident CTA (the kernel spins)
+      if (max_ks > num_kb / 2) max_ks = num_kb / 2;
+      if (max_ks > 32) max_ks = 32;
+      if (max_ks < 1) max_ks = 1;
+    }
     for (int ks = 1; ks <= max_ks; ++ks) {
       const int kb_per = (num_kb + ks - 1) / ks;
       const int ks_eff = (num_kb + kb_per - 1) / kb_per;
       if (ks_eff != ks) continue;
-      if (size_t(tiles) * ks * 128 * c * 4 > kWsBytes) continue;
+      if (ks > 1 && size_t(tiles) * ks * 128 * c * 4 > kWsBytes) continue;
       const long items = tiles * ks;
       const long waves = (items + g_num_sms - 1) / g_num_sms;
-      const double per_item = 2.5 + kb_per * t_kb + 0.012 * c + (ks > 1 ? 1.5 + 0.02 * ks : 0.0);
+      // split-K overhead: park one fp32 partial tile + read one tile's worth back (distributed reduce) at ~100 GB/s/SM
+      const double t_split = ks > 1 ? 2.0 + 2.0 * (128.0 * c * 4.0 / 100000.0) : 0.0;
+      const double per_item = 2.5 + kb_per * t_kb + 0.012 * c + t_split;
       const double cost = waves * per_item;
       if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = c; best_ks = ks; }
     }
