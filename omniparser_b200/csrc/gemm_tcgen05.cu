@@ -7,8 +7,9 @@
 // materialised.  Replaces the cuDNN/cuBLAS library kernels behind ref:util/yolov9.py:120-121 (TorchScript
 // YOLOv9-E forward) and ref:util/utils.py:125 (Florence-2 generate).
 //
-// Roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane), warp 2 also owns TMEM
-// alloc/dealloc, warps 2..9 = epilogue (TMEM lane group = warp % 4; the two warps of a group split the columns).
+// Roles (576 threads): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane), warp 2 also owns TMEM
+// alloc/dealloc, warps 2..17 = epilogue (TMEM lane group = warp % 4; the four warps of a group interleave the
+// 16-column chunks): the epilogue is latency-bound (dependent MUFU/FP32 chains), so it gets most of the warps.
 // Pipelines: smem ring full/empty (TMA <-> MMA), TMEM accumulator double buffer full/empty (MMA <-> epilogue).
 #include "ptx.cuh"
 #include "b2p_internal.h"
@@ -18,8 +19,9 @@
 
 namespace b2p {
 
-static constexpr int kThreads = 320;      // 2 control warps + 8 epilogue warps
-static constexpr int kEpiWarps = 8;
+static constexpr int kThreads = 576;      // 2 control warps + 16 epilogue warps
+static constexpr int kEpiWarps = 16;
+static constexpr int kEpiThreads = kEpiWarps * 32;
 static constexpr int kTileM = 128;
 static constexpr int kASlot = 16384;    // 128 rows x 128 B
 static constexpr int kMaxStages = 8;
@@ -29,6 +31,9 @@ struct GemmArgs {
   int mode, M, N, num_kb, bk, bn;
   int cin_blocks, tw, th, tiles_x, tiles_y, Ho, Wo, batch;
   int m_tiles, n_tiles, stages, ldpar;
+  int tw_valid;          // valid output columns per tile row (== tw except in halo mode, where tw is the halo pitch)
+  int stagesA, cin;      // halo mode: A ring depth, Cin
+  uint32_t a_slot;       // halo mode: bytes per A slot
   int ksplit, kb_per;    // split-K: work item = (m tile, n tile, k slice); the last CTA of a tile reduces + stores
   uint32_t a_bytes, b_bytes, b_slot;
   uint32_t idesc;
@@ -179,13 +184,16 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t stage_bytes = kASlot + g.b_slot;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(g.stages) * stage_bytes);
+  const uint32_t stage_bytes = (g.mode == 3) ? g.b_slot : kASlot + g.b_slot;
+  const uint32_t a_region = (g.mode == 3) ? uint32_t(g.stagesA) * g.a_slot : 0u;   // halo mode: [A slots][B slots]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a_region + size_t(g.stages) * stage_bytes);
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = bar_full + 8 * g.stages;
   const uint32_t bar_tfull = bar_empty + 8 * g.stages;
   const uint32_t bar_tempty = bar_tfull + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * g.stages + 4);
+  const uint32_t bar_afull = bar_tempty + 16;              // halo mode only
+  const uint32_t bar_aempty = bar_afull + 8 * g.stagesA;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * g.stages + 4 + 2 * g.stagesA);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -202,6 +210,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
       mbar_init(bar_tempty + 8 * a, kEpiWarps);
+    }
+    for (int a = 0; a < g.stagesA; ++a) {
+      mbar_init(bar_afull + 8 * a, 1);
+      mbar_init(bar_aempty + 8 * a, 1);
     }
     mbar_fence_init();
   }
@@ -220,8 +232,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------------------ TMA producer
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, stageA = 0;
+      uint32_t phase = 0, phaseA = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         const int ks = item % g.ksplit;
         const int tile = item / g.ksplit;
@@ -234,9 +246,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           img = mt / per_img;
           const int r = mt - img * per_img;
           y0 = (r / g.tiles_x) * g.th;
-          x0 = (r % g.tiles_x) * g.tw;
+          x0 = (r % g.tiles_x) * g.tw_valid;
         }
         const int kb0 = ks * g.kb_per, kb1 = min(g.num_kb, kb0 + g.kb_per);
+        if (g.mode == 3) {
+          // halo mode: ONE (th+2) x (tw+2) input tile per 64-channel block feeds all nine taps (the MMA side shifts
+          // the smem descriptor start address by (ky*pitch + kx) rows); only the weights stream per tap.
+          for (int cb = kb0; cb < kb1; ++cb) {
+            mbar_wait(bar_aempty + 8 * stageA, phaseA ^ 1);
+            const uint32_t fa = bar_afull + 8 * stageA;
+            mbar_expect_tx(fa, g.a_bytes);
+            tma_load_4d(smem_base + stageA * g.a_slot, &tmA, fa, cb * 64, x0 - 1, y0 - 1, img);
+            if (++stageA == g.stagesA) { stageA = 0; phaseA ^= 1; }
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+              const uint32_t fb = bar_full + 8 * stage;
+              mbar_expect_tx(fb, g.b_bytes);
+              tma_load_2d(smem_base + a_region + stage * stage_bytes, &tmB, fb, tap * g.cin + cb * 64, n0);
+              if (++stage == g.stages) { stage = 0; phase ^= 1; }
+            }
+          }
+          continue;
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t fb = bar_full + 8 * stage;
@@ -266,8 +297,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     if (lane == 0) {
       // ------------------------------------------------------------ MMA issuer
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, stageA = 0;
+      uint32_t phase = 0, phaseA = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       const int ksteps = g.bk / 16;
@@ -277,6 +308,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(acc * 256);
+        if (g.mode == 3) {
+          for (int cb = kb0; cb < kb1; ++cb) {
+            mbar_wait(bar_afull + 8 * stageA, phaseA);
+            const uint32_t sa0 = smem_base + stageA * g.a_slot;
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(bar_full + 8 * stage, phase);
+              tc_fence_after();
+              const int ky = tap / 3, kx = tap - ky * 3;
+              const uint32_t sa = sa0 + uint32_t(ky * g.tw + kx) * 128u;      // shifted view of the halo tile
+              const uint32_t sb = smem_base + a_region + stage * stage_bytes;
+              // start address not on a 1024-B swizzle-atom boundary -> matrix base offset = (addr >> 7) & 7 (bits 49..51)
+              const uint64_t da = g.desc_hi | uint64_t((sa & 0x3FFFF) >> 4) | (uint64_t((sa >> 7) & 7) << 49);
+              const uint64_t db = g.desc_hi | uint64_t((sb & 0x3FFFF) >> 4);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), g.idesc, ((cb - kb0) | tap | k) != 0);
+              umma_commit(bar_empty + 8 * stage);
+              if (++stage == g.stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(bar_aempty + 8 * stageA);
+            if (++stageA == g.stagesA) { stageA = 0; phaseA ^= 1; }
+          }
+          umma_commit(bar_tfull + 8 * acc);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+          continue;
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
@@ -297,9 +355,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    // -------------------------------------------------------------- epilogue (8 warps, 128 TMEM lanes x 2 column halves)
+    // -------------------------------------------------------------- epilogue (16 warps: 128 TMEM lanes x 4 column phases)
     const int grp = warp & 3;
-    const int chalf = (warp - 2) >> 2;   // which 16-column chunks this warp owns (even / odd)
+    const int cq = (warp - 2) >> 2;      // this warp owns the 16-column chunks cq, cq + 4, cq + 8, ...
     int acc = 0;
     uint32_t acc_phase = 0;
     EpiCtx e;
@@ -325,15 +383,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int rr = mt - img * per_img;
         const int ty = r / g.tw, tx = r - ty * g.tw;
         const int oy = (rr / g.tiles_x) * g.th + ty;
-        const int ox = (rr % g.tiles_x) * g.tw + tx;
-        valid = (ty < g.th) && (oy < g.Ho) && (ox < g.Wo);
+        const int ox = (rr % g.tiles_x) * g.tw_valid + tx;
+        valid = (ty < g.th) && (tx < g.tw_valid) && (oy < g.Ho) && (ox < g.Wo);
         pix = ((long long)img * g.Ho + oy) * g.Wo + ox;
       }
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(grp * 32) << 16) + uint32_t(acc * 256);
       if (g.ksplit == 1) {
-        for (int c = chalf * 16; c < g.bn; c += 32) {
+        for (int c = cq * 16; c < g.bn; c += 64) {
           uint32_t v[16];
           tmem_ld16(t_row + c, v);
           tmem_ld_wait();
@@ -351,7 +409,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // safe): park the raw partial tile; when all ksplit slices of this output tile have landed, each of the
         // ksplit CTAs reduces its share of the 128 rows (slice order => deterministic sums) and runs the epilogue.
         float* wsp = g.ws + ((size_t(tile) * g.ksplit + ks) * kTileM + r) * g.bn;
-        for (int c = chalf * 16; c < g.bn; c += 32) {
+        for (int c = cq * 16; c < g.bn; c += 64) {
           uint32_t v[16];
           tmem_ld16(t_row + c, v);
           tmem_ld_wait();
@@ -364,7 +422,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
         __threadfence();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         int* cnt = g.counters + 2 * tile;
         if (threadIdx.x == 64) {
           atomicAdd(cnt, 1);
@@ -373,13 +431,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (clock64() - t0 > 4000000000LL) { printf("b2p: split-K arrival timeout (tile %d)\n", tile); __trap(); }
           }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         __threadfence();
         const int rows_per = (kTileM + g.ksplit - 1) / g.ksplit;
         const int row0 = ks * rows_per, row1 = min(kTileM, row0 + rows_per);
         const int chunks = g.bn >> 4;
         const float* base = g.ws + size_t(tile) * g.ksplit * kTileM * g.bn;
-        for (int w = (threadIdx.x - 64); w < (row1 - row0) * chunks; w += 256) {
+        for (int w = (threadIdx.x - 64); w < (row1 - row0) * chunks; w += kEpiThreads) {
           const int rr_ = row0 + w / chunks, c = (w % chunks) << 4;
           if (n0 + c >= g.N) continue;
           long long pix2;
@@ -393,8 +451,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int rr = mt - img * per_img;
             const int ty = rr_ / g.tw, tx = rr_ - ty * g.tw;
             const int oy = (rr / g.tiles_x) * g.th + ty;
-            const int ox = (rr % g.tiles_x) * g.tw + tx;
-            valid2 = (ty < g.th) && (oy < g.Ho) && (ox < g.Wo);
+            const int ox = (rr % g.tiles_x) * g.tw_valid + tx;
+            valid2 = (ty < g.th) && (tx < g.tw_valid) && (oy < g.Ho) && (ox < g.Wo);
             pix2 = ((long long)img * g.Ho + oy) * g.Wo + ox;
           }
           float x[16];
@@ -410,7 +468,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           epi_store16(g, e, x, n0 + c, pix2, valid2);
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         if (threadIdx.x == 64) {
           // the last CTA to finish its share resets both counters for the next launch / graph replay
           if (atomicAdd(cnt + 1, 1) == g.ksplit - 1) { cnt[1] = 0; cnt[0] = 0; __threadfence(); }
@@ -546,9 +604,12 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
   if (d.mode != 0 && kred % 32 != 0) return set_error("conv3x3: Cin must be a multiple of 32");
   if (d.mode == 0 && (d.K % 8 != 0 || d.lda % 8 != 0)) return set_error("gemm: K and lda must be multiples of 8");
   if ((reinterpret_cast<uintptr_t>(d.A) & 15) || (reinterpret_cast<uintptr_t>(d.B) & 15)) return set_error("gemm: operands must be 16-byte aligned");
-  g.mode = d.mode;
+  static const bool no_halo = getenv("B2P_NO_HALO") != nullptr;
+  const bool halo = (d.mode == 1) && (bk == 64) && !no_halo;
+  g.mode = halo ? 3 : d.mode;
   g.N = d.N;
   g.bk = bk;
+  g.cin = d.Cin;
   g.desc_hi = make_desc_hi(bk);
   g.out = d.out; g.ldc = d.ldc; g.out_f32 = d.out_f32; g.bias = d.bias; g.res = d.res; g.ldr = d.ldr; g.act = d.act;
   g.split = (d.split_out && !d.out_f32) ? d.N : 0;
@@ -556,6 +617,7 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
 
   if (d.mode == 0) {
     g.M = d.M;
+    g.tw_valid = 0;
     g.num_kb = (d.K + bk - 1) / bk;
     g.m_tiles = (d.M + kTileM - 1) / kTileM;
     g.a_bytes = kTileM * bk * 2;
@@ -578,12 +640,33 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
       const double u = double(g.Ho) * g.Wo / (double(tiles) * 128.0);
       if (u > bu + 1e-9 || (u > bu - 1e-9 && tw > btw)) { bu = u; btw = tw; bth = th; }
     }
-    g.tw = btw; g.th = bth;
+    if (halo) {
+      // halo tile: (th+2) x (tw+2) input pixels loaded once per 64-channel block; the 128 MMA rows are 128 consecutive
+      // positions of that tile (row pitch tw+2), so 2 of every tw+2 rows are halo columns and carry no output.
+      btw = 1; bth = 1; bu = -1;
+      for (int tw = 1; tw <= g.Wo && tw <= 126; ++tw) {
+        int th = 128 / (tw + 2); if (th > g.Ho) th = g.Ho; if (th < 1) continue;
+        const long tiles = long((g.Wo + tw - 1) / tw) * ((g.Ho + th - 1) / th);
+        const double u = double(g.Ho) * g.Wo / (double(tiles) * 128.0);
+        if (u > bu + 1e-9 || (u > bu - 1e-9 && tw > btw)) { bu = u; btw = tw; bth = th; }
+      }
+      g.tw = btw + 2; g.tw_valid = btw; g.th = bth;
+      g.num_kb = g.cin_blocks;                                  // pipeline unit = one channel block (9 taps)
+      g.a_bytes = uint32_t(bth + 2) * (btw + 2) * 128;
+      g.a_slot = (uint32_t(2 * (btw + 2) + 2 + 128) * 128 + 1023) & ~1023u;
+    } else {
+      g.tw = btw; g.tw_valid = btw; g.th = bth;
+      g.a_bytes = uint32_t(btw) * bth * bk * 2;
+    }
     g.tiles_x = (g.Wo + btw - 1) / btw; g.tiles_y = (g.Ho + bth - 1) / bth;
     g.m_tiles = g.tiles_x * g.tiles_y * d.batch;
-    g.a_bytes = uint32_t(btw) * bth * bk * 2;
     const cuuint64_t ld = cuuint64_t(d.lda);
-    if (d.mode == 1) {
+    if (halo) {
+      cuuint64_t dims[4] = {cuuint64_t(d.Cin), cuuint64_t(d.W), cuuint64_t(d.H), cuuint64_t(d.batch)};
+      cuuint64_t str[3] = {ld * 2, ld * 2 * d.W, ld * 2 * d.W * d.H};
+      cuuint32_t box[4] = {64, cuuint32_t(btw + 2), cuuint32_t(bth + 2), 1};
+      if (int e = encode(&tmA, d.bf16, 4, d.A, dims, str, box, bk)) return e;
+    } else if (d.mode == 1) {
       cuuint64_t dims[4] = {cuuint64_t(d.Cin), cuuint64_t(d.W), cuuint64_t(d.H), cuuint64_t(d.batch)};
       cuuint64_t str[3] = {ld * 2, ld * 2 * d.W, ld * 2 * d.W * d.H};
       cuuint32_t box[4] = {cuuint32_t(bk), cuuint32_t(btw), cuuint32_t(bth), 1};
@@ -599,7 +682,7 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
   }
   int bn = 16, ksplit = 1;
   static const bool no_split = getenv("B2P_NO_SPLITK") != nullptr;
-  pick_tiling(d.N, g.m_tiles, g.num_kb, bk, g.a_bytes, d.bn_max > 0 ? d.bn_max : 256, !no_split, &bn, &ksplit);
+  pick_tiling(d.N, g.m_tiles, g.num_kb, halo ? 9 * bk : bk, g.a_bytes, d.bn_max > 0 ? d.bn_max : 256, !no_split, &bn, &ksplit);
   g.bn = bn;
   g.ksplit = ksplit;
   g.kb_per = (g.num_kb + ksplit - 1) / ksplit;
@@ -615,13 +698,15 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
     cuuint32_t box[2] = {cuuint32_t(bk), cuuint32_t(bn)};
     if (int e = encode(&tmB, d.bf16, 2, d.B, dims, str, box, bk)) return e;
   }
-  const int stage_bytes = kASlot + int(g.b_slot);
-  int stages = (g_max_smem - 1024 - 256) / stage_bytes;
+  const int stage_bytes = halo ? int(g.b_slot) : kASlot + int(g.b_slot);
+  g.stagesA = halo ? 2 : 0;
+  const int a_region = halo ? g.stagesA * int(g.a_slot) : 0;
+  int stages = (g_max_smem - 1024 - 512 - a_region) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages > g.kb_per && g.kb_per >= 2 && g.ksplit == 1) stages = g.kb_per;
+  if (!halo && stages > g.kb_per && g.kb_per >= 2 && g.ksplit == 1) stages = g.kb_per;
   if (stages < 2) stages = 2;
   g.stages = stages;
-  const size_t smem = size_t(stages) * stage_bytes + 1024 + 256;
+  const size_t smem = size_t(a_region) + size_t(stages) * stage_bytes + 1024 + 512;
   // vector epilogue needs 16-byte aligned rows in out / residual and bias
   const int esz = d.out_f32 ? 4 : 2;
   g.vec_ok = ((reinterpret_cast<uintptr_t>(d.out) & 15) == 0) && ((d.ldc * esz) % 16 == 0) &&
@@ -633,7 +718,7 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
   static const bool dbg = getenv("B2P_DEBUG") != nullptr;
   if (dbg)
     fprintf(stderr, "b2p_gemm mode=%d M=%d N=%d Ktot=%d bk=%d bn=%d tw=%d th=%d m_tiles=%d n_tiles=%d stages=%d grid=%d act=%d f32=%d res=%d ksplit=%d\n",
-            d.mode, d.mode == 0 ? d.M : g.m_tiles * 128, d.N, Ktot, bk, bn, g.tw, g.th, g.m_tiles, g.n_tiles, stages, grid,
+            g.mode, d.mode == 0 ? d.M : g.m_tiles * 128, d.N, Ktot, bk, bn, g.tw, g.th, g.m_tiles, g.n_tiles, stages, grid,
             d.act, d.out_f32, d.res != nullptr, ksplit);
   gemm_tcgen05_kernel<<<grid, kThreads, smem, st>>>(tmA, tmB, g);
   cudaError_t ce = cudaGetLastError();
