@@ -16,6 +16,7 @@
 #include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
+#include <mutex>
 
 namespace b2p {
 
@@ -198,6 +199,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  // Programmatic dependent launch: this grid is persistent (<= one CTA per SM, all resident), so the next kernel in
+  // the stream may start launching right away; its CTAs run their prologue on SMs as they free up and then block in
+  // griddepcontrol.wait until this grid has completed and flushed.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -225,6 +231,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above touched only this CTA's shared/tensor memory; global reads/writes start below
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const int total_items = g.m_tiles * g.n_tiles * g.ksplit;   // item = (mt * n_tiles + nt) * ksplit + ks
   const uint32_t smem_base = smem_u32(smem);
@@ -318,8 +326,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               const int ky = tap / 3, kx = tap - ky * 3;
               const uint32_t sa = sa0 + uint32_t(ky * g.tw + kx) * 128u;      // shifted view of the halo tile
               const uint32_t sb = smem_base + a_region + stage * stage_bytes;
-              // start address not on a 1024-B swizzle-atom boundary -> matrix base offset = (addr >> 7) & 7 (bits 49..51)
-              const uint64_t da = g.desc_hi | uint64_t((sa & 0x3FFFF) >> 4) | (uint64_t((sa >> 7) & 7) << 49);
+              // The 128B-swizzle pattern is anchored at the 1024-B aligned slot base (that is how TMA wrote it), so the
+              // "matrix base offset" field stays 0 even though the start address points into the middle of an atom:
+              // the XOR phase is taken from the address bits, exactly as for the +32 B K-advance.
+              const uint64_t da = g.desc_hi | uint64_t((sa & 0x3FFFF) >> 4);
               const uint64_t db = g.desc_hi | uint64_t((sb & 0x3FFFF) >> 4);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
@@ -522,9 +532,22 @@ static int encode(CUtensorMap* m, int bf16, int rank, const void* base, const cu
 }
 
 static int g_num_sms = 0;
-static float* g_ws = nullptr;
-static int* g_counters = nullptr;
-static constexpr size_t kWsBytes = size_t(96) << 20;     // split-K partial tiles
+// Split-K scratch is per stream (two streams may run split-K GEMMs concurrently): a few slots are allocated up
+// front (never inside a graph capture) and handed to streams in order of first use.
+static constexpr int kWsSlots = 8;
+static float* g_ws[kWsSlots] = {};
+static int* g_counters[kWsSlots] = {};
+static cudaStream_t g_ws_owner[kWsSlots] = {};
+static int g_ws_used = 0;
+static std::mutex g_ws_mu;
+static int ws_slot_for(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  for (int i = 0; i < g_ws_used; ++i)
+    if (g_ws_owner[i] == st) return i;
+  if (g_ws_used < kWsSlots) { g_ws_owner[g_ws_used] = st; return g_ws_used++; }
+  return -1;   // more concurrent streams than slots: the caller disables split-K for this launch
+}
+static constexpr size_t kWsBytes = size_t(64) << 20;     // split-K partial tiles (per slot)
 static constexpr int kMaxCounterTiles = 1 << 12;   // split-K only ever covers < #SMs tiles
 
 static int g_max_smem = 0;
@@ -540,9 +563,11 @@ static int device_setup() {
   g_max_smem = int(p.sharedMemPerBlockOptin);
   if (cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem) != cudaSuccess)
     return set_error("cudaFuncSetAttribute(max dynamic smem) failed");
-  if (cudaMalloc(&g_ws, kWsBytes) != cudaSuccess || cudaMalloc(&g_counters, 2 * kMaxCounterTiles * sizeof(int)) != cudaSuccess)
-    return set_error("cudaMalloc for the split-K workspace failed");
-  cudaMemset(g_counters, 0, 2 * kMaxCounterTiles * sizeof(int));
+  for (int i = 0; i < kWsSlots; ++i) {
+    if (cudaMalloc(&g_ws[i], kWsBytes) != cudaSuccess || cudaMalloc(&g_counters[i], 2 * kMaxCounterTiles * sizeof(int)) != cudaSuccess)
+      return set_error("cudaMalloc for the split-K workspace failed");
+    cudaMemset(g_counters[i], 0, 2 * kMaxCounterTiles * sizeof(int));
+  }
   return 0;
 }
 
@@ -682,12 +707,13 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
   }
   int bn = 16, ksplit = 1;
   static const bool no_split = getenv("B2P_NO_SPLITK") != nullptr;
-  pick_tiling(d.N, g.m_tiles, g.num_kb, halo ? 9 * bk : bk, g.a_bytes, d.bn_max > 0 ? d.bn_max : 256, !no_split, &bn, &ksplit);
+  const int slot = no_split ? -1 : ws_slot_for(st);
+  pick_tiling(d.N, g.m_tiles, g.num_kb, halo ? 9 * bk : bk, g.a_bytes, d.bn_max > 0 ? d.bn_max : 256, slot >= 0, &bn, &ksplit);
   g.bn = bn;
   g.ksplit = ksplit;
   g.kb_per = (g.num_kb + ksplit - 1) / ksplit;
-  g.ws = g_ws;
-  g.counters = g_counters;
+  g.ws = slot >= 0 ? g_ws[slot] : nullptr;
+  g.counters = slot >= 0 ? g_counters[slot] : nullptr;
   g.n_tiles = (d.N + bn - 1) / bn;
   g.b_bytes = uint32_t(bn) * bk * 2;
   g.b_slot = (g.b_bytes + 1023) & ~1023u;
@@ -720,8 +746,19 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
     fprintf(stderr, "b2p_gemm mode=%d M=%d N=%d Ktot=%d bk=%d bn=%d tw=%d th=%d m_tiles=%d n_tiles=%d stages=%d grid=%d act=%d f32=%d res=%d ksplit=%d\n",
             g.mode, d.mode == 0 ? d.M : g.m_tiles * 128, d.N, Ktot, bk, bn, g.tw, g.th, g.m_tiles, g.n_tiles, stages, grid,
             d.act, d.out_f32, d.res != nullptr, ksplit);
-  gemm_tcgen05_kernel<<<grid, kThreads, smem, st>>>(tmA, tmB, g);
-  cudaError_t ce = cudaGetLastError();
+  static const bool no_pdl = getenv("B2P_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = no_pdl ? 0 : 1;
+  cudaError_t ce = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel, tmA, tmB, g);
+  if (ce == cudaSuccess) ce = cudaGetLastError();
   if (ce != cudaSuccess) return set_error(cudaGetErrorString(ce));
   count_launch();
   return 0;

@@ -86,9 +86,9 @@ class B200YOLOv9Detector:
         with Image.open(source) as im:
             return np.asarray(im.convert("RGB"))
 
-    def _get_io(self, B, H, W, imgsz, max_det):
+    def _get_io(self, B, H, W, imgsz, max_det, slot=0):
         tw, th, scale, rw, rh, pl, pt = _geometry(W, H, imgsz)
-        key = (B, H, W, tw, th, max_det)
+        key = (B, H, W, tw, th, max_det, slot)
         io = self._io.get(key)
         if io is None:
             dev = self.device
@@ -102,6 +102,8 @@ class B200YOLOv9Detector:
             io = dict(
                 plan=plan, geom=(tw, th, scale, rw, rh, pl, pt), cap=cap,
                 host=torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory(),
+                host_count=torch.zeros((B,), dtype=torch.int32).pin_memory(),
+                host_box=torch.zeros((B, max_det, 4), dtype=torch.float32).pin_memory(),
                 src=torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev),
                 tmp=torch.empty((B, H, max(rw, 1), 3), dtype=torch.uint8, device=dev),
                 pad_l=torch.full((B,), float(pl), **f32), pad_t=torch.full((B,), float(pt), **f32),

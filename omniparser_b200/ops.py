@@ -13,6 +13,18 @@ import torch
 from . import _lib
 
 ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
+_CAPTURE_STREAMS = {}
+
+
+def capture_stream(tag, device):
+    """One capture stream per engine: split-K scratch is keyed by stream, and graphs of different engines may replay
+    concurrently on different streams."""
+    key = (tag, str(device))
+    if key not in _CAPTURE_STREAMS:
+        _CAPTURE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _CAPTURE_STREAMS[key]
+
+
 GRAPH_LAUNCHES = [0]   # kernels replayed through CUDA graphs (the C-side counter only sees direct launches)
 FLAG_BF16, FLAG_OUT_F32, FLAG_SPLIT = 1, 2, 4
 

@@ -131,6 +131,116 @@ def parse_screenshots(images: Sequence[np.ndarray], model: B200YOLOv9Detector, c
     return out
 
 
+class PipelinedParser:
+    """Two-deep software pipeline over batches of same-size screenshots: detection of batch i+1 (stream A) overlaps
+    the host list logic and the captioning of batch i (stream B).  Same results as :func:`parse_screenshots`, batch by
+    batch; only the scheduling differs.  Usage::
+
+        pp = PipelinedParser(model, caption_model_processor, BOX_TRESHOLD=0.05, iou_threshold=0.7)
+        for result in pp.run(iter_of_(images, ocr)):   # result = [(elems, ids), ...] per batch, in order
+            ...
+    """
+
+    def __init__(self, model: B200YOLOv9Detector, caption_model_processor: dict, BOX_TRESHOLD=0.01, iou_threshold=0.9,
+                 imgsz=640, max_new_tokens=20, prompt_ids: Sequence[int] = CAPTION_PROMPT_IDS):
+        self.model, self.cmp = model, caption_model_processor
+        self.conf, self.iou_thr, self.imgsz, self.T, self.prompt = BOX_TRESHOLD, iou_threshold, imgsz, max_new_tokens, list(prompt_ids)
+        dev = model.device
+        self.s_det = torch.cuda.Stream(device=dev)
+        self.s_cap = torch.cuda.Stream(device=dev)
+        self.timings = ParseTimings(detect_wait_s=0.0, glue_s=0.0, caption_s=0.0, n_boxes=0, n_crops=0, batches=0)
+
+    def _submit(self, slot: int, images, resident_src=None):
+        B = len(images)
+        H, W = images[0].shape[:2]
+        m = self.model
+        io_ = m._get_io(B, H, W, self.imgsz, 300, slot)
+        with torch.cuda.stream(self.s_det):
+            if resident_src is not None:
+                io_["src"].copy_(resident_src, non_blocking=True)
+            else:
+                for i, im in enumerate(images):
+                    io_["host"][i].copy_(torch.from_numpy(np.ascontiguousarray(im)))
+                io_["src"].copy_(io_["host"], non_blocking=True)
+            m.detect_device(io_, B, H, W, self.conf, 0.1, 300)
+            io_["host_count"].copy_(io_["out_count"], non_blocking=True)
+            io_["host_box"].copy_(io_["out_box"], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.s_det)
+        return dict(io=io_, ev=ev, B=B, H=H, W=W)
+
+    def _finish(self, h, ocr):
+        io_, B, H, W = h["io"], h["B"], h["H"], h["W"]
+        model, cap_model, processor = self.model, self.cmp["model"], self.cmp["processor"]
+        t0 = time.perf_counter()
+        h["ev"].synchronize()
+        t1 = time.perf_counter()
+        counts = io_["host_count"].tolist()
+        boxes = io_["host_box"]
+        whwh = torch.Tensor([W, H, W, H])
+        all_elems, crop_boxes, crop_img = [], [], []
+        for i in range(B):
+            xyxy = (boxes[i][:counts[i]] / whwh).tolist()
+            texts, obox = ocr[i]
+            oratio = (torch.tensor(obox) / whwh).tolist() if obox else None
+            elems, _ = host_glue.build_elements(xyxy, oratio, texts, W, H, self.iou_thr)
+            all_elems.append(elems)
+            for e in elems:
+                if e["content"] is None:
+                    crop_boxes.append(e["bbox"])
+                    crop_img.append(i)
+        n = len(crop_boxes)
+        t2 = time.perf_counter()
+        ids = None
+        if n:
+            dev = model.device
+            with torch.cuda.stream(self.s_cap):
+                plan = cap_model.plan_for(n, self.T, self.prompt)
+                d_boxes = torch.tensor(crop_boxes, dtype=torch.float32).to(dev, non_blocking=True)
+                d_bimg = torch.tensor(crop_img, dtype=torch.int32).to(dev, non_blocking=True)
+                key = ("crop_meta", B, H, W)
+                meta = model._io.get(key)
+                if meta is None:
+                    meta = dict(hw=torch.tensor([[H, W]] * B, dtype=torch.int32, device=dev),
+                                off=torch.tensor([i * H * W * 3 for i in range(B)], dtype=torch.int64, device=dev))
+                    model._io[key] = meta
+                status = torch.empty((n,), dtype=torch.int32, device=dev)
+                ops.crop_resize(io_["src"], meta["hw"], meta["off"], d_boxes, d_bimg, n, 64, plan.crops, status)
+                ids = cap_model.generate_from_device_crops(plan, n).cpu()
+        t3 = time.perf_counter()
+        texts_all = [t.strip() for t in processor.batch_decode(ids, skip_special_tokens=True)] if ids is not None else []
+        out, k = [], 0
+        for i in range(B):
+            mcap = sum(1 for e in all_elems[i] if e["content"] is None)
+            host_glue.fill_captions(all_elems[i], texts_all[k:k + mcap])
+            out.append((all_elems[i], ids[k:k + mcap] if ids is not None else torch.zeros((0, 1), dtype=torch.long)))
+            k += mcap
+        tm = self.timings
+        tm["detect_wait_s"] += t1 - t0; tm["glue_s"] += t2 - t1; tm["caption_s"] += t3 - t2
+        tm["n_boxes"] += sum(counts); tm["n_crops"] += n; tm["batches"] += 1
+        return out
+
+    @torch.inference_mode()
+    def run(self, batches, resident=None):
+        """batches: iterable of (images, ocr); resident: optional parallel iterable of device u8 tensors [B,H,W,3]."""
+        with torch.cuda.device(self.model.device):
+            it = iter(batches)
+            rit = iter(resident) if resident is not None else None
+            cur = next(it, None)
+            if cur is None:
+                return
+            slot = 0
+            h = self._submit(slot, cur[0], next(rit) if rit is not None else None)
+            while cur is not None:
+                nxt = next(it, None)
+                hn = None
+                if nxt is not None:
+                    slot ^= 1
+                    hn = self._submit(slot, nxt[0], next(rit) if rit is not None else None)
+                yield self._finish(h, cur[1])
+                cur, h = nxt, hn
+
+
 # ------------------------------------------------------------------------------------------------ reference API
 def _annotate(image_np: np.ndarray, boxes_xyxy_ratio, text_scale=0.4, text_padding=5, text_thickness=2, thickness=3):
     """Set-of-Marks overlay (numbered boxes).  Host post-step outside the hot path; a plain OpenCV

@@ -308,7 +308,7 @@ class YoloPlan:
                 f()
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=ops.capture_stream('yolo', self.dev)):
                 for f in self.ops:
                     f()
             self.graph = g

@@ -83,3 +83,22 @@ def test_get_som_labeled_img_api():
     ids = model.generate(input_ids=inputs["input_ids"], pixel_values=inputs["pixel_values"], max_new_tokens=20, num_beams=1, do_sample=False)
     texts2 = [t.strip() for t in proc.batch_decode(ids, skip_special_tokens=True)]
     assert texts2 == [e["content"] for e in elems if e["source"] == "box_yolo_content_yolo"]
+
+
+def test_pipelined_parser_equals_sequential():
+    """The 2-deep pipeline (detect of batch i+1 overlapping glue + caption of batch i, two streams) returns exactly what
+    the one-batch-at-a-time path returns."""
+    from omniparser_b200.utils import PipelinedParser
+    det, cmp_ = ge.standin_models(DEV)
+    batches = []
+    for b in range(4):
+        seeds = [40 + 2 * b, 41 + 2 * b]
+        batches.append(([synth.screenshot(s) for s in seeds], [synth.ocr_boxes(s) for s in seeds]))
+    ref = [parse_screenshots(imgs, det, cmp_, ocr, BOX_TRESHOLD=0.05, iou_threshold=0.7, max_new_tokens=8) for imgs, ocr in batches]
+    pp = PipelinedParser(det, cmp_, BOX_TRESHOLD=0.05, iou_threshold=0.7, max_new_tokens=8)
+    for rep in range(2):
+        got = list(pp.run(iter(batches)))
+        assert len(got) == len(ref)
+        for gb, rb in zip(got, ref):
+            for (ge_, gi), (re_, ri) in zip(gb, rb):
+                assert ge_ == re_ and torch.equal(gi, ri)
