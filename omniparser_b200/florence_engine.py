@@ -354,7 +354,7 @@ class FlorencePlan:
                 f()
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=ops.capture_stream('florence', self.dev)):
+            with torch.cuda.graph(g, stream=ops.capture_stream('florence', self.dev), capture_error_mode="thread_local"):
                 for f in lst:
                     f()
             setattr(self, which, g)

@@ -149,8 +149,11 @@ class PipelinedParser:
         self.s_det = torch.cuda.Stream(device=dev)
         self.s_cap = torch.cuda.Stream(device=dev)
         self.timings = ParseTimings(detect_wait_s=0.0, glue_s=0.0, caption_s=0.0, n_boxes=0, n_crops=0, batches=0)
+        from concurrent.futures import ThreadPoolExecutor
+        self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="b2p-submit")   # host staging copy off the main thread
 
     def _submit(self, slot: int, images, resident_src=None):
+        torch.cuda.set_device(self.model.device)
         B = len(images)
         H, W = images[0].shape[:2]
         m = self.model
@@ -233,11 +236,13 @@ class PipelinedParser:
             h = self._submit(slot, cur[0], next(rit) if rit is not None else None)
             while cur is not None:
                 nxt = next(it, None)
-                hn = None
+                fut = None
                 if nxt is not None:
                     slot ^= 1
-                    hn = self._submit(slot, nxt[0], next(rit) if rit is not None else None)
-                yield self._finish(h, cur[1])
+                    fut = self._pool.submit(self._submit, slot, nxt[0], next(rit) if rit is not None else None)
+                out = self._finish(h, cur[1])
+                hn = fut.result() if fut is not None else None
+                yield out
                 cur, h = nxt, hn
 
 
