@@ -152,8 +152,9 @@ class PipelinedParser:
         from concurrent.futures import ThreadPoolExecutor
         self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="b2p-submit")   # host staging copy off the main thread
 
+    @torch.inference_mode()
     def _submit(self, slot: int, images, resident_src=None):
-        torch.cuda.set_device(self.model.device)
+        torch.cuda.set_device(self.model.device)   # runs on the worker thread: device and inference mode are thread-local
         B = len(images)
         H, W = images[0].shape[:2]
         m = self.model
