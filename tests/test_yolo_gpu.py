@@ -154,3 +154,38 @@ def test_predict_end_to_end(setup):
         frac = (best > 0.9).float().mean().item()
         print(f"seed {seed}: gpu {len(gb)} boxes, fp32 oracle {len(kb32)} boxes, oracle boxes matched at IoU>0.9: {frac:.2f}")
         assert frac > 0.5
+
+
+def test_fullres_detect_config1(setup):
+    """BASELINE configs[1]: detect only, batch 1, 1920x1080 at full resolution (`scale_img=True, imgsz=(h, w)` ->
+    canvas 1088x1920, scale 1.0, no resample; ref:util/utils.py:391-397, ref:util/yolov9.py:52-61).  Head tensors vs the
+    fp32 oracle, and predict() vs the reference post-processing of its own heads."""
+    m, det = setup
+    img = synth.screenshot(5)
+    H, W = img.shape[:2]
+    imgsz = (H, W)
+    res = det.predict(img, conf=0.05, iou=0.1, imgsz=imgsz)[0].boxes
+    io = det._get_io(1, H, W, imgsz, 300)
+    plan = io["plan"]
+    canvas, scale, pl, pt = R.letterbox_numpy(img, imgsz)
+    assert canvas.shape == (1088, 1920, 3) and scale == 1.0 and (pl, pt) == (0, 4)
+    assert np.array_equal(plan.canvas[0].cpu().numpy(), canvas)
+    x = torch.from_numpy(canvas.astype(np.float32).transpose(2, 0, 1) / 255.0).unsqueeze(0)
+    _, _, raw = _oracle_taps(m, x)
+    outs = []
+    for i in range(3):
+        gc = plan.cls_out[i].permute(0, 3, 1, 2).cpu()
+        gb = plan.box_out[i].permute(0, 3, 1, 2).cpu().contiguous()
+        eb = (gb - raw[("box", i)]).abs().max().item()
+        ec = (gc - raw[("cls", i)]).abs().max().item()
+        print(f"full-res head {i} {tuple(gc.shape)}: box-logit err {eb:.4f}, cls-logit err {ec:.4f}")
+        assert eb < 0.3 and ec < 0.3
+        b, _, h, w = gb.shape
+        outs += [gc, (gb.view(b, 4, 16, h, w).softmax(2) * torch.arange(16.0).view(1, 1, 16, 1, 1)).sum(2)]
+    scores, boxes = R.decode_heads(outs)
+    bb, ss, cc = R.filter_candidates(scores[0], boxes[0], 0.05, scale, pl, pt)
+    keep, kb, ks = R.nms_and_clamp(bb, ss, cc, 0.1, 300, W, H)
+    gbx, gs = res.xyxy.cpu(), res.conf.cpu()
+    print(f"full-res: {len(bb)} candidates, {len(kb)} kept (gpu {len(gbx)})")
+    assert len(gbx) == len(kb)
+    assert (gbx - kb).abs().max().item() < 2e-3 and (gs - ks).abs().max().item() < 1e-6
