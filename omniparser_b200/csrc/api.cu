@@ -4,6 +4,7 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <stdlib.h>
 
 namespace b2p {
 static std::mutex g_err_mu;
@@ -16,6 +17,10 @@ int set_error(const char* msg) {
   return -1;
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static const bool on = getenv("B2P_NO_PDL") == nullptr;
+  return on;
+}
 }  // namespace b2p
 
 using namespace b2p;

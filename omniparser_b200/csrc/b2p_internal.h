@@ -37,4 +37,23 @@ struct ConvGemm {
 
 int gemm_launch(const ConvGemm& d, cudaStream_t st);
 
+// Programmatic dependent launch for the small SIMT kernels: launched with the stream-serialization attribute they may
+// be scheduled while the preceding (persistent, early-triggering) GEMM drains; each such kernel calls pdl_wait() before
+// touching global memory.  They never trigger their own dependents early (their grids are not guaranteed resident).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
 }  // namespace b2p

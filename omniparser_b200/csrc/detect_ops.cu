@@ -33,6 +33,7 @@ __device__ __forceinline__ void st8(__half* p, const uint4& v) { *reinterpret_ca
 // exactly the zero padding the following 3x3 stride-2 pad-1 conv would see (keeps H, W even for the TMA view).
 __global__ void adown_pool_kernel(const __half* __restrict__ x, long long ldx, int B, int H, int W, int C,
                                   __half* __restrict__ x1, long long ld1, __half* __restrict__ x2, long long ld2) {
+  pdl_wait();   // PDL: inputs come from the previous kernel in the stream
   const int c8n = C / 16;   // vectors per half
   const long long n1 = (long long)B * H * W * c8n;
   const int Ho = H / 2, Wo = W / 2;
@@ -84,6 +85,7 @@ __global__ void adown_pool_kernel(const __half* __restrict__ x, long long ldx, i
 // MaxPool2d(k, stride 1, pad k/2) on a channel slice (SPPELAN, k = 5).
 __global__ void maxpool_s1_kernel(const __half* __restrict__ x, long long ldx, int B, int H, int W, int C, int k,
                                   __half* __restrict__ y, long long ldy) {
+  pdl_wait();   // PDL: inputs come from the previous kernel in the stream
   const int cvn = C / 8;
   const long long n = (long long)B * H * W * cvn;
   const int r = k / 2;
@@ -120,6 +122,7 @@ __global__ void maxpool_s1_kernel(const __half* __restrict__ x, long long ldx, i
 // nn.Upsample(scale_factor=2, mode='nearest') into a channel slice.
 __global__ void upsample2x_kernel(const __half* __restrict__ x, long long ldx, int B, int H, int W, int C,
                                   __half* __restrict__ y, long long ldy) {
+  pdl_wait();   // PDL: inputs come from the previous kernel in the stream
   const int cvn = C / 8;
   const int Ho = 2 * H, Wo = 2 * W;
   const long long n = (long long)B * Ho * Wo * cvn;
@@ -140,6 +143,7 @@ struct FuseArgs { FuseSrc s[5]; int n; };
 // CBFuse (common.py::CBFuse): out = sum_i nearest_upsample(src_i) + last, summed in that order in fp32.
 __global__ void cbfuse_kernel(FuseArgs a, const __half* __restrict__ last, long long ldl, int B, int H, int W, int C,
                               __half* __restrict__ y, long long ldy) {
+  pdl_wait();   // PDL: inputs come from the previous kernel in the stream
   const int cvn = C / 8;
   const long long n = (long long)B * H * W * cvn;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -185,7 +189,7 @@ int b2p_adown_pool(const void* x, long long ldx, int B, int H, int W, int C, voi
                    long long ld2, cudaStream_t st) {
   if ((H & 1) || (W & 1) || (C % 16)) return set_error("adown_pool: H, W must be even and C a multiple of 16");
   const long long n = (long long)B * H * W * (C / 16) + (long long)B * (H / 2) * (W / 2) * (C / 16);
-  adown_pool_kernel<<<grid_for(n, 256), 256, 0, st>>>((const __half*)x, ldx, B, H, W, C, (__half*)x1, ld1, (__half*)x2, ld2);
+  launch_pdl(adown_pool_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, (const __half*)x, ldx, B, H, W, C, (__half*)x1, ld1, (__half*)x2, ld2);
   B2P_CHECK_LAUNCH();
   return 0;
 }
@@ -193,7 +197,7 @@ int b2p_adown_pool(const void* x, long long ldx, int B, int H, int W, int C, voi
 int b2p_maxpool_s1(const void* x, long long ldx, int B, int H, int W, int C, int k, void* y, long long ldy, cudaStream_t st) {
   if (C % 8) return set_error("maxpool_s1: C must be a multiple of 8");
   const long long n = (long long)B * H * W * (C / 8);
-  maxpool_s1_kernel<<<grid_for(n, 256), 256, 0, st>>>((const __half*)x, ldx, B, H, W, C, k, (__half*)y, ldy);
+  launch_pdl(maxpool_s1_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, (const __half*)x, ldx, B, H, W, C, k, (__half*)y, ldy);
   B2P_CHECK_LAUNCH();
   return 0;
 }
@@ -201,7 +205,7 @@ int b2p_maxpool_s1(const void* x, long long ldx, int B, int H, int W, int C, int
 int b2p_upsample2x(const void* x, long long ldx, int B, int H, int W, int C, void* y, long long ldy, cudaStream_t st) {
   if (C % 8) return set_error("upsample2x: C must be a multiple of 8");
   const long long n = (long long)B * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<grid_for(n, 256), 256, 0, st>>>((const __half*)x, ldx, B, H, W, C, (__half*)y, ldy);
+  launch_pdl(upsample2x_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, (const __half*)x, ldx, B, H, W, C, (__half*)y, ldy);
   B2P_CHECK_LAUNCH();
   return 0;
 }
@@ -222,7 +226,7 @@ int b2p_cbfuse(int nsrc, const void* const* srcs, const long long* lds, const in
     a.s[i].W = W >> shifts[i];
   }
   const long long n = (long long)B * H * W * (C / 8);
-  cbfuse_kernel<<<grid_for(n, 256), 256, 0, st>>>(a, (const __half*)last, ldl, B, H, W, C, (__half*)y, ldy);
+  launch_pdl(cbfuse_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, a, (const __half*)last, ldl, B, H, W, C, (__half*)y, ldy);
   B2P_CHECK_LAUNCH();
   return 0;
 }

@@ -47,6 +47,7 @@ __device__ __forceinline__ void store_act4(__half* row, int c, int split, const 
 __global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ g,
                                  const float* __restrict__ b, float eps, int T, int C, __half* __restrict__ o16,
                                  long long ld16, float* __restrict__ o32, long long ld32, int split) {
+  pdl_wait();   // PDL: inputs come from the previous kernel in the stream
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= T) return;
@@ -79,6 +80,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, con
 __global__ void dwconv_ln_kernel(const float* __restrict__ x, int B, int H, int W, int C, const float* __restrict__ w9c,
                                  const float* __restrict__ bias, float* __restrict__ y, const float* __restrict__ g,
                                  const float* __restrict__ bt, float eps, __half* __restrict__ o16, int split) {
+  pdl_wait();   // PDL: inputs come from the previous kernel in the stream
   const long long tok = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (tok >= (long long)B * H * W) return;
@@ -131,6 +133,7 @@ __global__ void dwconv_ln_kernel(const float* __restrict__ x, int B, int H, int 
 __global__ void dwconv3x3_res_kernel(const float* __restrict__ x, int B, int H, int W, int C,
                                      const float* __restrict__ w /*[9][C]*/, const float* __restrict__ bias,
                                      float* __restrict__ y) {
+  pdl_wait();   // PDL: inputs come from the previous kernel in the stream
   const long long n = (long long)B * H * W * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int c = int(i % C);
@@ -162,6 +165,7 @@ __global__ void dwconv3x3_res_kernel(const float* __restrict__ x, int B, int H, 
 template <int D>
 __global__ void window_attn_kernel(const float* __restrict__ qkv, const float* __restrict__ qkv_bias, int B, int H,
                                    int W, int C, int heads, int win, __half* __restrict__ out, int split) {
+  pdl_wait();   // PDL: inputs come from the previous kernel in the stream
   extern __shared__ float4 sm4[];
   constexpr int D4 = D / 4;
   const int nwx = (W + win - 1) / win, nwy = (H + win - 1) / win;
@@ -244,6 +248,7 @@ __global__ void window_attn_kernel(const float* __restrict__ qkv, const float* _
 // One CTA (1024 threads = 32 x 32) per (batch, group); tokens streamed through shared memory in chunks.
 __global__ void __launch_bounds__(256) channel_attn_kernel(const float* __restrict__ qkv, int N, int C, int groups,
                                                            __half* __restrict__ out, int split) {
+  pdl_wait();   // PDL: inputs come from the previous kernel in the stream
   constexpr int D = 32, CH = 64;
   __shared__ float qs[CH][D + 1], ks[CH][D + 1];
   __shared__ float P[D][D + 1];
@@ -305,6 +310,7 @@ struct MhaArgs {
 };
 
 __global__ void mha_kernel(MhaArgs a) {
+  pdl_wait();   // PDL: inputs come from the previous kernel in the stream
   const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int total = a.B * a.heads * a.Lq;
@@ -354,6 +360,78 @@ __global__ void mha_kernel(MhaArgs a) {
   store_act(orow, h * 64 + 2 * lane + 1, a.split, acc.y * inv);
 }
 
+// Small-L variant (64x64-crop mode: L = 13 encoder tokens, <= 21 decoder positions): one THREAD per (batch, head,
+// query) with q and the output accumulator in registers; K/V rows are read as float4 (the queries of one (b, h) share
+// them through L1).  Replaces 5 warp shuffles per key of mha_kernel with straight FMAs.
+__global__ void __launch_bounds__(128) mha_small_kernel(MhaArgs a) {
+  pdl_wait();
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = a.B * a.heads * a.Lq;
+  if (tid >= total) return;
+  const int qi = tid % a.Lq;
+  const int h = (tid / a.Lq) % a.heads;
+  const int b = tid / (a.Lq * a.heads);
+  const int HD = a.heads * 64;
+  float4 q[16], acc[16];
+  const float4* qp = reinterpret_cast<const float4*>(a.q + ((long long)b * a.Lq + qi) * a.ldq + h * 64);
+#pragma unroll
+  for (int d = 0; d < 16; ++d) {
+    q[d] = qp[d];
+    q[d].x *= 0.125f; q[d].y *= 0.125f; q[d].z *= 0.125f; q[d].w *= 0.125f;
+    acc[d] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  int Lk = a.Lk;
+  const float *kb, *vb;
+  long long ldk;
+  if (a.kcache) {
+    const int t = *a.step;
+    const float4* kn = reinterpret_cast<const float4*>(a.knew + (long long)b * a.ldnew + h * 64);
+    const float4* vn = reinterpret_cast<const float4*>(a.vnew + (long long)b * a.ldnew + h * 64);
+    float4* kc = reinterpret_cast<float4*>(a.kcache + ((long long)b * a.tmax + t) * HD + h * 64);
+    float4* vc = reinterpret_cast<float4*>(a.vcache + ((long long)b * a.tmax + t) * HD + h * 64);
+#pragma unroll
+    for (int d = 0; d < 16; ++d) { kc[d] = kn[d]; vc[d] = vn[d]; }
+    Lk = t + 1;
+    kb = a.kcache + (long long)b * a.tmax * HD + h * 64;
+    vb = a.vcache + (long long)b * a.tmax * HD + h * 64;
+    ldk = HD;
+  } else {
+    kb = a.k + (long long)b * a.Lk * a.ldk + h * 64;
+    vb = a.v + (long long)b * a.Lk * a.ldk + h * 64;
+    ldk = a.ldk;
+  }
+  float m = -INFINITY, l = 0.f;
+  for (int j = 0; j < Lk; ++j) {
+    const float4* kr = reinterpret_cast<const float4*>(kb + j * ldk);
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) {
+      const float4 kk = kr[d];
+      s += (q[d].x * kk.x + q[d].y * kk.y) + (q[d].z * kk.z + q[d].w * kk.w);
+    }
+    if (s > m) {
+      const float r = __expf(m - s);
+      l *= r;
+#pragma unroll
+      for (int d = 0; d < 16; ++d) { acc[d].x *= r; acc[d].y *= r; acc[d].z *= r; acc[d].w *= r; }
+      m = s;
+    }
+    const float p = __expf(s - m);
+    l += p;
+    const float4* vr = reinterpret_cast<const float4*>(vb + j * ldk);
+#pragma unroll
+    for (int d = 0; d < 16; ++d) {
+      const float4 vv = vr[d];
+      acc[d].x += p * vv.x; acc[d].y += p * vv.y; acc[d].z += p * vv.z; acc[d].w += p * vv.w;
+    }
+  }
+  const float inv = 1.f / l;
+  __half* orow = a.out + ((long long)b * a.Lq + qi) * a.ldo;
+#pragma unroll
+  for (int d = 0; d < 16; ++d)
+    store_act4(orow, h * 64 + 4 * d, a.split, make_float4(acc[d].x * inv, acc[d].y * inv, acc[d].z * inv, acc[d].w * inv));
+}
+
 // ---------------------------------------------------------------------------------------- embeddings
 // Encoder input: row (b, i) = (i < n_img ? image_feat[b][i] : E[prompt[i - n_img]]) + P[i + 2]
 // (hf:models/florence2/modeling_florence2.py:742-761; learned positions with offset 2, hf:models/bart/
@@ -361,6 +439,7 @@ __global__ void mha_kernel(MhaArgs a) {
 __global__ void encoder_embed_kernel(const float* __restrict__ img, int n_img, const float* __restrict__ E,
                                      const int* __restrict__ prompt, int n_prompt, const float* __restrict__ P, int B,
                                      int C, float* __restrict__ out) {
+  pdl_wait();   // PDL: inputs come from the previous kernel in the stream
   const int L = n_img + n_prompt;
   const long long n = (long long)B * L * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -375,6 +454,7 @@ __global__ void encoder_embed_kernel(const float* __restrict__ img, int n_img, c
 __global__ void decoder_embed_kernel(const float* __restrict__ E, const int* __restrict__ seq, int seq_ld,
                                      const int* __restrict__ step, const float* __restrict__ P, int B, int C,
                                      float* __restrict__ out) {
+  pdl_wait();   // PDL: inputs come from the previous kernel in the stream
   const int t = *step;
   const long long n = (long long)B * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -388,6 +468,7 @@ __global__ void decoder_embed_kernel(const float* __restrict__ E, const int* __r
 // rows: [mean over HW] ++ [HW tokens]; fp16 out [B][1+HW][C] feeding the 1024->768 projection GEMM.
 __global__ void projector_prep_kernel(const float* __restrict__ x /*[B][HW][C]*/, const float* __restrict__ pos /*[HW][C]*/,
                                       int B, int HW, int C, __half* __restrict__ out, int split) {
+  pdl_wait();   // PDL: inputs come from the previous kernel in the stream
   const long long n = (long long)B * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int c = int(i % C);
@@ -418,6 +499,7 @@ struct PickArgs {
 };
 
 __global__ void __launch_bounds__(1024) greedy_pick_kernel(PickArgs a) {
+  pdl_wait();   // PDL: inputs come from the previous kernel in the stream
   const int b = blockIdx.x;
   const int t = *a.step;            // tokens so far = t + 1
   const int cur_len = t + 1;
@@ -446,12 +528,44 @@ __global__ void __launch_bounds__(1024) greedy_pick_kernel(PickArgs a) {
   if (cur_len == a.max_len - 1 && a.forced_eos >= 0) force = a.forced_eos;
   float best = -INFINITY;
   int besti = 0x7fffffff;
-  for (int v = threadIdx.x; v < a.V; v += blockDim.x) {
-    float s = lg[v];
-    for (int k = 0; k < nbanned; ++k) if (banned[k] == v) s = -INFINITY;
-    if (force >= 0) s = (v == force) ? 0.f : -INFINITY;
-    if (a.dump) a.dump[(long long)b * a.V + v] = s;
-    if (s > best || (s == best && v < besti)) { best = s; besti = v; }
+  if (a.dump || force < 0) {
+    const bool vec = !a.dump && force < 0 && (a.ld % 2 == 0) && ((reinterpret_cast<uintptr_t>(lg) & 7) == 0);
+    if (vec) {
+      // plain scan; the (<= 19-entry) ban list is only consulted when a value would become the running maximum
+      const float2* lp = reinterpret_cast<const float2*>(lg);
+      const int V2 = a.V >> 1;
+      for (int v2 = threadIdx.x; v2 < V2; v2 += blockDim.x) {
+        const float2 t2 = lp[v2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float sv = e ? t2.y : t2.x;
+          const int v = 2 * v2 + e;
+          if (sv > best) {   // ascending v within a thread: ties keep the earlier index
+            bool ban = false;
+            for (int k = 0; k < nbanned; ++k) ban = ban || (banned[k] == v);
+            if (!ban) { best = sv; besti = v; }
+          }
+        }
+      }
+      if ((a.V & 1) && threadIdx.x == 0) {
+        const int v = a.V - 1;
+        const float sv = lg[v];
+        bool ban = false;
+        for (int k = 0; k < nbanned; ++k) ban = ban || (banned[k] == v);
+        if (!ban && sv > best) { best = sv; besti = v; }
+      }
+    } else {
+      for (int v = threadIdx.x; v < a.V; v += blockDim.x) {
+        float sv = lg[v];
+        for (int k = 0; k < nbanned; ++k) if (banned[k] == v) sv = -INFINITY;
+        if (force >= 0) sv = (v == force) ? 0.f : -INFINITY;
+        if (a.dump) a.dump[(long long)b * a.V + v] = sv;
+        if (sv > best || (sv == best && v < besti)) { best = sv; besti = v; }
+      }
+    }
+  } else if (threadIdx.x == 0) {
+    best = 0.f;          // forced token: every other score is -inf (hf:generation/logits_process.py:1552,1597)
+    besti = force;
   }
   for (int o = 16; o; o >>= 1) {
     const float ov = __shfl_xor_sync(0xffffffffu, best, o);
@@ -473,7 +587,10 @@ __global__ void __launch_bounds__(1024) greedy_pick_kernel(PickArgs a) {
   }
 }
 
-__global__ void step_advance_kernel(int* step) { *step += 1; }
+__global__ void step_advance_kernel(int* step) {
+  pdl_wait();
+  *step += 1;
+}
 
 static inline int grid_for(long long n, int threads) {
   long long b = (n + threads - 1) / threads;
@@ -492,7 +609,7 @@ int b2p_layernorm(const float* x, long long ldx, const float* gamma, const float
   if (T <= 0) return 0;
   if (C % 4 || C > 1024 || (ldx % 4) || (ld32 % 4) || (ld16 % 4)) return set_error("layernorm: C, ld must be multiples of 4, C <= 1024");
   const int wpb = 8;
-  layernorm_kernel<<<(T + wpb - 1) / wpb, wpb * 32, 0, st>>>(x, ldx, gamma, beta, eps, T, C, (__half*)out16, ld16, out32, ld32, split ? C : 0);
+  launch_pdl(layernorm_kernel, dim3((T + wpb - 1) / wpb), dim3(wpb * 32), 0, st, x, ldx, gamma, beta, eps, T, C, (__half*)out16, ld16, out32, ld32, split ? C : 0);
   B2P_CHECK_LAUNCH();
   return 0;
 }
@@ -502,14 +619,14 @@ int b2p_dwconv_ln(const float* x, int B, int H, int W, int C, const float* w9c, 
   if (C % 4 || C > 1024) return set_error("dwconv_ln: C must be a multiple of 4 and <= 1024");
   const long long T = (long long)B * H * W;
   const int wpb = 8;
-  dwconv_ln_kernel<<<int((T + wpb - 1) / wpb), wpb * 32, 0, st>>>(x, B, H, W, C, w9c, bias, y, gamma, beta, eps, (__half*)out16, split ? C : 0);
+  launch_pdl(dwconv_ln_kernel, dim3(int((T + wpb - 1) / wpb)), dim3(wpb * 32), 0, st, x, B, H, W, C, w9c, bias, y, gamma, beta, eps, (__half*)out16, split ? C : 0);
   B2P_CHECK_LAUNCH();
   return 0;
 }
 
 int b2p_dwconv3x3_res(const float* x, int B, int H, int W, int C, const float* w9c, const float* bias, float* y,
                       cudaStream_t st) {
-  dwconv3x3_res_kernel<<<grid_for((long long)B * H * W * C, 256), 256, 0, st>>>(x, B, H, W, C, w9c, bias, y);
+  launch_pdl(dwconv3x3_res_kernel, dim3(grid_for((long long)B * H * W * C, 256)), dim3(256), 0, st, x, B, H, W, C, w9c, bias, y);
   B2P_CHECK_LAUNCH();
   return 0;
 }
@@ -525,14 +642,14 @@ int b2p_window_attn(const float* qkv, const float* qkv_bias, int B, int H, int W
     attr = true;
   }
   if (smem > 64 * 1024) return set_error("window_attn: window too large");
-  window_attn_kernel<32><<<B * nw * heads, 160, smem, st>>>(qkv, qkv_bias, B, H, W, C, heads, win, (__half*)out, split ? C : 0);
+  launch_pdl(window_attn_kernel<32>, dim3(B * nw * heads), dim3(160), smem, st, qkv, qkv_bias, B, H, W, C, heads, win, (__half*)out, split ? C : 0);
   B2P_CHECK_LAUNCH();
   return 0;
 }
 
 int b2p_channel_attn(const float* qkv, int B, int N, int C, int groups, void* out, int split, cudaStream_t st) {
   if (C / groups != 32) return set_error("channel_attn: channels per group must be 32");
-  channel_attn_kernel<<<B * groups, 256, 0, st>>>(qkv, N, C, groups, (__half*)out, split ? C : 0);
+  launch_pdl(channel_attn_kernel, dim3(B * groups), dim3(256), 0, st, qkv, N, C, groups, (__half*)out, split ? C : 0);
   B2P_CHECK_LAUNCH();
   return 0;
 }
@@ -544,7 +661,10 @@ int b2p_mha(const float* q, long long ldq, const float* k, const float* v, long 
   a.q = q; a.ldq = ldq; a.k = k; a.v = v; a.ldk = ldk;
   a.B = B; a.Lq = Lq; a.Lk = Lk; a.heads = heads; a.out = (__half*)out; a.ldo = ldo; a.split = split ? heads * 64 : 0;
   const int total = B * heads * Lq;
-  mha_kernel<<<(total + 7) / 8, 256, 0, st>>>(a);
+  if (Lk <= 64 && (ldq % 4) == 0 && (ldk % 4) == 0)
+    launch_pdl(mha_small_kernel, dim3((total + 127) / 128), dim3(128), 0, st, a);
+  else
+    launch_pdl(mha_kernel, dim3((total + 7) / 8), dim3(256), 0, st, a);
   B2P_CHECK_LAUNCH();
   return 0;
 }
@@ -558,14 +678,17 @@ int b2p_mha_cached(const float* q, long long ldq, const float* knew, const float
   a.kcache = kcache; a.vcache = vcache; a.tmax = tmax; a.step = step;
   a.B = B; a.Lq = 1; a.Lk = 0; a.heads = heads; a.out = (__half*)out; a.ldo = ldo; a.split = split ? heads * 64 : 0;
   const int total = B * heads;
-  mha_kernel<<<(total + 7) / 8, 256, 0, st>>>(a);
+  if (tmax <= 64 && (ldq % 4) == 0 && (ldnew % 4) == 0)
+    launch_pdl(mha_small_kernel, dim3((total + 127) / 128), dim3(128), 0, st, a);
+  else
+    launch_pdl(mha_kernel, dim3((total + 7) / 8), dim3(256), 0, st, a);
   B2P_CHECK_LAUNCH();
   return 0;
 }
 
 int b2p_encoder_embed(const float* img, int n_img, const float* E, const int* prompt, int n_prompt, const float* P,
                       int B, int C, float* out, cudaStream_t st) {
-  encoder_embed_kernel<<<grid_for((long long)B * (n_img + n_prompt) * C, 256), 256, 0, st>>>(img, n_img, E, prompt,
+  launch_pdl(encoder_embed_kernel, dim3(grid_for((long long)B * (n_img + n_prompt) * C, 256)), dim3(256), 0, st, img, n_img, E, prompt,
                                                                                             n_prompt, P, B, C, out);
   B2P_CHECK_LAUNCH();
   return 0;
@@ -573,13 +696,13 @@ int b2p_encoder_embed(const float* img, int n_img, const float* E, const int* pr
 
 int b2p_decoder_embed(const float* E, const int* seq, int seq_ld, const int* step, const float* P, int B, int C,
                       float* out, cudaStream_t st) {
-  decoder_embed_kernel<<<grid_for((long long)B * C, 256), 256, 0, st>>>(E, seq, seq_ld, step, P, B, C, out);
+  launch_pdl(decoder_embed_kernel, dim3(grid_for((long long)B * C, 256)), dim3(256), 0, st, E, seq, seq_ld, step, P, B, C, out);
   B2P_CHECK_LAUNCH();
   return 0;
 }
 
 int b2p_projector_prep(const float* x, const float* pos, int B, int HW, int C, void* out, int split, cudaStream_t st) {
-  projector_prep_kernel<<<grid_for((long long)B * C, 256), 256, 0, st>>>(x, pos, B, HW, C, (__half*)out, split ? C : 0);
+  launch_pdl(projector_prep_kernel, dim3(grid_for((long long)B * C, 256)), dim3(256), 0, st, x, pos, B, HW, C, (__half*)out, split ? C : 0);
   B2P_CHECK_LAUNCH();
   return 0;
 }
@@ -591,13 +714,13 @@ int b2p_greedy_pick(const float* logits, long long ld, int V, int B, int* seq, i
   a.logits = logits; a.ld = ld; a.V = V; a.seq = seq; a.seq_ld = seq_ld; a.finished = finished; a.step = step;
   a.ngram = ngram; a.forced_bos = forced_bos; a.forced_eos = forced_eos; a.eos = eos; a.pad = pad; a.max_len = max_len;
   a.dump = dump; a.n_unfinished = n_unfinished;
-  greedy_pick_kernel<<<B, 1024, 0, st>>>(a);
+  launch_pdl(greedy_pick_kernel, dim3(B), dim3(1024), 0, st, a);
   B2P_CHECK_LAUNCH();
   return 0;
 }
 
 int b2p_step_advance(int* step, cudaStream_t st) {
-  step_advance_kernel<<<1, 1, 0, st>>>(step);
+  launch_pdl(step_advance_kernel, dim3(1), dim3(1), 0, st, step);
   B2P_CHECK_LAUNCH();
   return 0;
 }

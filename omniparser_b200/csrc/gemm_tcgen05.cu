@@ -264,13 +264,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_wait(bar_aempty + 8 * stageA, phaseA ^ 1);
             const uint32_t fa = bar_afull + 8 * stageA;
             mbar_expect_tx(fa, g.a_bytes);
-            tma_load_4d(smem_base + stageA * g.a_slot, &tmA, fa, cb * 64, x0 - 1, y0 - 1, img);
+            tma_load_4d(smem_base + stageA * g.a_slot, &tmA, fa, cb * g.bk, x0 - 1, y0 - 1, img);
             if (++stageA == g.stagesA) { stageA = 0; phaseA ^= 1; }
             for (int tap = 0; tap < 9; ++tap) {
               mbar_wait(bar_empty + 8 * stage, phase ^ 1);
               const uint32_t fb = bar_full + 8 * stage;
               mbar_expect_tx(fb, g.b_bytes);
-              tma_load_2d(smem_base + a_region + stage * stage_bytes, &tmB, fb, tap * g.cin + cb * 64, n0);
+              tma_load_2d(smem_base + a_region + stage * stage_bytes, &tmB, fb, tap * g.cin + cb * g.bk, n0);
               if (++stage == g.stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -324,15 +324,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               mbar_wait(bar_full + 8 * stage, phase);
               tc_fence_after();
               const int ky = tap / 3, kx = tap - ky * 3;
-              const uint32_t sa = sa0 + uint32_t(ky * g.tw + kx) * 128u;      // shifted view of the halo tile
+              const uint32_t sa = sa0 + uint32_t(ky * g.tw + kx) * uint32_t(2 * g.bk);   // shifted view of the halo tile
               const uint32_t sb = smem_base + a_region + stage * stage_bytes;
               // The 128B-swizzle pattern is anchored at the 1024-B aligned slot base (that is how TMA wrote it), so the
               // "matrix base offset" field stays 0 even though the start address points into the middle of an atom:
               // the XOR phase is taken from the address bits, exactly as for the +32 B K-advance.
               const uint64_t da = g.desc_hi | uint64_t((sa & 0x3FFFF) >> 4);
               const uint64_t db = g.desc_hi | uint64_t((sb & 0x3FFFF) >> 4);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
+              for (int k = 0; k < ksteps; ++k)
                 umma_f16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), g.idesc, ((cb - kb0) | tap | k) != 0);
               umma_commit(bar_empty + 8 * stage);
               if (++stage == g.stages) { stage = 0; phase ^= 1; }
@@ -630,7 +629,8 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
   if (d.mode == 0 && (d.K % 8 != 0 || d.lda % 8 != 0)) return set_error("gemm: K and lda must be multiples of 8");
   if ((reinterpret_cast<uintptr_t>(d.A) & 15) || (reinterpret_cast<uintptr_t>(d.B) & 15)) return set_error("gemm: operands must be 16-byte aligned");
   static const bool no_halo = getenv("B2P_NO_HALO") != nullptr;
-  const bool halo = (d.mode == 1) && (bk == 64) && !no_halo;
+  static const bool no_halo32 = getenv("B2P_NO_HALO32") != nullptr;
+  const bool halo = (d.mode == 1) && !no_halo && (bk == 64 || !no_halo32);
   g.mode = halo ? 3 : d.mode;
   g.N = d.N;
   g.bk = bk;
@@ -677,8 +677,8 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
       }
       g.tw = btw + 2; g.tw_valid = btw; g.th = bth;
       g.num_kb = g.cin_blocks;                                  // pipeline unit = one channel block (9 taps)
-      g.a_bytes = uint32_t(bth + 2) * (btw + 2) * 128;
-      g.a_slot = (uint32_t(2 * (btw + 2) + 2 + 128) * 128 + 1023) & ~1023u;
+      g.a_bytes = uint32_t(bth + 2) * (btw + 2) * uint32_t(2 * bk);
+      g.a_slot = (uint32_t(2 * (btw + 2) + 2 + 128) * uint32_t(2 * bk) + 1023) & ~1023u;
     } else {
       g.tw = btw; g.tw_valid = btw; g.th = bth;
       g.a_bytes = uint32_t(btw) * bth * bk * 2;
@@ -689,7 +689,7 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
     if (halo) {
       cuuint64_t dims[4] = {cuuint64_t(d.Cin), cuuint64_t(d.W), cuuint64_t(d.H), cuuint64_t(d.batch)};
       cuuint64_t str[3] = {ld * 2, ld * 2 * d.W, ld * 2 * d.W * d.H};
-      cuuint32_t box[4] = {64, cuuint32_t(btw + 2), cuuint32_t(bth + 2), 1};
+      cuuint32_t box[4] = {cuuint32_t(bk), cuuint32_t(btw + 2), cuuint32_t(bth + 2), 1};
       if (int e = encode(&tmA, d.bf16, 4, d.A, dims, str, box, bk)) return e;
     } else if (d.mode == 1) {
       cuuint64_t dims[4] = {cuuint64_t(d.Cin), cuuint64_t(d.W), cuuint64_t(d.H), cuuint64_t(d.batch)};

@@ -122,6 +122,7 @@ __global__ void lanczos_h_kernel(const unsigned char* __restrict__ src, int B, i
 __global__ void lanczos_v_paste_kernel(const unsigned char* __restrict__ tmp, int B, int H, int Wo, int Ho,
                                        const int* __restrict__ bounds, const int* __restrict__ kk, int ksize,
                                        int Tw, int Th, int pad_l, int pad_t, unsigned char* __restrict__ canvas) {
+  pdl_wait();   // PDL: inputs come from the previous kernel in the stream
   const long long n = (long long)B * Th * Tw;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int x = int(i % Tw);
@@ -152,6 +153,7 @@ __global__ void lanczos_v_paste_kernel(const unsigned char* __restrict__ tmp, in
 __global__ void im2col_u8_kernel(const unsigned char* __restrict__ img, int B, int H, int W, int k, int s, int p,
                                  int Ho, int Wo, int Kpad, const float* __restrict__ lut /*[3][256]*/,
                                  __half* __restrict__ out, int split) {
+  pdl_wait();   // PDL: inputs come from the previous kernel in the stream
   const long long n = (long long)B * Ho * Wo;
   const int K = k * k * 3;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -193,6 +195,7 @@ __global__ void crop_resize_kernel(const unsigned char* __restrict__ imgs, const
                                    const long long* __restrict__ img_off, const float* __restrict__ boxes /*[n][4] ratios*/,
                                    const int* __restrict__ box_img, int out_hw, unsigned char* __restrict__ out,
                                    int* __restrict__ status) {
+  pdl_wait();   // PDL: inputs come from the previous kernel in the stream
   const int n = blockIdx.x;
   const int im = box_img[n];
   const int H = img_hw[2 * im], W = img_hw[2 * im + 1];
@@ -293,7 +296,7 @@ int b2p_letterbox(const unsigned char* src, int B, int H, int W, int Wr, int Hr,
   Coeffs cv{};
   if (Hr != H)
     if (int e = get_coeffs(H, Hr, &cv)) return e;
-  lanczos_v_paste_kernel<<<grid_for((long long)B * Th * Tw, 256), 256, 0, st>>>(hsrc, B, H, hW, Hr, cv.d_bounds, cv.d_kk, cv.ksize,
+  launch_pdl(lanczos_v_paste_kernel, dim3(grid_for((long long)B * Th * Tw, 256)), dim3(256), 0, st, hsrc, B, H, hW, Hr, cv.d_bounds, cv.d_kk, cv.ksize,
                                                                               Tw, Th, pad_l, pad_t, canvas);
   B2P_CHECK_LAUNCH();
   return 0;
@@ -303,7 +306,7 @@ int b2p_im2col_u8(const unsigned char* img, int B, int H, int W, int k, int s, i
                   void* out, int split, cudaStream_t st) {
   if (Kpad % 8 || Kpad < k * k * 3) return set_error("im2col_u8: Kpad must be a multiple of 8 and >= 3*k*k");
   const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;
-  im2col_u8_kernel<<<grid_for((long long)B * Ho * Wo, 128), 128, 0, st>>>(img, B, H, W, k, s, p, Ho, Wo, Kpad, lut, (__half*)out, split);
+  launch_pdl(im2col_u8_kernel, dim3(grid_for((long long)B * Ho * Wo, 128)), dim3(128), 0, st, img, B, H, W, k, s, p, Ho, Wo, Kpad, lut, (__half*)out, split);
   B2P_CHECK_LAUNCH();
   return 0;
 }
@@ -311,7 +314,7 @@ int b2p_im2col_u8(const unsigned char* img, int B, int H, int W, int k, int s, i
 int b2p_crop_resize(const unsigned char* imgs, const int* img_hw, const long long* img_off, const float* boxes,
                     const int* box_img, int n_box, int out_hw, unsigned char* out, int* status, cudaStream_t st) {
   if (n_box <= 0) return 0;
-  crop_resize_kernel<<<n_box, 256, 0, st>>>(imgs, img_hw, img_off, boxes, box_img, out_hw, out, status);
+  launch_pdl(crop_resize_kernel, dim3(n_box), dim3(256), 0, st, imgs, img_hw, img_off, boxes, box_img, out_hw, out, status);
   B2P_CHECK_LAUNCH();
   return 0;
 }
