@@ -131,8 +131,9 @@ class B200Florence2Model:
             while steps < plan.T:
                 plan.decode_step()
                 steps += 1
-                if steps % sync_every == 0 and steps < plan.T and int(plan.n_unfinished.item()) == 0:
+                if steps % sync_every == 0 and steps < plan.T and plan.unfinished() == 0:
                     break
+            plan.join()
             # exact stop length: first step after which no row was unfinished
             seq = plan.seq[:n, :steps + 1]
             if steps > 1:

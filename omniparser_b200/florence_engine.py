@@ -168,15 +168,14 @@ class FlorencePlan:
         self.L = self.n_img + self.n_prompt
         self.seq = torch.zeros((K, self.max_len + 1), dtype=torch.int32, device=dev)
         self.finished = torch.zeros((K,), dtype=torch.int32, device=dev)
-        self.step = torch.zeros((1,), dtype=torch.int32, device=dev)
-        self.n_unfinished = torch.zeros((1,), dtype=torch.int32, device=dev)
         self.logits = torch.empty((K, w.vocab), dtype=torch.float32, device=dev)
         self.enc_ops, self.dec_ops = [], []
         self.flops_enc = 0   # logical (useful) FLOPs; the fp16x3 mode executes 3x this on the tensor cores
         self.flops_dec = 0
         self._build_vision_encoder()
         self._build_decoder()
-        self.g_enc = self.g_dec = None
+        self.g_enc = None
+        self._forked = False
 
     # ------------------------------------------------------------------ helpers
     def _e(self, *shape, dt=torch.float32):
@@ -295,75 +294,99 @@ class FlorencePlan:
 
     # ------------------------------------------------------------------ one greedy decode step
     def _build_decoder(self):
-        w, K, D, ops_, x3 = self.w, self.K, self.D, self.dec_ops, self.x3
+        """The decode step is ~70 small, latency-bound launches.  The crop rows are therefore split into `parts`
+        independent chains (own KV cache, step counter, CUDA graph, stream) that replay concurrently, so one chain's
+        launch gaps and sub-wave GEMMs are filled by the other's."""
+        K = self.K
+        P = int(os.environ.get("B2P_DECODE_PARTS", "2"))
+        if K < 64 * P:
+            P = 1
+        per = (K // P + 15) // 16 * 16 if P > 1 else K
+        self.parts = []
+        r0 = 0
+        for i in range(P):
+            r1 = K if i == P - 1 else min(K, r0 + per)
+            self.parts.append(self._build_dec_part(i, r0, r1))
+            r0 = r1
+        self.dec_ops = [f for pt in self.parts for f in pt["ops"]]   # (counting / introspection only)
+
+    def _build_dec_part(self, idx, r0, r1):
+        w, D, x3 = self.w, self.D, self.x3
+        R = r1 - r0
         g = w.gen
         tmax = self.max_len
-        e0 = self._e(K, D)
-        ops_.append(lambda: ops.decoder_embed(w.E32, self.seq, self.seq.stride(0), self.step, w.dec_pos, K, D, e0))
-        x = self._e(K, D); h = self._act(K, D)
-        self._ln(ops_, e0, w.dec_ln_emb, K, D, h, x)
-        self.kcache, self.vcache = [], []
+        ops_ = []
+        seq, finished, logits = self.seq[r0:r1], self.finished[r0:r1], self.logits[r0:r1]
+        step = torch.zeros((1,), dtype=torch.int32, device=self.dev)
+        n_unf = torch.zeros((1,), dtype=torch.int32, device=self.dev)
+        e0 = self._e(R, D)
+        ops_.append(lambda: ops.decoder_embed(w.E32, seq, seq.stride(0), step, w.dec_pos, R, D, e0))
+        x = self._e(R, D); h = self._act(R, D)
+        self._ln(ops_, e0, w.dec_ln_emb, R, D, h, x)
         for li, lay in enumerate(w.dec_layers):
-            qkv = self._e(K, 3 * D)
+            qkv = self._e(R, 3 * D)
             self._gemm(ops_, h, lay["qkv"], qkv, enc=False)
-            kc = torch.zeros((K, tmax, D), dtype=torch.float32, device=self.dev)
-            vc = torch.zeros((K, tmax, D), dtype=torch.float32, device=self.dev)
-            self.kcache.append(kc); self.vcache.append(vc)
-            a = self._act(K, D)
+            kc = torch.zeros((R, tmax, D), dtype=torch.float32, device=self.dev)
+            vc = torch.zeros((R, tmax, D), dtype=torch.float32, device=self.dev)
+            a = self._act(R, D)
             ops_.append(lambda qkv=qkv, kc=kc, vc=vc, a=a: ops.mha_cached(qkv, 3 * D, qkv[:, D:], qkv[:, 2 * D:], 3 * D, kc, vc, tmax,
-                                                                       self.step, K, self.HEADS, a, a.stride(0), split=x3))
-            y = self._e(K, D)
+                                                                       step, R, self.HEADS, a, a.stride(0), split=x3))
+            y = self._e(R, D)
             self._gemm(ops_, a, lay["o"], y, res=x, enc=False)
-            x = self._e(K, D); h = self._act(K, D)
-            self._ln(ops_, y, lay["ln1"], K, D, h, x)
-            q = self._e(K, D)
+            x = self._e(R, D); h = self._act(R, D)
+            self._ln(ops_, y, lay["ln1"], R, D, h, x)
+            q = self._e(R, D)
             self._gemm(ops_, h, lay["cq"], q, enc=False)
-            kv = self.cross_kv[li]
-            a2 = self._act(K, D)
-            ops_.append(lambda q=q, kv=kv, a2=a2: ops.mha(q, D, kv, kv[:, D:], 2 * D, K, 1, self.L, self.HEADS, a2, a2.stride(0), split=x3))
-            y = self._e(K, D)
+            kv = self.cross_kv[li][r0 * self.L:r1 * self.L]
+            a2 = self._act(R, D)
+            ops_.append(lambda q=q, kv=kv, a2=a2: ops.mha(q, D, kv, kv[:, D:], 2 * D, R, 1, self.L, self.HEADS, a2, a2.stride(0), split=x3))
+            y = self._e(R, D)
             self._gemm(ops_, a2, lay["co"], y, res=x, enc=False)
-            x = self._e(K, D); h = self._act(K, D)
-            self._ln(ops_, y, lay["ln2"], K, D, h, x)
-            f = self._act(K, 4 * D)
+            x = self._e(R, D); h = self._act(R, D)
+            self._ln(ops_, y, lay["ln2"], R, D, h, x)
+            f = self._act(R, 4 * D)
             self._gemm(ops_, h, lay["fc1"], f, act=ACT_GELU, enc=False, split=x3)
-            y = self._e(K, D)
+            y = self._e(R, D)
             self._gemm(ops_, f, lay["fc2"], y, res=x, enc=False)
-            x = self._e(K, D); h = self._act(K, D)
-            self._ln(ops_, y, lay["ln3"], K, D, h, x)
-        self.dec_hidden16 = h
+            x = self._e(R, D); h = self._act(R, D)
+            self._ln(ops_, y, lay["ln3"], R, D, h, x)
         lm = type("W", (), {})()
         lm.w, lm.b, lm.N, lm.K, lm.Klog = w.E16, None, w.vocab, w.E16.shape[1], D
-        self._gemm(ops_, h, lm, self.logits, enc=False)
+        self._gemm(ops_, h, lm, logits, enc=False)
         fb = g.get("forced_bos_token_id")
         fe = g.get("forced_eos_token_id")
-        self.pick = lambda dump=None: ops.greedy_pick(self.logits, self.logits.stride(0), w.vocab, K, self.seq, self.seq.stride(0),
-                                                      self.finished, self.step, g.get("no_repeat_ngram_size", 0) or 0,
-                                                      -1 if fb is None else fb, -1 if fe is None else fe,
-                                                      g["eos_token_id"], g["pad_token_id"], self.max_len, dump, self.n_unfinished)
+        pick = lambda dump=None: ops.greedy_pick(logits, logits.stride(0), w.vocab, R, seq, seq.stride(0), finished, step,
+                                                 g.get("no_repeat_ngram_size", 0) or 0, -1 if fb is None else fb,
+                                                 -1 if fe is None else fe, g["eos_token_id"], g["pad_token_id"], self.max_len,
+                                                 dump, n_unf)
+        return dict(idx=idx, r0=r0, r1=r1, ops=ops_, pick=pick, step=step, n_unf=n_unf, graph=None,
+                    stream=torch.cuda.Stream(device=self.dev), full=ops_ + [lambda: pick(None), lambda: ops.step_advance(step)])
 
     # ------------------------------------------------------------------ running
-    def _run(self, lst, which):
+    def _run(self, lst, holder, key, tag):
         if not self.use_graph:
             for f in lst:
                 f()
             return
-        g = getattr(self, which)
+        g = holder[key] if isinstance(holder, dict) else getattr(holder, key)
         if g is None:
             for f in lst:
                 f()
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=ops.capture_stream('florence', self.dev), capture_error_mode="thread_local"):
+            with torch.cuda.graph(g, stream=ops.capture_stream(tag, self.dev), capture_error_mode="thread_local"):
                 for f in lst:
                     f()
-            setattr(self, which, g)
+            if isinstance(holder, dict):
+                holder[key] = g
+            else:
+                setattr(holder, key, g)
             return
         g.replay()
         ops.GRAPH_LAUNCHES[0] += len(lst)
 
     def encode(self):
-        self._run(self.enc_ops, "g_enc")
+        self._run(self.enc_ops, self, "g_enc", "florence")
 
     def reset_decode(self, n_active: int):
         self.seq.zero_()
@@ -371,23 +394,47 @@ class FlorencePlan:
         self.finished.zero_()
         if n_active < self.K:
             self.finished[n_active:] = 1     # padding rows never gate the stop test
-        self.step.zero_()
-        self.n_unfinished.fill_(n_active)
+        for pt in self.parts:
+            pt["step"].zero_()
+            pt["n_unf"].fill_(max(0, min(n_active, pt["r1"]) - pt["r0"]))
+        self._forked = False
+
+    def unfinished(self) -> int:
+        tot = 0
+        for pt in self.parts:
+            if len(self.parts) > 1:
+                pt["stream"].synchronize()
+            tot += int(pt["n_unf"].item())
+        return tot
 
     def decode_step(self, dump=None, force_tokens=None):
         """one token for every row; ``force_tokens`` [K] (teacher forcing) overwrites the picked ids."""
         if dump is None and force_tokens is None:
-            self._run(self.dec_ops_full(), "g_dec")
+            cur = torch.cuda.current_stream()
+            if len(self.parts) == 1:
+                self._run(self.parts[0]["full"], self.parts[0], "graph", "florence_dec0")
+                return
+            if not self._forked:
+                for pt in self.parts:
+                    pt["stream"].wait_stream(cur)     # encoder outputs / reset are ready
+                self._forked = True
+            for pt in self.parts:
+                with torch.cuda.stream(pt["stream"]):
+                    self._run(pt["full"], pt, "graph", f"florence_dec{pt['idx']}")
             return
-        for f in self.dec_ops:
-            f()
-        self.pick(dump)
-        if force_tokens is not None:
-            t = int(self.step.item())
-            self.seq[:, t + 1] = force_tokens
-        ops.step_advance(self.step)
+        for pt in self.parts:   # eager path used by the parity tests
+            for f in pt["ops"]:
+                f()
+            pt["pick"](dump[pt["r0"]:pt["r1"]] if dump is not None else None)
+            if force_tokens is not None:
+                t = int(pt["step"].item())
+                self.seq[pt["r0"]:pt["r1"], t + 1] = force_tokens[pt["r0"]:pt["r1"]]
+            ops.step_advance(pt["step"])
 
-    def dec_ops_full(self):
-        if not hasattr(self, "_dec_full"):
-            self._dec_full = self.dec_ops + [lambda: self.pick(None), lambda: ops.step_advance(self.step)]
-        return self._dec_full
+    def join(self):
+        """make the current stream wait for the decode chains (call before reading seq / starting the next encode)."""
+        if len(self.parts) > 1 and getattr(self, "_forked", False):
+            cur = torch.cuda.current_stream()
+            for pt in self.parts:
+                cur.wait_stream(pt["stream"])
+            self._forked = False

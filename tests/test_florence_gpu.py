@@ -86,8 +86,9 @@ def test_free_running_ids_identical(setup, use_graph):
         while steps < T_NEW:
             plan.decode_step()
             steps += 1
-            if int(plan.n_unfinished.item()) == 0:
+            if plan.unfinished() == 0:
                 break
+        plan.join()
         torch.cuda.synchronize()
         got = plan.seq[:K, :steps + 1].cpu().long()
         print(f"graph={use_graph} rep={rep} steps={steps}\n{got[:2]}")
