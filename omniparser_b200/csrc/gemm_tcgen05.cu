@@ -32,6 +32,7 @@ struct GemmArgs {
   int mode, M, N, num_kb, bk, bn;
   int cin_blocks, tw, th, tiles_x, tiles_y, Ho, Wo, batch;
   int m_tiles, n_tiles, stages, ldpar;
+  int nb;                // images per tile (small maps: a TMA box spans nb consecutive images)
   int tw_valid;          // valid output columns per tile row (== tw except in halo mode, where tw is the halo pitch)
   int stagesA, cin;      // halo mode: A ring depth, Cin
   uint32_t a_slot;       // halo mode: bytes per A slot
@@ -79,7 +80,18 @@ __device__ __forceinline__ float fast_rcp(float x) {
 }
 __device__ __forceinline__ float act_fn(float x, int act) {
   if (act == 1) return x * fast_rcp(1.0f + fast_ex2(x * -1.4426950408889634f));   // SiLU: 2 MUFU + 3 FP32, ~2 ulp
-  if (act == 2) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));        // exact GELU (Florence-2 parity)
+  if (act == 2) {
+    // exact (erf) GELU, Florence-2 parity: erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7) on MUFU rcp/ex2 instead
+    // of the ~25-instruction libdevice erff: the GELU epilogues were instruction-bound
+    const float z = fabsf(x) * 0.70710678118654752f;
+    const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = 1.0f - p * t * fast_ex2(z * z * -1.4426950408889634f);   // erf(|x|/sqrt2)
+    return 0.5f * x + 0.5f * fabsf(x) * e;                                      // 0.5 x (1 + sign(x) erf)
+  }
   return x;
 }
 
@@ -255,6 +267,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int r = mt - img * per_img;
           y0 = (r / g.tiles_x) * g.th;
           x0 = (r % g.tiles_x) * g.tw_valid;
+          img *= g.nb;   // nb > 1 only when one tile covers whole images (per_img == 1)
         }
         const int kb0 = ks * g.kb_per, kb1 = min(g.num_kb, kb0 + g.kb_per);
         if (g.mode == 3) {
@@ -388,12 +401,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         valid = pix < g.M;
       } else {
         const int per_img = g.tiles_x * g.tiles_y;
-        const int img = mt / per_img;
-        const int rr = mt - img * per_img;
-        const int ty = r / g.tw, tx = r - ty * g.tw;
+        const int img0 = mt / per_img;
+        const int rr = mt - img0 * per_img;
+        const int rows_img = g.tw * g.th;                  // rows of one image inside the tile
+        const int sub = (g.nb > 1) ? r / rows_img : 0;
+        const int rloc = r - sub * rows_img;
+        const int img = img0 * g.nb + sub;
+        const int ty = rloc / g.tw, tx = rloc - ty * g.tw;
         const int oy = (rr / g.tiles_x) * g.th + ty;
         const int ox = (rr % g.tiles_x) * g.tw_valid + tx;
-        valid = (ty < g.th) && (tx < g.tw_valid) && (oy < g.Ho) && (ox < g.Wo);
+        valid = (sub < g.nb) && (img < g.batch) && (ty < g.th) && (tx < g.tw_valid) && (oy < g.Ho) && (ox < g.Wo);
         pix = ((long long)img * g.Ho + oy) * g.Wo + ox;
       }
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
@@ -456,12 +473,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             valid2 = pix2 < g.M;
           } else {
             const int per_img = g.tiles_x * g.tiles_y;
-            const int img = mt / per_img;
-            const int rr = mt - img * per_img;
-            const int ty = rr_ / g.tw, tx = rr_ - ty * g.tw;
+            const int img0 = mt / per_img;
+            const int rr = mt - img0 * per_img;
+            const int rows_img = g.tw * g.th;
+            const int sub = (g.nb > 1) ? rr_ / rows_img : 0;
+            const int rloc = rr_ - sub * rows_img;
+            const int img = img0 * g.nb + sub;
+            const int ty = rloc / g.tw, tx = rloc - ty * g.tw;
             const int oy = (rr / g.tiles_x) * g.th + ty;
             const int ox = (rr % g.tiles_x) * g.tw_valid + tx;
-            valid2 = (ty < g.th) && (tx < g.tw_valid) && (oy < g.Ho) && (ox < g.Wo);
+            valid2 = (sub < g.nb) && (img < g.batch) && (ty < g.th) && (tx < g.tw_valid) && (oy < g.Ho) && (ox < g.Wo);
             pix2 = ((long long)img * g.Ho + oy) * g.Wo + ox;
           }
           float x[16];
@@ -683,8 +704,17 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
       g.tw = btw; g.tw_valid = btw; g.th = bth;
       g.a_bytes = uint32_t(btw) * bth * bk * 2;
     }
+    g.nb = 1;
     g.tiles_x = (g.Wo + btw - 1) / btw; g.tiles_y = (g.Ho + bth - 1) / bth;
-    g.m_tiles = g.tiles_x * g.tiles_y * d.batch;
+    if (!halo && g.tiles_x == 1 && g.tiles_y == 1 && btw == g.Wo && bth == g.Ho && btw * bth * 2 <= 128 && d.batch > 1) {
+      // tiny maps (DaViT stages at 64x64 crops: 8x8, 4x4, 2x2 outputs): one TMA box spans nb whole images so the 128
+      // MMA rows are full instead of 64/16/4 valid ones
+      int nb = 128 / (btw * bth);
+      if (nb > d.batch) nb = d.batch;
+      g.nb = nb;
+      g.a_bytes *= uint32_t(nb);
+    }
+    g.m_tiles = (g.nb > 1) ? (d.batch + g.nb - 1) / g.nb : g.tiles_x * g.tiles_y * d.batch;
     const cuuint64_t ld = cuuint64_t(d.lda);
     if (halo) {
       cuuint64_t dims[4] = {cuuint64_t(d.Cin), cuuint64_t(d.W), cuuint64_t(d.H), cuuint64_t(d.batch)};
@@ -694,14 +724,14 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
     } else if (d.mode == 1) {
       cuuint64_t dims[4] = {cuuint64_t(d.Cin), cuuint64_t(d.W), cuuint64_t(d.H), cuuint64_t(d.batch)};
       cuuint64_t str[3] = {ld * 2, ld * 2 * d.W, ld * 2 * d.W * d.H};
-      cuuint32_t box[4] = {cuuint32_t(bk), cuuint32_t(btw), cuuint32_t(bth), 1};
+      cuuint32_t box[4] = {cuuint32_t(bk), cuuint32_t(btw), cuuint32_t(bth), cuuint32_t(g.nb)};
       if (int e = encode(&tmA, d.bf16, 4, d.A, dims, str, box, bk)) return e;
     } else {
       // (x parity, channel) merged in dim0: element (n, 2*yo+py, 2*xo+px, c) at c + px*ld  (+ xo*2ld + py*W*ld + yo*2W*ld)
       g.ldpar = int(d.lda);   // producer adds px * ldA to the channel coordinate
       cuuint64_t dims[5] = {ld + cuuint64_t(d.Cin), cuuint64_t(d.W / 2), 2, cuuint64_t(d.H / 2), cuuint64_t(d.batch)};
       cuuint64_t str[4] = {ld * 4, ld * 2 * d.W, ld * 4 * d.W, ld * 2 * d.W * d.H};
-      cuuint32_t box[5] = {cuuint32_t(bk), cuuint32_t(btw), 1, cuuint32_t(bth), 1};
+      cuuint32_t box[5] = {cuuint32_t(bk), cuuint32_t(btw), 1, cuuint32_t(bth), cuuint32_t(g.nb)};
       if (int e = encode(&tmA, d.bf16, 5, d.A, dims, str, box, bk)) return e;
     }
   }

@@ -294,11 +294,11 @@ class FlorencePlan:
 
     # ------------------------------------------------------------------ one greedy decode step
     def _build_decoder(self):
-        """The decode step is ~70 small, latency-bound launches.  The crop rows are therefore split into `parts`
-        independent chains (own KV cache, step counter, CUDA graph, stream) that replay concurrently, so one chain's
-        launch gaps and sub-wave GEMMs are filled by the other's."""
+        """The decode step is ~70 small, latency-bound launches.  The crop rows CAN be split into `parts` independent
+        chains (own KV cache, step counter, CUDA graph, stream) replayed concurrently; on B200 that measured slower
+        (every chain re-streams the 0.5 GB of decoder weights), so the default is one chain."""
         K = self.K
-        P = int(os.environ.get("B2P_DECODE_PARTS", "2"))
+        P = int(os.environ.get("B2P_DECODE_PARTS", "1"))   # measured: 2 chains -8 %, 3 chains -16 % (weights stream twice)
         if K < 64 * P:
             P = 1
         per = (K // P + 15) // 16 * 16 if P > 1 else K

@@ -69,7 +69,8 @@ def test_gemm_strided_views():
                                                     (1, 80, 80, 32, 32, 1), (1, 40, 40, 128, 64, 1),
                                                     (3, 34, 60, 64, 64, 1), (1, 160, 160, 64, 64, 1),
                                                     (1, 40, 40, 256, 64, 2), (2, 80, 80, 128, 128, 2),
-                                                    (1, 320, 320, 64, 128, 2), (1, 22, 38, 32, 48, 2)])
+                                                    (1, 320, 320, 64, 128, 2), (1, 22, 38, 32, 48, 2),
+                                                    (37, 16, 16, 128, 64, 2), (10, 8, 8, 256, 96, 2), (5, 4, 4, 64, 48, 2)])
 def test_conv3x3(B, H, W, Cin, Cout, stride):
     g = torch.Generator(device="cpu").manual_seed(B + H + Cin + Cout + stride)
     ld = Cin + 64
