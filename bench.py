@@ -274,6 +274,11 @@ def run_b200(args):
     fwd_ms = e0.elapsed_time(e1) / reps
     peak_tf, hbm, how = _peaks()
     achieved = plan.flops / (fwd_ms * 1e-3) / 1e12
+    traffic = None
+    tp = ROOT / "profiles" / "r1_yolo_b8_traffic.json"
+    if tp.is_file() and B == 8:   # measured once under ncu for this exact forward (batch 8); not re-measured per run
+        tj = json.loads(tp.read_text())
+        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
 
     # p50 latency of one screenshot through the public batched entry point (host buffers)
     lat = []
@@ -295,7 +300,8 @@ def run_b200(args):
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clocks,
                 "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (YOLOv9-E forward, batch %d: 241 GEMM/conv launches + 11 pooling launches)" % B,
-                             "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                             "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
+                             "traffic_note": "DRAM bytes per forward from the committed ncu launch list (caches flushed per kernel), not from this run",
                              "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})", "forward_ms": fwd_ms,
                              "algorithmic_gflop_per_forward": plan.flops / 1e9},
                 "p50_latency_ms_batch1": lat[len(lat) // 2],
