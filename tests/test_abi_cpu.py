@@ -48,3 +48,19 @@ def test_lanczos_coeff_table_equals_oracle():
         assert ks.value == rk.shape[1]
         assert np.array_equal(bounds, rb)
         assert np.array_equal(kk[: n_out * ks.value].reshape(n_out, ks.value), rk)
+
+
+def test_product_never_imports_oracle_or_standin():
+    """The product path must not route through the oracle (or the seeded checkpoint definitions)."""
+    import ast
+    pkg = ROOT / "omniparser_b200"
+    for f in pkg.glob("*.py"):
+        tree = ast.parse(f.read_text())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom) and node.module:
+                names = [node.module]
+            for n in names:
+                assert not (n == "oracle" or n.startswith("oracle.") or n == "standin" or n.startswith("standin.")), (f.name, n)

@@ -102,3 +102,20 @@ def test_pipelined_parser_equals_sequential():
         for gb, rb in zip(got, ref):
             for (ge_, gi), (re_, ri) in zip(gb, rb):
                 assert ge_ == re_ and torch.equal(gi, ri)
+
+
+def test_edge_cases_no_boxes_and_no_ocr():
+    """Empty inputs the reference either mishandles or never produces: no detection above the threshold (only OCR
+    elements come back, no caption launch) and no OCR boxes at all (the reference raises TypeError at
+    ref:util/utils.py:444; the drop-in treats it as an empty OCR list)."""
+    det, cmp_ = ge.standin_models(DEV)
+    img = synth.screenshot(2)
+    texts, boxes = synth.ocr_boxes(2)
+    (elems, ids), = parse_screenshots([img], det, cmp_, [(texts, boxes)], BOX_TRESHOLD=0.9999999, iou_threshold=0.7, max_new_tokens=8)
+    assert ids.shape[0] == 0 and all(e["type"] == "text" for e in elems) and len(elems) == len(texts)
+    (elems, ids), = parse_screenshots([img], det, cmp_, [([], None)], BOX_TRESHOLD=0.05, iou_threshold=0.7, max_new_tokens=8)
+    assert len(elems) > 10 and all(e["source"] == "box_yolo_content_yolo" for e in elems) and ids.shape[0] == len(elems)
+    # a batch whose images yield different crop counts, one of them zero
+    out = parse_screenshots([img, np.full_like(img, 200)], det, cmp_, [([], None), ([], None)], BOX_TRESHOLD=0.3, iou_threshold=0.7,
+                            max_new_tokens=8)
+    assert len(out) == 2 and out[0][1].shape[0] == len(out[0][0]) and out[1][1].shape[0] == len(out[1][0])
