@@ -60,6 +60,9 @@ int b2p_cbfuse(int nsrc, const void* const* srcs_host, const long long* lds_host
 int b2p_lanczos_coeffs_host(int in_size, int out_size, int* ksize_host, int* bounds_host, int* kk_host, int kk_capacity);
 int b2p_letterbox(const unsigned char* src, int B, int H, int W, int Wr, int Hr, int Tw, int Th, int pad_l, int pad_t,
                   unsigned char* tmp, unsigned char* canvas, b2p_stream_t stream);
+/* Pillow-exact u8 resize, filter 0 LANCZOS / 1 BICUBIC (CLIP processor resample=3, ref:util/utils.py:123 CPU branch) */
+int b2p_resize_u8(const unsigned char* src, int B, int H, int W, int Wr, int Hr, int filter, unsigned char* tmp,
+                  unsigned char* out, b2p_stream_t stream);
 int b2p_im2col_u8(const unsigned char* img, int B, int H, int W, int k, int s, int p, int Kpad, const float* lut,
                   void* out, int split, b2p_stream_t stream);
 int b2p_yolo_decode(const float* const* cls_host, const float* const* box_host, const int* Hs_host, const int* Ws_host,

@@ -29,6 +29,7 @@ CAPTION_PROMPT_IDS = [0, 2264, 473, 5, 2274, 6190, 116, 2]
 DEFAULT_GEN = dict(forced_bos_token_id=0, forced_eos_token_id=2, no_repeat_ngram_size=3, eos_token_id=2, pad_token_id=1,
                    bos_token_id=0, decoder_start_token_id=2)
 BUCKET = 32
+BUCKET_768 = 16      # 768x768 mode: 36864 stage-0 tokens per crop -> small chunks (activations ~1.5 GB per crop)
 
 
 class _Batch(dict):
@@ -50,17 +51,24 @@ class B200Florence2Processor:
         self.tokenizer = tokenizer
         self.prompt_ids = list(prompt_ids)
 
-    def __call__(self, images=None, text=None, return_tensors="pt", do_resize=False, **kw):
-        if do_resize:
-            raise NotImplementedError("the B200 caption path implements the reference's CUDA branch (do_resize=False, "
-                                      "64x64 crops, ref:util/utils.py:121); the 768x768 CPU branch is not planned")
+    def __call__(self, images=None, text=None, return_tensors="pt", do_resize=True, **kw):
+        # Default do_resize=True as in HF's CLIPImageProcessor (what the reference gets when it omits the argument).
+        # do_resize=False: the reference's CUDA branch (ref:util/utils.py:121), crops go in as 64x64.
+        # do_resize=True (HF default): its CPU branch (:123): CLIP image processor bicubic resize to 768x768 on the u8
+        # image (resample=3), done here with Pillow exactly as the HF processor does; the model sees 768x768 u8.
         arr = []
         for im in images:
-            a = np.asarray(im.convert("RGB") if hasattr(im, "convert") else im, dtype=np.uint8)
-            if a.shape != (64, 64, 3):
-                raise ValueError(f"expected 64x64 RGB crops, got {a.shape}")
+            pil = im if hasattr(im, "convert") else __import__("PIL.Image", fromlist=["Image"]).fromarray(np.asarray(im, dtype=np.uint8))
+            pil = pil.convert("RGB")
+            if do_resize:
+                from PIL import Image as _I
+                pil = pil.resize((768, 768), _I.Resampling.BICUBIC)
+            a = np.asarray(pil, dtype=np.uint8)
+            if a.shape not in ((64, 64, 3), (768, 768, 3)):
+                raise ValueError(f"expected 64x64 RGB crops (or do_resize=True), got {a.shape}")
             arr.append(a)
-        px = torch.from_numpy(np.stack(arr)) if arr else torch.zeros((0, 64, 64, 3), dtype=torch.uint8)
+        side = arr[0].shape[0] if arr else 64
+        px = torch.from_numpy(np.stack(arr)) if arr else torch.zeros((0, side, side, 3), dtype=torch.uint8)
         ids = torch.tensor([self.prompt_ids] * len(arr), dtype=torch.long).reshape(len(arr), len(self.prompt_ids))
         return _Batch(input_ids=ids, pixel_values=px)
 
@@ -100,32 +108,35 @@ class B200Florence2Model:
     def eval(self):
         return self
 
-    def plan_for(self, n: int, max_new_tokens: int, prompt_ids: Sequence[int]) -> FlorencePlan:
-        K = max(BUCKET, ((n + BUCKET - 1) // BUCKET) * BUCKET)
-        key = (K, max_new_tokens, tuple(prompt_ids))
+    def plan_for(self, n: int, max_new_tokens: int, prompt_ids: Sequence[int], size: int = 64) -> FlorencePlan:
+        if size == 64:
+            K = max(BUCKET, ((n + BUCKET - 1) // BUCKET) * BUCKET)
+        else:
+            K = BUCKET_768
+        key = (K, max_new_tokens, tuple(prompt_ids), size)
         if key not in self._plans:
             with torch.cuda.device(self.device):
-                self._plans[key] = FlorencePlan(self.weights, K, max_new_tokens, list(prompt_ids), self.use_graph)
+                self._plans[key] = FlorencePlan(self.weights, K, max_new_tokens, list(prompt_ids), self.use_graph, size)
         return self._plans[key]
 
     def _to_u8(self, pixel_values: torch.Tensor) -> torch.Tensor:
         if pixel_values.dtype == torch.uint8:
             if pixel_values.dim() == 4 and pixel_values.shape[-1] == 3:
                 return pixel_values
-            raise ValueError("uint8 pixel_values must be [K,64,64,3]")
+            raise ValueError("uint8 pixel_values must be [K,S,S,3]")
         x = pixel_values.float().cpu()   # [K,3,64,64] normalised
         mean = torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1)
         std = torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)
         return ((x * std + mean) * 255.0).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
 
     @torch.inference_mode()
-    def generate_from_device_crops(self, plan: FlorencePlan, n: int, sync_every: int = 4) -> torch.Tensor:
-        """Crops already in ``plan.crops[:n]`` (device).  Returns LongTensor [n, T] on the device, HF layout
-        ``[decoder_start, tokens..., eos, pad...]`` truncated where every row has finished."""
+    def generate_from_device_crops(self, plan: FlorencePlan, n: int, sync_every: int = 4, from_resized: bool = False) -> torch.Tensor:
+        """Crops already in ``plan.crops[:n]`` (device; ``plan.crops_in`` if from_resized).  Returns LongTensor [n, T] on
+        the device, HF layout ``[decoder_start, tokens..., eos, pad...]`` truncated where every row has finished."""
         with torch.cuda.device(self.device):
             if n < plan.K:
-                plan.crops[n:].zero_()
-            plan.encode()
+                (plan.crops_in if from_resized else plan.crops)[n:].zero_()
+            plan.encode(from_resized)
             plan.reset_decode(n)
             steps = 0
             while steps < plan.T:
@@ -164,9 +175,30 @@ class B200Florence2Model:
         prompt = input_ids[0].tolist() if input_ids is not None else CAPTION_PROMPT_IDS
         if input_ids is not None and not bool((input_ids == input_ids[0:1]).all()):
             raise NotImplementedError("all rows must share one prompt (the reference passes [prompt]*len(batch))")
-        plan = self.plan_for(n, max_new_tokens, prompt)
-        plan.crops[:n].copy_(u8.to(self.device, non_blocking=True))
-        return self.generate_from_device_crops(plan, n)
+        side = int(u8.shape[1])
+        if side == 64:
+            plan = self.plan_for(n, max_new_tokens, prompt)
+            plan.crops[:n].copy_(u8.to(self.device, non_blocking=True))
+            return self.generate_from_device_crops(plan, n)
+        if side != 768:
+            raise ValueError("pixel_values must be 64x64 (do_resize=False) or 768x768 (processor default)")
+        return self.generate_chunked(u8, max_new_tokens, prompt, from_resized=True)
+
+    @torch.inference_mode()
+    def generate_chunked(self, crops_u8: torch.Tensor, max_new_tokens: int, prompt, from_resized: bool) -> torch.Tensor:
+        """768x768 mode: run the crops through the (small-K) plan chunk by chunk; HF pads the shorter chunks with pad."""
+        n = crops_u8.shape[0]
+        plan = self.plan_for(n, max_new_tokens, prompt, 768)
+        outs = []
+        for c0 in range(0, n, plan.K):
+            m = min(plan.K, n - c0)
+            dst = plan.crops_in if from_resized else plan.crops
+            dst[:m].copy_(crops_u8[c0:c0 + m].to(self.device, non_blocking=True))
+            outs.append(self.generate_from_device_crops(plan, m, from_resized=from_resized).clone())
+        width = max(o.shape[1] for o in outs)
+        pad = self.gen["pad_token_id"]
+        outs = [torch.nn.functional.pad(o, (0, width - o.shape[1]), value=pad) for o in outs]
+        return torch.cat(outs, 0)
 
 
 def load_florence_state(path: str | Path):

@@ -26,6 +26,15 @@ static double lanczos_filter(double x) {
   if (-3.0 <= x && x < 3.0) return sinc_filter(x) * sinc_filter(x / 3);
   return 0.0;
 }
+// Pillow bicubic_filter (a = -0.5, support 2): the CLIP image processor's resample=3 of the reference's CPU caption
+// branch (ref:util/utils.py:123 -> HF processor default do_resize=True, 768x768)
+static double bicubic_filter(double x) {
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+  if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+  return 0.0;
+}
 
 struct Coeffs {
   int ksize = 0, out = 0;
@@ -33,12 +42,13 @@ struct Coeffs {
   int* d_kk = nullptr;       // [out][ksize] 22-bit fixed point
 };
 
-void host_lanczos_coeffs(int inSize, int outSize, int* ksize_out, std::vector<int>& bounds, std::vector<int>& kk) {
+void host_lanczos_coeffs(int inSize, int outSize, int* ksize_out, std::vector<int>& bounds, std::vector<int>& kk, int filter = 0) {
+  const double fsupport = filter == 1 ? 2.0 : 3.0;
   const float in0 = 0.f, in1 = float(inSize);
   double filterscale, scale;
   filterscale = scale = double(in1 - in0) / outSize;
   if (filterscale < 1.0) filterscale = 1.0;
-  const double support = 3.0 * filterscale;
+  const double support = fsupport * filterscale;
   const int ksize = int(ceil(support)) * 2 + 1;
   bounds.assign(size_t(outSize) * 2, 0);
   kk.assign(size_t(outSize) * ksize, 0);
@@ -54,7 +64,8 @@ void host_lanczos_coeffs(int inSize, int outSize, int* ksize_out, std::vector<in
     xmax -= xmin;
     int x;
     for (x = 0; x < xmax; ++x) {
-      const double w = lanczos_filter((x + xmin - center + 0.5) * ss);
+      const double arg = (x + xmin - center + 0.5) * ss;
+      const double w = filter == 1 ? bicubic_filter(arg) : lanczos_filter(arg);
       k[x] = w;
       ww += w;
     }
@@ -72,16 +83,16 @@ void host_lanczos_coeffs(int inSize, int outSize, int* ksize_out, std::vector<in
 }
 
 static std::mutex g_coeff_mu;
-static std::map<std::pair<int, int>, Coeffs> g_coeffs;   // per (device is implicit: one process per GPU)
+static std::map<std::pair<std::pair<int, int>, int>, Coeffs> g_coeffs;   // (in, out, filter); one process per GPU
 
-static int get_coeffs(int inSize, int outSize, Coeffs* out) {
+static int get_coeffs(int inSize, int outSize, Coeffs* out, int filter = 0) {
   std::lock_guard<std::mutex> lk(g_coeff_mu);
-  auto key = std::make_pair(inSize, outSize);
+  auto key = std::make_pair(std::make_pair(inSize, outSize), filter);
   auto it = g_coeffs.find(key);
   if (it != g_coeffs.end()) { *out = it->second; return 0; }
   std::vector<int> bounds, kk;
   Coeffs c;
-  host_lanczos_coeffs(inSize, outSize, &c.ksize, bounds, kk);
+  host_lanczos_coeffs(inSize, outSize, &c.ksize, bounds, kk, filter);
   c.out = outSize;
   if (cudaMalloc(&c.d_bounds, bounds.size() * 4) != cudaSuccess || cudaMalloc(&c.d_kk, kk.size() * 4) != cudaSuccess)
     return set_error("letterbox: cudaMalloc for coefficient tables failed");
@@ -298,6 +309,29 @@ int b2p_letterbox(const unsigned char* src, int B, int H, int W, int Wr, int Hr,
     if (int e = get_coeffs(H, Hr, &cv)) return e;
   launch_pdl(lanczos_v_paste_kernel, dim3(grid_for((long long)B * Th * Tw, 256)), dim3(256), 0, st, hsrc, B, H, hW, Hr, cv.d_bounds, cv.d_kk, cv.ksize,
                                                                               Tw, Th, pad_l, pad_t, canvas);
+  B2P_CHECK_LAUNCH();
+  return 0;
+}
+
+// Pillow-exact resize of u8 HWC images (filter 0 = LANCZOS, 1 = BICUBIC), no padding: [B][H][W][3] -> [B][Hr][Wr][3].
+int b2p_resize_u8(const unsigned char* src, int B, int H, int W, int Wr, int Hr, int filter, unsigned char* tmp,
+                  unsigned char* out, cudaStream_t st) {
+  if (filter != 0 && filter != 1) return set_error("resize_u8: filter must be 0 (LANCZOS) or 1 (BICUBIC)");
+  const unsigned char* hsrc = src;
+  int hW = W;
+  if (Wr != W) {
+    Coeffs ch;
+    if (int e = get_coeffs(W, Wr, &ch, filter)) return e;
+    lanczos_h_kernel<<<grid_for((long long)B * H * Wr, 256), 256, 0, st>>>(src, B, H, W, Wr, ch.d_bounds, ch.d_kk, ch.ksize, tmp);
+    B2P_CHECK_LAUNCH();
+    hsrc = tmp;
+    hW = Wr;
+  }
+  Coeffs cv{};
+  if (Hr != H)
+    if (int e = get_coeffs(H, Hr, &cv, filter)) return e;
+  launch_pdl(lanczos_v_paste_kernel, dim3(grid_for((long long)B * Hr * Wr, 256)), dim3(256), 0, st, hsrc, B, H, hW, Hr, cv.d_bounds,
+             cv.d_kk, cv.ksize, Wr, Hr, 0, 0, out);
   B2P_CHECK_LAUNCH();
   return 0;
 }

@@ -153,7 +153,11 @@ class FlorencePlan:
     D = 768
     HEADS = 12
 
-    def __init__(self, w: FlorenceWeights, K: int, max_new_tokens: int, prompt_ids: List[int], use_graph=True):
+    def __init__(self, w: FlorenceWeights, K: int, max_new_tokens: int, prompt_ids: List[int], use_graph=True, size: int = 64):
+        """size = 64: the reference's CUDA branch (crops fed un-resized, 5 image tokens, ref:util/utils.py:121);
+        size = 768: its CPU branch (CLIP processor bicubic resize of every crop to 768x768, 577 image tokens, :123)."""
+        assert size in (64, 768)
+        self.S = size
         self.w, self.K, self.dev = w, K, w.device
         self.x3 = w.x3
         self.KX = 3 if w.x3 else 1
@@ -164,7 +168,7 @@ class FlorencePlan:
         self.crops = torch.zeros((K, 64, 64, 3), dtype=torch.uint8, device=dev)
         self.prompt = torch.tensor(prompt_ids, dtype=torch.int32, device=dev)
         self.n_prompt = len(prompt_ids)
-        self.n_img = 5
+        self.n_img = (size // 32) ** 2 + 1
         self.L = self.n_img + self.n_prompt
         self.seq = torch.zeros((K, self.max_len + 1), dtype=torch.int32, device=dev)
         self.finished = torch.zeros((K,), dtype=torch.int32, device=dev)
@@ -175,6 +179,7 @@ class FlorencePlan:
         self._build_vision_encoder()
         self._build_decoder()
         self.g_enc = None
+        self.g_enc_nr = None
         self._forked = False
 
     # ------------------------------------------------------------------ helpers
@@ -202,11 +207,18 @@ class FlorencePlan:
 
     # ------------------------------------------------------------------ DaViT + projector + BART encoder
     def _build_vision_encoder(self):
-        w, K, ops_, x3 = self.w, self.K, self.enc_ops, self.x3
-        H = 16
+        w, K, ops_, x3, S = self.w, self.K, self.enc_ops, self.x3, self.S
+        if S == 64:
+            src = self.crops
+        else:   # Pillow-exact bicubic 64x64 -> SxS on the u8 crops (what the HF CLIP image processor does on the host)
+            self.crops_in = torch.zeros((K, S, S, 3), dtype=torch.uint8, device=self.dev)
+            tmp = torch.empty((K, 64, S, 3), dtype=torch.uint8, device=self.dev)
+            ops_.append(lambda: ops.resize_u8(self.crops, K, 64, 64, S, S, 1, tmp, self.crops_in))
+            src = self.crops_in
+        H = S // 4
         T = K * H * H
         A0 = self._act(T, 160)
-        ops_.append(lambda: ops.im2col_u8(self.crops, K, 64, 64, 7, 4, 3, 160, w.lut, A0, split=x3))
+        ops_.append(lambda: ops.im2col_u8(src, K, S, S, 7, 4, 3, 160, w.lut, A0, split=x3))
         y = self._e(T, 128)
         self._gemm(ops_, A0, w.conv_embed[0], y)
         x = self._e(T, 128)
@@ -385,8 +397,12 @@ class FlorencePlan:
         g.replay()
         ops.GRAPH_LAUNCHES[0] += len(lst)
 
-    def encode(self):
-        self._run(self.enc_ops, self, "g_enc", "florence")
+    def encode(self, from_resized: bool = False):
+        """from_resized: the SxS crops are already in ``crops_in`` (host-side processor did the bicubic resize)."""
+        if from_resized and self.S != 64:
+            self._run(self.enc_ops[1:], self, "g_enc_nr", "florence")
+        else:
+            self._run(self.enc_ops, self, "g_enc", "florence")
 
     def reset_decode(self, n_active: int):
         self.seq.zero_()

@@ -154,6 +154,11 @@ def letterbox(src_u8, B, H, W, Wr, Hr, Tw, Th, pad_l, pad_t, tmp, canvas):
                                         _stream()))
 
 
+def resize_u8(src_u8, B, H, W, Wr, Hr, filt, tmp, out):
+    """Pillow-exact resize; filt 0 = LANCZOS, 1 = BICUBIC."""
+    _lib.check(_lib.lib().b2p_resize_u8(_p(src_u8), B, H, W, Wr, Hr, filt, _p(tmp), _p(out), _stream()))
+
+
 def im2col_u8(img, B, H, W, k, s, p, Kpad, lut, out, split=False):
     _lib.check(_lib.lib().b2p_im2col_u8(_p(img), B, H, W, k, s, p, Kpad, _p(lut), _p(out), int(split), _stream()))
 

@@ -64,8 +64,10 @@ class ParseTimings(dict):
 def parse_screenshots(images: Sequence[np.ndarray], model: B200YOLOv9Detector, caption_model_processor: dict,
                       ocr: Sequence[tuple], BOX_TRESHOLD=0.01, iou_threshold=0.9, imgsz=640, max_new_tokens=20,
                       prompt_ids: Sequence[int] = CAPTION_PROMPT_IDS, timings: Optional[ParseTimings] = None,
-                      _skip_h2d: bool = False, _det_override=None):
-    """Same-size u8 HWC screenshots + per-image ``(ocr_text, ocr_bbox_xyxy_pixels)`` -> per-image
+                      _skip_h2d: bool = False, _det_override=None, caption_size: int = 64):
+    """``caption_size`` 64 = the reference's CUDA branch (crops captioned at 64x64, ref:util/utils.py:121); 768 = its
+    CPU branch (CLIP processor bicubic-resizes every crop to 768x768 first, :123), done on the device, in chunks.
+    Same-size u8 HWC screenshots + per-image ``(ocr_text, ocr_bbox_xyxy_pixels)`` -> per-image
     ``(filtered_boxes_elem, caption_token_ids)``; the compute of ``get_som_labeled_img`` without the overlay drawing.
     NMS IoU is fixed at 0.1 as in ref:util/utils.py:431; ``iou_threshold`` feeds the overlap filter (:446)."""
     B = len(images)
@@ -103,8 +105,12 @@ def parse_screenshots(images: Sequence[np.ndarray], model: B200YOLOv9Detector, c
         t2 = time.perf_counter()
         ids = None
         if n:
-            plan = cap_model.plan_for(n, max_new_tokens, prompt_ids)
             dev = model.device
+            if caption_size == 64:
+                plan = cap_model.plan_for(n, max_new_tokens, prompt_ids)
+                crops_dst = plan.crops
+            else:
+                crops_dst = torch.empty((n, 64, 64, 3), dtype=torch.uint8, device=dev)
             d_boxes = torch.tensor(crop_boxes, dtype=torch.float32).to(dev, non_blocking=True)
             d_bimg = torch.tensor(crop_img, dtype=torch.int32).to(dev, non_blocking=True)
             key = ("crop_meta", B, H, W)
@@ -114,8 +120,11 @@ def parse_screenshots(images: Sequence[np.ndarray], model: B200YOLOv9Detector, c
                             off=torch.tensor([i * H * W * 3 for i in range(B)], dtype=torch.int64, device=dev))
                 model._io[key] = meta
             status = torch.empty((n,), dtype=torch.int32, device=dev)
-            ops.crop_resize(io_["src"], meta["hw"], meta["off"], d_boxes, d_bimg, n, 64, plan.crops, status)
-            ids = cap_model.generate_from_device_crops(plan, n).cpu()  # D2H #2 (sync)
+            ops.crop_resize(io_["src"], meta["hw"], meta["off"], d_boxes, d_bimg, n, 64, crops_dst, status)
+            if caption_size == 64:
+                ids = cap_model.generate_from_device_crops(plan, n).cpu()  # D2H #2 (sync)
+            else:
+                ids = cap_model.generate_chunked(crops_dst, max_new_tokens, prompt_ids, from_resized=False).cpu()
         t3 = time.perf_counter()
     out = []
     k = 0

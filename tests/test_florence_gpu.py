@@ -93,3 +93,65 @@ def test_free_running_ids_identical(setup, use_graph):
         got = plan.seq[:K, :steps + 1].cpu().long()
         print(f"graph={use_graph} rep={rep} steps={steps}\n{got[:2]}")
         assert got.shape == seq.shape and torch.equal(got, seq)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# 768x768 mode: the reference's CPU branch (ref:util/utils.py:123 -- processor default do_resize=True, 577 image tokens)
+# --------------------------------------------------------------------------------------------------------------------
+K768 = 2
+
+
+@pytest.fixture(scope="module")
+def setup768(setup):
+    from PIL import Image
+    m, crops, *_rest, ws = setup
+    c64 = crops[:K768]
+    big = torch.from_numpy(np.stack([np.asarray(Image.fromarray(a.numpy()).resize((768, 768), Image.Resampling.BICUBIC)) for a in c64]))
+    pv = FS.pixel_values_from_u8(big)
+    ids = FS.input_ids_for(K768, 577)
+    with torch.no_grad():
+        seq = m.generate(input_ids=ids, pixel_values=pv, max_new_tokens=8, num_beams=1, do_sample=False)
+        out = m(input_ids=ids, pixel_values=pv, decoder_input_ids=seq[:, :-1])
+        img = m.get_image_features(pv).pooler_output
+    return m, c64, big, seq, out, img, ws
+
+
+def test_768_mode_encoder_logits_and_ids(setup768):
+    m, c64, big, seq, out, img, ws = setup768
+    w = ws["fp16x3"]
+    plan = FlorencePlan(w, K768, 8, FS.PROMPT_IDS, use_graph=False, size=768)
+    assert plan.n_img == 577 and plan.L == 585
+    plan.crops.copy_(c64.to(DEV))
+    plan.encode()
+    torch.cuda.synchronize()
+    assert torch.equal(plan.crops_in.cpu(), big), "device bicubic resize != Pillow BICUBIC"
+    e_img = (plan.img_feat.view(K768, 577, 768).cpu() - img).abs().max().item()
+    e_enc = (plan.enc_out32.view(K768, 585, 768).cpu() - out.encoder_last_hidden_state).abs().max().item()
+    print(f"[768] image tokens max abs err {e_img:.5f}; encoder states max abs err {e_enc:.5f}")
+    assert e_img < 2e-3 and e_enc < 2e-3
+    plan.reset_decode(K768)
+    dump = torch.empty((K768, w.vocab), dtype=torch.float32, device=DEV)
+    worst = 0.0
+    for t in range(seq.shape[1] - 1):
+        plan.decode_step(dump=dump, force_tokens=seq[:, t + 1].to(DEV).int())
+        torch.cuda.synchronize()
+        worst = max(worst, (plan.logits.cpu() - out.logits[:, t]).abs().max().item())
+        assert torch.equal(dump.cpu().argmax(-1), seq[:, t + 1]), f"step {t}"
+    print(f"[768] teacher-forced logits max abs err {worst:.6f}")
+    assert worst < 1e-3
+
+
+def test_768_mode_model_api(setup768):
+    """processor(do_resize=True) -> 768x768 u8 -> generate(); and the device-resize chunked route; both == oracle ids."""
+    from omniparser_b200.caption import B200Florence2Model, B200Florence2Processor
+    from PIL import Image
+    m, c64, big, seq, out, img, ws = setup768
+    model = B200Florence2Model(m.state_dict(), FS.GEN, device=DEV, precision="fp16x3")
+    proc = B200Florence2Processor()
+    inputs = proc(images=[Image.fromarray(a.numpy()) for a in c64], text=["<CAPTION>"] * K768, return_tensors="pt")
+    assert tuple(inputs["pixel_values"].shape[1:3]) == (768, 768)
+    ids_a = model.generate(input_ids=inputs["input_ids"], pixel_values=inputs["pixel_values"], max_new_tokens=8, num_beams=1,
+                           do_sample=False).cpu()
+    ids_b = model.generate_chunked(c64.to(DEV), 8, FS.PROMPT_IDS, from_resized=False).cpu()
+    ref = seq[:, :ids_a.shape[1]]
+    assert torch.equal(ids_a, ref) and torch.equal(ids_b, ref)
