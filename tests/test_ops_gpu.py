@@ -187,6 +187,27 @@ def test_letterbox_bit_exact(size, imgsz):
         assert np.array_equal(ref, canvas[b].cpu().numpy())
 
 
+@pytest.mark.parametrize("filt", [0, 1])
+@pytest.mark.parametrize("src_hw,dst_wh", [((64, 64), (768, 768)), ((37, 53), (100, 80)), ((300, 200), (64, 48))])
+def test_resize_u8_bit_exact_vs_pillow(filt, src_hw, dst_wh):
+    """b2p_resize_u8 == PIL Image.resize (LANCZOS / BICUBIC): the CLIP image processor's resize in the 768 caption mode."""
+    from PIL import Image
+    rng = np.random.default_rng(11)
+    B = 2
+    H, W = src_hw
+    Wr, Hr = dst_wh
+    imgs = rng.integers(0, 256, size=(B, H, W, 3), dtype=np.uint8)
+    src = torch.from_numpy(imgs).to(DEV)
+    tmp = torch.empty(B, H, Wr, 3, dtype=torch.uint8, device=DEV)
+    out = torch.empty(B, Hr, Wr, 3, dtype=torch.uint8, device=DEV)
+    ops.resize_u8(src, B, H, W, Wr, Hr, filt, tmp, out)
+    torch.cuda.synchronize()
+    res = Image.Resampling.BICUBIC if filt else Image.Resampling.LANCZOS
+    for b in range(B):
+        ref = np.asarray(Image.fromarray(imgs[b]).resize((Wr, Hr), res))
+        assert np.array_equal(ref, out[b].cpu().numpy())
+
+
 def test_crop_resize_bit_exact():
     import cv2
     rng = np.random.default_rng(4)

@@ -56,6 +56,21 @@ def test_batch_equals_cpu_oracle_on_gpu_boxes():
         assert ids.shape[0] > 10
 
 
+def test_caption_768_mode_equals_cpu_oracle():
+    """The reference's CPU-branch caption semantics (768x768 crops, ref:util/utils.py:123) through the fused parse."""
+    det, cmp_ = ge.standin_models(DEV)
+    pipe = OraclePipeline(yolo=torch.nn.Identity())
+    img = synth.screenshot(21)
+    texts, boxes = synth.ocr_boxes(21)
+    det_boxes = [[100.0, 120.0, 164.0, 190.0], [800.0, 400.0, 840.0, 436.0], [1500.0, 900.0, 1620.0, 960.0]]
+    (elems, ids), = parse_screenshots([img], det, cmp_, [(texts, boxes)], BOX_TRESHOLD=0.05, iou_threshold=0.7, max_new_tokens=6,
+                                      _det_override=[det_boxes], caption_size=768)
+    ref_elems, ref_ids = pipe.parse(img, texts, boxes, BOX_TRESHOLD=0.05, iou_threshold=0.7, max_new_tokens=6,
+                                    det_boxes=torch.tensor(det_boxes), caption_768=True)
+    _same_elements(elems, ref_elems, ids, ref_ids)
+    assert 1 <= ids.shape[0] <= 3
+
+
 def test_get_som_labeled_img_api():
     import base64, io
     from PIL import Image
