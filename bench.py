@@ -65,34 +65,70 @@ def _dist():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons WHILE the timed region runs (B200_PROFILING.md recipe): NVML in-process every 20 ms
+    (same counters nvidia-smi prints), falling back to the nvidia-smi command line if NVML cannot be loaded."""
 
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()   # samples: (sm_mhz, max_mhz, reason names)
+        self.source, self.h, self.nv = "nvidia-smi", None, None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self.h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.nv, self.source = nv, "nvml"
+            self.sample()
+            self.samples.clear()
+        except Exception:
+            self.nv = self.h = None
+            self.source = "nvidia-smi"
+
+    def sample(self):
+        if self.nv is not None:
+            nv = self.nv
+            sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            try:
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            self.samples.append((int(sm), int(mx), [n for n, b in self.BITS if mask & b]))
+            return
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=10).stdout.strip()
+        if out:
+            f = [x.strip() for x in out.splitlines()[0].split(",")]
+            names = [n for n, _ in self.BITS]
+            self.samples.append((int(f[0]), int(f[1]), [names[i] for i in range(4) if f[2 + i].lower().startswith("active")]))
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
+                self.sample()
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.02 if self.nv is not None else 0.2)
+
+    def finish(self):
+        self.stop_flag.set()
+        self.join(timeout=15)
+        return self.summary()
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.samples)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0, "source": self.source}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = sorted({r for s in self.samples for r in s[2]})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": reasons, "samples": len(self.samples),
+                "source": self.source}
 
 
 def _peaks():
@@ -156,7 +192,7 @@ def _config(args, per_gpu_batch):
             "l2": f"inputs rotate over {N_SETS} distinct batches ({N_SETS * per_gpu_batch * W * H * 3 / 1e6:.0f} MB/GPU) > 126 MB L2",
             "parallelism": f"dp{args.gpus} (screenshots sharded, one NCCL gather of results per step)",
             "schedule": "one batch at a time" if getattr(args, "no_pipeline", False) else
-                        "2-deep pipeline across steps: detection of step i+1 overlaps host list logic + captioning of step i"}
+                        f"pipeline across steps: detect(i+1) on stream A | host list logic(i) | {args.caption_lanes} caption lanes (batches i-1.. on own streams/plans); fill and drain are inside the timed region"}
 
 
 # ------------------------------------------------------------------------------------------------ this repo
@@ -203,7 +239,8 @@ def run_b200(args):
     torch.cuda.synchronize()
 
     from omniparser_b200.utils import PipelinedParser
-    pp = PipelinedParser(model, cmp_, BOX_TRESHOLD=args.box_threshold, iou_threshold=0.7, max_new_tokens=args.max_new_tokens)
+    pp = PipelinedParser(model, cmp_, BOX_TRESHOLD=args.box_threshold, iou_threshold=0.7, max_new_tokens=args.max_new_tokens,
+                         caption_lanes=args.caption_lanes)
 
     def run_steps(n_steps, resident):
         if args.no_pipeline:
@@ -238,16 +275,16 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
         wall = time.perf_counter() - t0
-        sampler.stop_flag.set()
+        clk = sampler.finish()
         ms = e0.elapsed_time(e1)
         t = torch.tensor([ms], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         launches = (_lib.launch_count() - l0) + (ops.GRAPH_LAUNCHES[0] - g0)
-        return float(t.item()), wall, launches, sampler.summary(), tms, dict(stats)
+        return float(t.item()), wall, launches, clk, tms, dict(stats)
 
     if not args.no_pipeline:
-        run_steps(max(args.warmup, N_SETS), True)   # warm the pipelined path (second io slot, stream-local scratch)
+        run_steps(max(args.warmup, N_SETS, args.caption_lanes + 4), True)   # warm the pipelined path (second io slot, stream-local scratch)
         run_steps(2, False)
         torch.cuda.synchronize()
         log("pipelined warm-up done")
@@ -339,7 +376,8 @@ def cpu_baseline(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--caption-lanes", type=int, default=2, help="caption batches in flight (own stream + plan each)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="screenshots per GPU per step")

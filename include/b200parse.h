@@ -46,6 +46,10 @@ int b2p_maxpool_s1(const void* x, long long ldx, int B, int H, int W, int C, int
                    b2p_stream_t stream);
 int b2p_upsample2x(const void* x, long long ldx, int B, int H, int W, int C, void* y, long long ldy,
                    b2p_stream_t stream);
+/* explicit 3x3 / pad-1 im2col of an NHWC f16 map -> [B*Ho*Wo][9*C] (tap-major), for convs whose output map is far
+ * smaller than one 128-pixel implicit-GEMM tile (DaViT patch-embed convs of the 64x64-crop mode, hf:modeling_florence2.py
+ * ConvEmbed, reached from ref:util/utils.py:125 generate) */
+int b2p_im2col3x3(const void* x, long long ldx, int B, int H, int W, int C, int stride, void* out, b2p_stream_t stream);
 int b2p_cbfuse(int nsrc, const void* const* srcs_host, const long long* lds_host, const int* shifts_host,
                const void* last, long long ldl, int B, int H, int W, int C, void* y, long long ldy,
                b2p_stream_t stream);

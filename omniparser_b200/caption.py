@@ -14,6 +14,7 @@ table.  Float ``pixel_values`` (K,3,64,64) are also accepted and mapped back to 
 from __future__ import annotations
 
 import json
+import threading
 from pathlib import Path
 from types import SimpleNamespace
 from typing import Dict, List, Optional, Sequence
@@ -97,6 +98,7 @@ class B200Florence2Model:
             self.weights = FlorenceWeights(state_dict, self.device, self.gen, precision)
         self.use_graph = use_graph
         self._plans: Dict[tuple, FlorencePlan] = {}
+        self._plan_lock = threading.Lock()
         inv = np.zeros((3, 256), np.float32)
         for c in range(3):
             inv[c] = (np.arange(256, dtype=np.float32) * np.float32(1 / 255.0) - np.float32(IMAGENET_MEAN[c])) / np.float32(IMAGENET_STD[c])
@@ -108,16 +110,19 @@ class B200Florence2Model:
     def eval(self):
         return self
 
-    def plan_for(self, n: int, max_new_tokens: int, prompt_ids: Sequence[int], size: int = 64) -> FlorencePlan:
+    def plan_for(self, n: int, max_new_tokens: int, prompt_ids: Sequence[int], size: int = 64, instance: int = 0) -> FlorencePlan:
+        """Launch plan (buffers + CUDA graphs) for up to ``n`` crops.  Plans of different ``instance`` share nothing
+        mutable, so the pipeline can caption two batches concurrently on two streams."""
         if size == 64:
             K = max(BUCKET, ((n + BUCKET - 1) // BUCKET) * BUCKET)
         else:
             K = BUCKET_768
-        key = (K, max_new_tokens, tuple(prompt_ids), size)
-        if key not in self._plans:
-            with torch.cuda.device(self.device):
-                self._plans[key] = FlorencePlan(self.weights, K, max_new_tokens, list(prompt_ids), self.use_graph, size)
-        return self._plans[key]
+        key = (K, max_new_tokens, tuple(prompt_ids), size, instance)
+        with self._plan_lock:
+            if key not in self._plans:
+                with torch.cuda.device(self.device):
+                    self._plans[key] = FlorencePlan(self.weights, K, max_new_tokens, list(prompt_ids), self.use_graph, size, instance)
+            return self._plans[key]
 
     def _to_u8(self, pixel_values: torch.Tensor) -> torch.Tensor:
         if pixel_values.dtype == torch.uint8:

@@ -554,7 +554,7 @@ static int encode(CUtensorMap* m, int bf16, int rank, const void* base, const cu
 static int g_num_sms = 0;
 // Split-K scratch is per stream (two streams may run split-K GEMMs concurrently): a few slots are allocated up
 // front (never inside a graph capture) and handed to streams in order of first use.
-static constexpr int kWsSlots = 12;
+static constexpr int kWsSlots = 24;
 static float* g_ws[kWsSlots] = {};
 static int* g_counters[kWsSlots] = {};
 static cudaStream_t g_ws_owner[kWsSlots] = {};

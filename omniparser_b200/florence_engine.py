@@ -153,11 +153,13 @@ class FlorencePlan:
     D = 768
     HEADS = 12
 
-    def __init__(self, w: FlorenceWeights, K: int, max_new_tokens: int, prompt_ids: List[int], use_graph=True, size: int = 64):
-        """size = 64: the reference's CUDA branch (crops fed un-resized, 5 image tokens, ref:util/utils.py:121);
+    def __init__(self, w: FlorenceWeights, K: int, max_new_tokens: int, prompt_ids: List[int], use_graph=True, size: int = 64, instance: int = 0):
+        """instance: plans of different instances own disjoint buffers and capture streams (split-K scratch is keyed by
+        stream), so they may run concurrently on different streams.  size = 64: the reference's CUDA branch (crops fed un-resized, 5 image tokens, ref:util/utils.py:121);
         size = 768: its CPU branch (CLIP processor bicubic resize of every crop to 768x768, 577 image tokens, :123)."""
         assert size in (64, 768)
         self.S = size
+        self.tag = f"florence{instance}"
         self.w, self.K, self.dev = w, K, w.device
         self.x3 = w.x3
         self.KX = 3 if w.x3 else 1
@@ -233,8 +235,18 @@ class FlorencePlan:
                 T = K * H * H
                 xo = ops.new_map(K, H, H, C, self.dev, torch.float32)
                 ce = w.conv_embed[s]
-                self.flops_enc += 2 * T * C * 9 * Cp
-                ops_.append(lambda hmap=hmap, xo=xo, ce=ce: ops.conv3x3(hmap, ce.w, xo, 2, ce.b, None, ACT_NONE, out_f32=True))
+                if H * H <= 32:
+                    # 4x4 / 2x2 output maps (64x64-crop mode): a 128-pixel implicit-GEMM tile would be 8x / 32x padding, so
+                    # gather the taps explicitly (row copies) and run the dense GEMM on [T, 9*Cs]
+                    col = torch.empty((T, 9 * hmap.C), dtype=torch.float16, device=self.dev)
+                    ops_.append(lambda hmap=hmap, col=col: ops.im2col3x3(hmap, 2, col))
+                    xv = xo.buf.view(T, C)
+                    lin = type("W", (), {})()
+                    lin.w, lin.b, lin.N, lin.K, lin.Klog = ce.w, ce.b, C, 9 * hmap.C, 9 * Cp
+                    self._gemm(ops_, col, lin, xv)
+                else:
+                    self.flops_enc += 2 * T * C * 9 * Cp
+                    ops_.append(lambda hmap=hmap, xo=xo, ce=ce: ops.conv3x3(hmap, ce.w, xo, 2, ce.b, None, ACT_NONE, out_f32=True))
                 x = xo.buf.view(T, C)
             for blk in w.blocks[s]:
                 for kind in ("spatial_block", "channel_block"):
@@ -384,11 +396,12 @@ class FlorencePlan:
         if g is None:
             for f in lst:
                 f()
-            torch.cuda.synchronize()
+            torch.cuda.current_stream().synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=ops.capture_stream(tag, self.dev), capture_error_mode="thread_local"):
-                for f in lst:
-                    f()
+            with ops.CAPTURE_LOCK:   # one capture at a time across the pipeline's threads
+                with torch.cuda.graph(g, stream=ops.capture_stream(tag, self.dev), capture_error_mode="thread_local"):
+                    for f in lst:
+                        f()
             if isinstance(holder, dict):
                 holder[key] = g
             else:
@@ -400,9 +413,9 @@ class FlorencePlan:
     def encode(self, from_resized: bool = False):
         """from_resized: the SxS crops are already in ``crops_in`` (host-side processor did the bicubic resize)."""
         if from_resized and self.S != 64:
-            self._run(self.enc_ops[1:], self, "g_enc_nr", "florence")
+            self._run(self.enc_ops[1:], self, "g_enc_nr", self.tag)
         else:
-            self._run(self.enc_ops, self, "g_enc", "florence")
+            self._run(self.enc_ops, self, "g_enc", self.tag)
 
     def reset_decode(self, n_active: int):
         self.seq.zero_()
@@ -428,7 +441,7 @@ class FlorencePlan:
         if dump is None and force_tokens is None:
             cur = torch.cuda.current_stream()
             if len(self.parts) == 1:
-                self._run(self.parts[0]["full"], self.parts[0], "graph", "florence_dec0")
+                self._run(self.parts[0]["full"], self.parts[0], "graph", self.tag + "_dec0")
                 return
             if not self._forked:
                 for pt in self.parts:
@@ -436,7 +449,7 @@ class FlorencePlan:
                 self._forked = True
             for pt in self.parts:
                 with torch.cuda.stream(pt["stream"]):
-                    self._run(pt["full"], pt, "graph", f"florence_dec{pt['idx']}")
+                    self._run(pt["full"], pt, "graph", f"{self.tag}_dec{pt['idx']}")
             return
         for pt in self.parts:   # eager path used by the parity tests
             for f in pt["ops"]:

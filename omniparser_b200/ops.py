@@ -6,6 +6,7 @@ so concatenations (``torch.cat`` in the reference graph) are never materialised.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from dataclasses import dataclass
 
 import torch
@@ -14,6 +15,7 @@ from . import _lib
 
 ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
 _CAPTURE_STREAMS = {}
+CAPTURE_LOCK = threading.RLock()   # one CUDA-graph capture at a time across the pipeline's threads
 
 
 def capture_stream(tag, device):
@@ -121,6 +123,11 @@ def maxpool_s1(x: Map, y: Map, k=5):
 
 def upsample2x(x: Map, y: Map):
     _lib.check(_lib.lib().b2p_upsample2x(_p(x.ptr), x.ld, x.B, x.H, x.W, x.C, _p(y.ptr), y.ld, _stream()))
+
+
+def im2col3x3(x: Map, stride, out):
+    """out [B*Ho*Wo, 9*C] f16 (tap-major) for a 3x3 / pad 1 conv over the NHWC map ``x``."""
+    _lib.check(_lib.lib().b2p_im2col3x3(_p(x.ptr), x.ld, x.B, x.H, x.W, x.C, stride, _p(out), _stream()))
 
 
 def cbfuse(srcs: list[Map], last: Map, out: Map):

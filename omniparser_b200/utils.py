@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import base64
 import io
+import threading
 import time
 from pathlib import Path
 from typing import List, Optional, Sequence, Union
@@ -141,8 +142,8 @@ def parse_screenshots(images: Sequence[np.ndarray], model: B200YOLOv9Detector, c
 
 
 class PipelinedParser:
-    """Two-deep software pipeline over batches of same-size screenshots: detection of batch i+1 (stream A) overlaps
-    the host list logic and the captioning of batch i (stream B).  Same results as :func:`parse_screenshots`, batch by
+    """Three-stage software pipeline over batches of same-size screenshots: detection of batch i+1 (stream A), the host
+    list logic of batch i and the captioning of batch i-1 (stream B) run concurrently.  Same results as :func:`parse_screenshots`, batch by
     batch; only the scheduling differs.  Usage::
 
         pp = PipelinedParser(model, caption_model_processor, BOX_TRESHOLD=0.05, iou_threshold=0.7)
@@ -151,7 +152,7 @@ class PipelinedParser:
     """
 
     def __init__(self, model: B200YOLOv9Detector, caption_model_processor: dict, BOX_TRESHOLD=0.01, iou_threshold=0.9,
-                 imgsz=640, max_new_tokens=20, prompt_ids: Sequence[int] = CAPTION_PROMPT_IDS):
+                 imgsz=640, max_new_tokens=20, prompt_ids: Sequence[int] = CAPTION_PROMPT_IDS, caption_lanes: int = 2):
         self.model, self.cmp = model, caption_model_processor
         self.conf, self.iou_thr, self.imgsz, self.T, self.prompt = BOX_TRESHOLD, iou_threshold, imgsz, max_new_tokens, list(prompt_ids)
         dev = model.device
@@ -160,6 +161,13 @@ class PipelinedParser:
         self.timings = ParseTimings(detect_wait_s=0.0, glue_s=0.0, caption_s=0.0, n_boxes=0, n_crops=0, batches=0)
         from concurrent.futures import ThreadPoolExecutor
         self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="b2p-submit")   # host staging copy off the main thread
+        # caption stage: CAPTION_LANES batches in flight, each on its own stream with its own plan instance -- the
+        # latency-bound decode steps of one batch fill the SMs the other batch's encoder leaves idle, and vice versa
+        self.lanes = max(1, int(caption_lanes))
+        self.s_caps = [self.s_cap] + [torch.cuda.Stream(device=dev) for _ in range(self.lanes - 1)]
+        self._cap_pool = ThreadPoolExecutor(max_workers=self.lanes, thread_name_prefix="b2p-caption")
+        self._tm_lock = threading.Lock()
+        self._job = 0
 
     @torch.inference_mode()
     def _submit(self, slot: int, images, resident_src=None):
@@ -182,9 +190,9 @@ class PipelinedParser:
             ev.record(self.s_det)
         return dict(io=io_, ev=ev, B=B, H=H, W=W)
 
-    def _finish(self, h, ocr):
+    def _glue(self, h, ocr):
+        """Stage 2 (caller's thread): wait for the detector's boxes, run the reference's host list logic."""
         io_, B, H, W = h["io"], h["B"], h["H"], h["W"]
-        model, cap_model, processor = self.model, self.cmp["model"], self.cmp["processor"]
         t0 = time.perf_counter()
         h["ev"].synchronize()
         t1 = time.perf_counter()
@@ -202,16 +210,33 @@ class PipelinedParser:
                 if e["content"] is None:
                     crop_boxes.append(e["bbox"])
                     crop_img.append(i)
+        t2 = time.perf_counter()
+        tm = self.timings
+        tm["detect_wait_s"] += t1 - t0; tm["glue_s"] += t2 - t1
+        tm["n_boxes"] += sum(counts); tm["n_crops"] += len(crop_boxes); tm["batches"] += 1
+        lane = self._job % self.lanes
+        self._job += 1
+        return dict(h=h, all_elems=all_elems, crop_boxes=crop_boxes, crop_img=crop_img, lane=lane)
+
+    @torch.inference_mode()
+    def _caption(self, g):
+        """Stage 3 (caption thread, stream B): crop+resize from the resident screenshots, Florence-2 greedy decode,
+        token ids back to the host, captions into the element lists."""
+        torch.cuda.set_device(self.model.device)
+        h, all_elems, crop_boxes, crop_img = g["h"], g["all_elems"], g["crop_boxes"], g["crop_img"]
+        io_, B, H, W = h["io"], h["B"], h["H"], h["W"]
+        model, cap_model, processor = self.model, self.cmp["model"], self.cmp["processor"]
         n = len(crop_boxes)
         t2 = time.perf_counter()
         ids = None
         if n:
             dev = model.device
-            with torch.cuda.stream(self.s_cap):
-                plan = cap_model.plan_for(n, self.T, self.prompt)
+            lane = g.get("lane", 0)
+            with torch.cuda.stream(self.s_caps[lane]):
+                plan = cap_model.plan_for(n, self.T, self.prompt, instance=lane)
                 d_boxes = torch.tensor(crop_boxes, dtype=torch.float32).to(dev, non_blocking=True)
                 d_bimg = torch.tensor(crop_img, dtype=torch.int32).to(dev, non_blocking=True)
-                key = ("crop_meta", B, H, W)
+                key = ("crop_meta", B, H, W, lane)
                 meta = model._io.get(key)
                 if meta is None:
                     meta = dict(hw=torch.tensor([[H, W]] * B, dtype=torch.int32, device=dev),
@@ -228,14 +253,20 @@ class PipelinedParser:
             host_glue.fill_captions(all_elems[i], texts_all[k:k + mcap])
             out.append((all_elems[i], ids[k:k + mcap] if ids is not None else torch.zeros((0, 1), dtype=torch.long)))
             k += mcap
-        tm = self.timings
-        tm["detect_wait_s"] += t1 - t0; tm["glue_s"] += t2 - t1; tm["caption_s"] += t3 - t2
-        tm["n_boxes"] += sum(counts); tm["n_crops"] += n; tm["batches"] += 1
+        with self._tm_lock:
+            self.timings["caption_s"] += t3 - t2
         return out
+
+    def _finish(self, h, ocr):
+        return self._caption(self._glue(h, ocr))
 
     @torch.inference_mode()
     def run(self, batches, resident=None):
-        """batches: iterable of (images, ocr); resident: optional parallel iterable of device u8 tensors [B,H,W,3]."""
+        """batches: iterable of (images, ocr); resident: optional parallel iterable of device u8 tensors [B,H,W,3].
+        Stages in flight: detect(i+1) on stream A (submit thread) | host list logic of batch i (this thread) |
+        caption(i-1), caption(i-2) on their lane's stream (caption threads).  lanes + 2 io slots keep a batch's resident
+        screenshots alive until its crops have been cut.  Results come out in order, ``lanes`` batches behind the glue."""
+        from collections import deque
         with torch.cuda.device(self.model.device):
             it = iter(batches)
             rit = iter(resident) if resident is not None else None
@@ -244,16 +275,21 @@ class PipelinedParser:
                 return
             slot = 0
             h = self._submit(slot, cur[0], next(rit) if rit is not None else None)
+            pending = deque()
             while cur is not None:
                 nxt = next(it, None)
                 fut = None
                 if nxt is not None:
-                    slot ^= 1
+                    slot = (slot + 1) % (self.lanes + 2)
                     fut = self._pool.submit(self._submit, slot, nxt[0], next(rit) if rit is not None else None)
-                out = self._finish(h, cur[1])
+                g = self._glue(h, cur[1])
+                pending.append(self._cap_pool.submit(self._caption, g))
+                if len(pending) > self.lanes:
+                    yield pending.popleft().result()
                 hn = fut.result() if fut is not None else None
-                yield out
                 cur, h = nxt, hn
+            while pending:
+                yield pending.popleft().result()
 
 
 # ------------------------------------------------------------------------------------------------ reference API

@@ -187,6 +187,19 @@ def test_letterbox_bit_exact(size, imgsz):
         assert np.array_equal(ref, canvas[b].cpu().numpy())
 
 
+@pytest.mark.parametrize("B,H,W,C,stride", [(3, 8, 8, 48, 2), (2, 4, 4, 768, 2), (2, 5, 7, 16, 1), (1, 9, 6, 24, 2)])
+def test_im2col3x3_exact(B, H, W, C, stride):
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, H, W, C, generator=g).half().to(DEV)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    out = torch.empty(B * Ho * Wo, 9 * C, dtype=torch.float16, device=DEV)
+    ops.im2col3x3(ops.Map(x, 0, C), stride, out)
+    torch.cuda.synchronize()
+    xp = torch.nn.functional.pad(x.cpu().float(), (0, 0, 1, 1, 1, 1))
+    ref = torch.stack([xp[:, ky:ky + (Ho - 1) * stride + 1:stride, kx:kx + (Wo - 1) * stride + 1:stride] for ky in range(3) for kx in range(3)], 3)
+    assert torch.equal(out.cpu().float(), ref.reshape(B * Ho * Wo, 9 * C))
+
+
 @pytest.mark.parametrize("filt", [0, 1])
 @pytest.mark.parametrize("src_hw,dst_wh", [((64, 64), (768, 768)), ((37, 53), (100, 80)), ((300, 200), (64, 48))])
 def test_resize_u8_bit_exact_vs_pillow(filt, src_hw, dst_wh):
