@@ -30,7 +30,10 @@ int b2p_abi_version(void);
 
 /* ---- dense contractions (tcgen05 + TMA + TMEM), ref:util/yolov9.py:120-121 and ref:util/utils.py:125 ----
  * flags: bit0 operands bf16 (else fp16) | bit1 output fp32 (else fp16) | bit2 fp16 output in the "fp16x3" operand
- * layout [hi | hi | lo] (ldc >= 3N) | bits 8.. maximum N tile (0 = auto).  act: 0 none, 1 SiLU, 2 exact GELU.
+ * layout [hi(N) | lo(N)] (ldc >= 2N) | bit3 fp16x3 OPERANDS: A rows [hi(K) | lo(K)] (lda >= 2K; conv: pixels
+ * [hi(Cin) | lo(Cin)]), weight rows [hi | lo] likewise (conv: per tap), K / Cin the logical sizes; the kernel loads each
+ * half once per k-block and accumulates hi*hi + hi*lo + lo*hi in fp32 | bits 8.. maximum N tile (0 = auto).
+ * act: 0 none, 1 SiLU, 2 exact GELU.
  * out = act(A[M,K] * B[N,K]^T + bias[N]) + residual (residual has the dtype of out). */
 int b2p_gemm(const void* A, long long lda, const void* B, int M, int N, int K, void* out, long long ldc,
              const float* bias, const void* residual, long long ldr, int act, int flags, b2p_stream_t stream);
@@ -49,7 +52,8 @@ int b2p_upsample2x(const void* x, long long ldx, int B, int H, int W, int C, voi
 /* explicit 3x3 / pad-1 im2col of an NHWC f16 map -> [B*Ho*Wo][9*C] (tap-major), for convs whose output map is far
  * smaller than one 128-pixel implicit-GEMM tile (DaViT patch-embed convs of the 64x64-crop mode, hf:modeling_florence2.py
  * ConvEmbed, reached from ref:util/utils.py:125 generate) */
-int b2p_im2col3x3(const void* x, long long ldx, int B, int H, int W, int C, int stride, void* out, b2p_stream_t stream);
+int b2p_im2col3x3(const void* x, long long ldx, int B, int H, int W, int C, int stride, int halves, void* out,
+                  b2p_stream_t stream);   /* halves = 2: fp16x3 pixels [hi(C) | lo(C)] -> rows [hi: 9C | lo: 9C] */
 int b2p_cbfuse(int nsrc, const void* const* srcs_host, const long long* lds_host, const int* shifts_host,
                const void* last, long long ldl, int B, int H, int W, int C, void* y, long long ldy,
                b2p_stream_t stream);

@@ -124,6 +124,16 @@ class B200Florence2Model:
                     self._plans[key] = FlorencePlan(self.weights, K, max_new_tokens, list(prompt_ids), self.use_graph, size, instance)
             return self._plans[key]
 
+    def plan_ready(self, n: int, max_new_tokens: int, prompt_ids: Sequence[int], size: int = 64, instance: int = 0) -> bool:
+        K = max(BUCKET, ((n + BUCKET - 1) // BUCKET) * BUCKET) if size == 64 else BUCKET_768
+        p = self._plans.get((K, max_new_tokens, tuple(prompt_ids), size, instance))
+        return p is not None and (p.warmed or not p.use_graph)
+
+    def warm_plan(self, n: int, max_new_tokens: int, prompt_ids: Sequence[int], size: int = 64, instance: int = 0, stream=None):
+        """Construct the plan for this crop-count bucket and capture its graphs on scratch inputs."""
+        with torch.cuda.device(self.device), torch.cuda.stream(stream if stream is not None else torch.cuda.current_stream()):
+            self.plan_for(n, max_new_tokens, prompt_ids, size, instance).warm()
+
     def _to_u8(self, pixel_values: torch.Tensor) -> torch.Tensor:
         if pixel_values.dtype == torch.uint8:
             if pixel_values.dim() == 4 and pixel_values.shape[-1] == 3:

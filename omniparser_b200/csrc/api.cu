@@ -42,17 +42,19 @@ long long b2p_launch_count(void) { return g_launches.load(); }
 int b2p_abi_version(void) { return 1; }
 
 // C[M,N] = act(A[M,K] * B[N,K]^T + bias) (+ residual); A, B fp16 (bf16 if flags&1); out fp16 or fp32 (flags&2);
-// flags&4: fp16 output in the fp16x3 operand layout [hi | hi | lo] (ldc >= 3N).
+// flags&4: fp16 output in the fp16x3 operand layout [hi(N) | lo(N)] (ldc >= 2N).
+// flags&8: fp16x3 operands: A rows [hi(K) | lo(K)] (lda >= 2K), B rows [hi(K) | lo(K)]; K is the logical reduction size.
 int b2p_gemm(const void* A, long long lda, const void* B, int M, int N, int K, void* out, long long ldc,
              const float* bias, const void* residual, long long ldr, int act, int flags, cudaStream_t st) {
   ConvGemm d{};
   d.mode = 0; d.bf16 = flags & 1; d.A = A; d.lda = lda; d.B = B; d.M = M; d.N = N; d.K = K;
   d.out = out; d.ldc = ldc; d.out_f32 = (flags >> 1) & 1; d.bias = bias; d.res = residual; d.ldr = ldr; d.act = act;
-  d.bn_max = (flags >> 8) & 0x1ff; d.split_out = (flags >> 2) & 1;
+  d.bn_max = (flags >> 8) & 0x1ff; d.split_out = (flags >> 2) & 1; d.x3 = (flags >> 3) & 1;
   return gemm_launch(d, st);
 }
 
 // 3x3 pad-1 convolution (stride 1 or 2) on an NHWC fp16 channel slice; weights [Cout][9*Cin] ordered (ky,kx,c).
+// flags&8 (fp16x3 operands): pixels are [hi(Cin) | lo(Cin)], weights [Cout][9][hi(Cin) | lo(Cin)]; Cin is the logical size.
 int b2p_conv3x3(const void* in, long long ld_in, int batch, int H, int W, int Cin, int stride, const void* weight,
                 int Cout, void* out, long long ldc, const float* bias, const void* residual, long long ldr, int act,
                 int flags, cudaStream_t st) {
@@ -61,7 +63,7 @@ int b2p_conv3x3(const void* in, long long ld_in, int batch, int H, int W, int Ci
   d.mode = stride; d.bf16 = flags & 1; d.A = in; d.lda = ld_in; d.B = weight; d.N = Cout;
   d.batch = batch; d.H = H; d.W = W; d.Cin = Cin;
   d.out = out; d.ldc = ldc; d.out_f32 = (flags >> 1) & 1; d.bias = bias; d.res = residual; d.ldr = ldr; d.act = act;
-  d.bn_max = (flags >> 8) & 0x1ff; d.split_out = (flags >> 2) & 1;
+  d.bn_max = (flags >> 8) & 0x1ff; d.split_out = (flags >> 2) & 1; d.x3 = (flags >> 3) & 1;
   return gemm_launch(d, st);
 }
 

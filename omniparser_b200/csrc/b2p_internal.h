@@ -32,7 +32,9 @@ struct ConvGemm {
   long long ldr;
   int act;             // 0 none, 1 SiLU, 2 GELU(erf)
   int bn_max;          // 0 = auto
-  int split_out;       // fp16 output written as [hi | hi | lo] (row stride ldc >= 3N): operand of a fp16x3 GEMM
+  int split_out;       // fp16 output written as [hi(N) | lo(N)] (row stride ldc >= 2N): operand of a fp16x3 GEMM
+  int x3;              // fp16x3 operands: A rows [hi(K) | lo(K)] (conv: per pixel [hi(Cin) | lo(Cin)]), B rows likewise;
+                       // K / Cin are the LOGICAL sizes.  out = A_hi*B_hi + A_hi*B_lo + A_lo*B_hi, fp32 accumulate
 };
 
 int gemm_launch(const ConvGemm& d, cudaStream_t st);

@@ -213,33 +213,37 @@ int b2p_upsample2x(const void* x, long long ldx, int B, int H, int W, int C, voi
 // Explicit im2col of an NHWC fp16 map for a 3x3 / pad 1 conv: out[(b,yo,xo)][tap*C + c] = x[b][yo*s+ky-1][xo*s+kx-1][c] (0 outside).
 // Used where the implicit-GEMM tile would be mostly padding (DaViT stage 2/3 patch-embed convs on 4x4 / 2x2 output maps of the
 // 64x64-crop mode: a 128-pixel tile holds 16 / 4 real pixels); the result feeds the plain GEMM.  HBM-bound row copies (uint4).
+// halves == 2: fp16x3 operands -- pixels are [hi(C) | lo(C)] and the output row is [hi: 9*C | lo: 9*C].
 __global__ void im2col3x3_kernel(const __half* __restrict__ x, long long ldx, int B, int H, int W, int C, int s, int Ho, int Wo,
-                                 __half* __restrict__ out) {
+                                 int halves, __half* __restrict__ out) {
   pdl_wait();
   const int c8 = C >> 3;
-  const long long total = (long long)B * Ho * Wo * 9 * c8;
+  const long long total = (long long)B * Ho * Wo * halves * 9 * c8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = int(i % c8);
     long long r = i / c8;
     const int tap = int(r % 9); r /= 9;
+    const int half = int(r % halves); r /= halves;
     const int xo = int(r % Wo); r /= Wo;
     const int yo = int(r % Ho);
     const int b = int(r / Ho);
     const int y = yo * s + tap / 3 - 1, xx = xo * s + tap % 3 - 1;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (y >= 0 && y < H && xx >= 0 && xx < W)
-      v = *reinterpret_cast<const uint4*>(x + (((long long)b * H + y) * W + xx) * ldx + c * 8);
+      v = *reinterpret_cast<const uint4*>(x + (((long long)b * H + y) * W + xx) * ldx + half * C + c * 8);
     reinterpret_cast<uint4*>(out)[i] = v;
   }
 }
 
-int b2p_im2col3x3(const void* x, long long ldx, int B, int H, int W, int C, int stride, void* out, cudaStream_t st) {
+int b2p_im2col3x3(const void* x, long long ldx, int B, int H, int W, int C, int stride, int halves, void* out, cudaStream_t st) {
   if (C % 8 || ldx % 8) return set_error("im2col3x3: C and the pixel stride must be multiples of 8");
   if (stride != 1 && stride != 2) return set_error("im2col3x3: stride 1 or 2");
+  if (halves != 1 && halves != 2) return set_error("im2col3x3: halves is 1 (plain) or 2 (fp16x3 [hi | lo] pixels)");
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
-  const long long n = (long long)B * Ho * Wo * 9 * (C / 8);
+  const long long n = (long long)B * Ho * Wo * halves * 9 * (C / 8);
   if (n == 0) return 0;
-  launch_pdl(im2col3x3_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, (const __half*)x, ldx, B, H, W, C, stride, Ho, Wo, (__half*)out);
+  launch_pdl(im2col3x3_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, (const __half*)x, ldx, B, H, W, C, stride, Ho, Wo, halves,
+             (__half*)out);
   B2P_CHECK_LAUNCH();
   return 0;
 }

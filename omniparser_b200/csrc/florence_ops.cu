@@ -18,16 +18,13 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// fp16 activation store.  split == 0: plain.  split == K > 0: "fp16x3" operand layout [hi | hi | lo] (row stride 3K)
-// so that a K-concatenated GEMM against [W_hi | W_lo | W_hi] accumulates hi*hi + hi*lo + lo*hi in fp32
-// (2^-22-class products instead of 2^-11): the parity-grade precision mode of the caption path.
+// fp16 activation store.  split == 0: plain.  split == K > 0: "fp16x3" operand layout [hi(K) | lo(K)] (row stride 2K):
+// the GEMM loads both halves of A and of W = [W_hi | W_lo] once per k-block and accumulates hi*hi + hi*lo + lo*hi in
+// fp32 (2^-22-class products instead of 2^-11): the parity-grade precision mode of the caption path.
 __device__ __forceinline__ void store_act(__half* row, int c, int split, float v) {
   const __half h = __float2half_rn(v);
   row[c] = h;
-  if (split) {
-    row[split + c] = h;
-    row[2 * split + c] = __float2half_rn(v - __half2float(h));
-  }
+  if (split) row[split + c] = __float2half_rn(v - __half2float(h));
 }
 
 // 4 consecutive channels (c % 4 == 0) as one 8-byte store per copy
@@ -35,10 +32,9 @@ __device__ __forceinline__ void store_act4(__half* row, int c, int split, const 
   __align__(8) __half2 h[2] = {__floats2half2_rn(v.x, v.y), __floats2half2_rn(v.z, v.w)};
   *reinterpret_cast<uint2*>(row + c) = *reinterpret_cast<const uint2*>(h);
   if (split) {
-    *reinterpret_cast<uint2*>(row + split + c) = *reinterpret_cast<const uint2*>(h);
     const float2 a = __half22float2(h[0]), b = __half22float2(h[1]);
     __align__(8) __half2 l[2] = {__floats2half2_rn(v.x - a.x, v.y - a.y), __floats2half2_rn(v.z - b.x, v.w - b.y)};
-    *reinterpret_cast<uint2*>(row + 2 * split + c) = *reinterpret_cast<const uint2*>(l);
+    *reinterpret_cast<uint2*>(row + split + c) = *reinterpret_cast<const uint2*>(l);
   }
 }
 
@@ -118,7 +114,7 @@ __global__ void dwconv_ln_kernel(const float* __restrict__ x, int B, int H, int 
   }
   const float rstd = rsqrtf(warp_sum(q) / float(C) + eps);
   n = 0;
-  __half* orow = o16 + tok * (split ? 3 * C : C);
+  __half* orow = o16 + tok * (split ? 2 * C : C);
   for (int c = lane; c < C4; c += 32, ++n) {
     const float4 gg = reinterpret_cast<const float4*>(g)[c], bb = reinterpret_cast<const float4*>(bt)[c];
     float4 o;
@@ -235,7 +231,7 @@ __global__ void window_attn_kernel(const float* __restrict__ qkv, const float* _
       }
     }
     const float inv = 1.f / l;
-    __half* orow = out + tok * (split ? 3 * C : C);
+    __half* orow = out + tok * (split ? 2 * C : C);
 #pragma unroll
     for (int d = 0; d < D4; ++d)
       store_act4(orow, head * D + 4 * d, split, make_float4(acc[d].x * inv, acc[d].y * inv, acc[d].z * inv, acc[d].w * inv));
@@ -290,7 +286,7 @@ __global__ void __launch_bounds__(256) channel_attn_kernel(const float* __restri
     float acc = 0.f;
 #pragma unroll
     for (int jj = 0; jj < D; ++jj) acc += pr[jj] * __shfl_sync(0xffffffffu, vj, jj);
-    store_act(out + ((long long)b * N + n) * (split ? 3 * C : C), g * D + j, split, acc);
+    store_act(out + ((long long)b * N + n) * (split ? 2 * C : C), g * D + j, split, acc);
   }
 }
 
@@ -477,9 +473,9 @@ __global__ void projector_prep_kernel(const float* __restrict__ x /*[B][HW][C]*/
     for (int t = 0; t < HW; ++t) {
       const float v = x[((long long)b * HW + t) * C + c] + pos[(long long)t * C + c];
       s += v;
-      store_act(out + ((long long)b * (HW + 1) + 1 + t) * (split ? 3 * C : C), c, split, v);
+      store_act(out + ((long long)b * (HW + 1) + 1 + t) * (split ? 2 * C : C), c, split, v);
     }
-    store_act(out + (long long)b * (HW + 1) * (split ? 3 * C : C), c, split, s / float(HW));
+    store_act(out + (long long)b * (HW + 1) * (split ? 2 * C : C), c, split, s / float(HW));
   }
 }
 

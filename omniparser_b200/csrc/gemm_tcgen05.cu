@@ -47,7 +47,11 @@ struct GemmArgs {
   const void* res;
   long long ldr;
   int act, vec_ok;
-  int split;   // > 0: fp16 output in the fp16x3 operand layout [hi | hi | lo] with logical width `split`
+  int split;   // > 0: fp16 output in the fp16x3 operand layout [hi | lo] with logical width `split`
+  // fp16x3 operands: A rows are [hi(K) | lo(K)] (conv: per pixel [hi(Cin) | lo(Cin)]), W rows [hi | lo] likewise.  Each
+  // pipeline stage holds A_hi, A_lo, B_hi, B_lo of ONE logical k-block (each loaded once) and the MMA warp issues the
+  // three products hi*hi + hi*lo + lo*hi into the same fp32 accumulator.
+  int x3, lo_a, lo_b, b_tap;   // lo_a / lo_b: column offset of the lo half in A / B; b_tap: B columns per conv tap
   float* ws;   // split-K partial tiles [tile][slice][128][bn] fp32
   int* counters;   // split-K {arrived, finished} counters per output tile (self-resetting)
 };
@@ -152,9 +156,6 @@ __device__ __forceinline__ void epi_store16(const GemmArgs& g, const EpiCtx& e, 
       op[0] = pk[0];
       op[1] = pk[1];
       if (g.split) {
-        uint4* o2 = reinterpret_cast<uint4*>(e.outh + pix * g.ldc + g.split + nb);
-        o2[0] = pk[0];
-        o2[1] = pk[1];
         uint4 lo[2];
         __half2* lp = reinterpret_cast<__half2*>(lo);
 #pragma unroll
@@ -162,7 +163,7 @@ __device__ __forceinline__ void epi_store16(const GemmArgs& g, const EpiCtx& e, 
           const float2 hf = __half22float2(hp[k]);
           lp[k] = __floats2half2_rn(x[2 * k] - hf.x, x[2 * k + 1] - hf.y);
         }
-        uint4* o3 = reinterpret_cast<uint4*>(e.outh + pix * g.ldc + 2 * g.split + nb);
+        uint4* o3 = reinterpret_cast<uint4*>(e.outh + pix * g.ldc + g.split + nb);
         o3[0] = lo[0];
         o3[1] = lo[1];
       }
@@ -182,10 +183,7 @@ __device__ __forceinline__ void epi_store16(const GemmArgs& g, const EpiCtx& e, 
           else {
             const __half hh = __float2half_rn(t);
             e.outh[pix * g.ldc + n] = hh;
-            if (g.split) {
-              e.outh[pix * g.ldc + g.split + n] = hh;
-              e.outh[pix * g.ldc + 2 * g.split + n] = __float2half_rn(t - __half2float(hh));
-            }
+            if (g.split) e.outh[pix * g.ldc + g.split + n] = __float2half_rn(t - __half2float(hh));
           }
         }
       }
@@ -197,7 +195,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t stage_bytes = (g.mode == 3) ? g.b_slot : kASlot + g.b_slot;
+  const uint32_t a_part = g.x3 ? 2u * kASlot : uint32_t(kASlot);                     // [A_hi][A_lo] | [A]
+  const uint32_t stage_bytes = (g.mode == 3) ? g.b_slot : a_part + (g.x3 ? 2u : 1u) * g.b_slot;
   const uint32_t a_region = (g.mode == 3) ? uint32_t(g.stagesA) * g.a_slot : 0u;   // halo mode: [A slots][B slots]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a_region + size_t(g.stages) * stage_bytes);
   const uint32_t bar_full = smem_u32(bars);
@@ -293,24 +292,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t fb = bar_full + 8 * stage;
           const uint32_t sa = smem_base + stage * stage_bytes;
-          const uint32_t sb = sa + kASlot;
-          mbar_expect_tx(fb, g.a_bytes + g.b_bytes);
-          if (g.mode == 0) {
-            tma_load_2d(sa, &tmA, fb, kb * g.bk, mt * kTileM);
-          } else {
-            const int tap = kb / g.cin_blocks;
-            const int c0 = (kb - tap * g.cin_blocks) * g.bk;
-            const int ky = tap / 3, kx = tap - ky * 3;
-            if (g.mode == 1) {
-              tma_load_4d(sa, &tmA, fb, c0, x0 + kx - 1, y0 + ky - 1, img);
+          const uint32_t sb = sa + a_part;
+          mbar_expect_tx(fb, g.x3 ? 2u * (g.a_bytes + g.b_bytes) : g.a_bytes + g.b_bytes);
+          int bcol = kb * g.bk;
+          for (int half = 0; half <= g.x3; ++half) {     // half 1 = the lo parts (fp16x3 operands only)
+            const uint32_t dst = sa + half * kASlot;
+            const int ca = half * g.lo_a;
+            if (g.mode == 0) {
+              tma_load_2d(dst, &tmA, fb, ca + kb * g.bk, mt * kTileM);
             } else {
-              // input row 2*oy + (ky-1): ky=0 -> (oy-1, odd), ky=1 -> (oy, even), ky=2 -> (oy, odd); same in x.
-              const int py = (ky != 1), px = (kx != 1);
-              const int yo = y0 - (ky == 0), xo = x0 - (kx == 0);
-              tma_load_5d(sa, &tmA, fb, c0 + px * g.ldpar, xo, py, yo, img);
+              const int tap = kb / g.cin_blocks;
+              const int c0 = (kb - tap * g.cin_blocks) * g.bk;
+              const int ky = tap / 3, kx = tap - ky * 3;
+              bcol = tap * g.b_tap + c0;
+              if (g.mode == 1) {
+                tma_load_4d(dst, &tmA, fb, ca + c0, x0 + kx - 1, y0 + ky - 1, img);
+              } else {
+                // input row 2*oy + (ky-1): ky=0 -> (oy-1, odd), ky=1 -> (oy, even), ky=2 -> (oy, odd); same in x.
+                const int py = (ky != 1), px = (kx != 1);
+                const int yo = y0 - (ky == 0), xo = x0 - (kx == 0);
+                tma_load_5d(dst, &tmA, fb, ca + c0 + px * g.ldpar, xo, py, yo, img);
+              }
             }
           }
-          tma_load_2d(sb, &tmB, fb, kb * g.bk, n0);
+          tma_load_2d(sb, &tmB, fb, bcol, n0);
+          if (g.x3) tma_load_2d(sb + g.b_slot, &tmB, fb, bcol + g.lo_b, n0);
           if (++stage == g.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -361,12 +367,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * stage_bytes;
-          const uint32_t sb = sa + kASlot;
+          const uint32_t sb = sa + a_part;
           const uint64_t da = g.desc_hi | uint64_t((sa & 0x3FFFF) >> 4);
           const uint64_t db = g.desc_hi | uint64_t((sb & 0x3FFFF) >> 4);
-          for (int k = 0; k < ksteps; ++k) {
-            // advancing K inside the swizzle span = +32 B on the start address (encoded >> 4)
-            umma_f16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), g.idesc, ((kb - kb0) | k) != 0);
+          if (g.x3) {
+            const uint64_t da_lo = g.desc_hi | uint64_t(((sa + kASlot) & 0x3FFFF) >> 4);
+            const uint64_t db_lo = g.desc_hi | uint64_t(((sb + g.b_slot) & 0x3FFFF) >> 4);
+            for (int k = 0; k < ksteps; ++k) {
+              umma_f16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), g.idesc, ((kb - kb0) | k) != 0);   // hi * hi
+              umma_f16(d_tmem, da + uint64_t(2 * k), db_lo + uint64_t(2 * k), g.idesc, 1u);                   // hi * lo
+              umma_f16(d_tmem, da_lo + uint64_t(2 * k), db + uint64_t(2 * k), g.idesc, 1u);                   // lo * hi
+            }
+          } else {
+            for (int k = 0; k < ksteps; ++k) {
+              // advancing K inside the swizzle span = +32 B on the start address (encoded >> 4)
+              umma_f16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), g.idesc, ((kb - kb0) | k) != 0);
+            }
           }
           umma_commit(bar_empty + 8 * stage);
           if (++stage == g.stages) { stage = 0; phase ^= 1; }
@@ -596,8 +612,8 @@ static int device_setup() {
 //   per k-block  max(MMA issue, smem fill): MMA = bn*bk/32 cycles at ~1.9 GHz; fill = (A + B bytes) / ~70 GB/s per SM
 //   (measured: L2 -> SM delivery tops out near 12 TB/s chip-wide, profiles/r1_gemm_notes.md)
 //   per item     ~2.5 us pipeline fill/drain + epilogue (~0.012 us per output column) + split-K park/reduce.
-static void pick_tiling(int N, int m_tiles, int num_kb, int bk, uint32_t a_bytes, int bn_max, bool allow_split, int* bn_out,
-                        int* ksplit_out) {
+static void pick_tiling(int N, int m_tiles, int num_kb, int bk, uint32_t a_bytes, int bn_max, bool allow_split, bool x3,
+                        int* bn_out, int* ksplit_out) {
   static const int cand[] = {256, 192, 128, 96, 64, 48, 32, 16};
   const int n16 = (N + 15) / 16 * 16;
   double best_cost = -1;
@@ -611,8 +627,10 @@ static void pick_tiling(int N, int m_tiles, int num_kb, int bk, uint32_t a_bytes
     }
     const long n_tiles = (N + c - 1) / c;
     const long tiles = n_tiles * m_tiles;
-    const double t_mma = double(c) * bk / 32.0 / 1900.0;
-    const double t_fill = (double(a_bytes) + double(c) * bk * 2.0) / 70000.0;
+    // fp16x3 operands: three MMAs and two (hi, lo) tile pairs per logical k-block
+    const double t_mma = (x3 ? 3.0 : 1.0) * double(c) * bk / 32.0 / 1900.0;
+    const double t_fill = (x3 ? 2.0 : 1.0) * (double(a_bytes) + double(c) * bk * 2.0) / 70000.0;
+    if (x3 && 2 * (2 * kASlot + 2 * ((c * bk * 2 + 1023) & ~1023)) + 2048 > g_max_smem) continue;   // needs >= 2 stages
     const double t_kb = t_mma > t_fill ? t_mma : t_fill;
     int max_ks = 1;
     if (allow_split && tiles * 2 <= g_num_sms && tiles * 2 <= kMaxCounterTiles) {
@@ -651,7 +669,13 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
   if ((reinterpret_cast<uintptr_t>(d.A) & 15) || (reinterpret_cast<uintptr_t>(d.B) & 15)) return set_error("gemm: operands must be 16-byte aligned");
   static const bool no_halo = getenv("B2P_NO_HALO") != nullptr;
   static const bool no_halo32 = getenv("B2P_NO_HALO32") != nullptr;
-  const bool halo = (d.mode == 1) && !no_halo && (bk == 64 || !no_halo32);
+  const bool halo = (d.mode == 1) && !no_halo && (bk == 64 || !no_halo32) && !d.x3;
+  if (d.x3 && (kred % bk != 0)) return set_error("gemm: fp16x3 operands need K (Cin) to be a multiple of 32");
+  if (d.x3 && d.bf16) return set_error("gemm: fp16x3 operands are fp16");
+  const int xk = d.x3 ? 2 : 1;   // operand rows carry [hi | lo]
+  g.x3 = d.x3 ? 1 : 0;
+  g.lo_a = kred; g.lo_b = kred;
+  g.b_tap = xk * d.Cin;
   g.mode = halo ? 3 : d.mode;
   g.N = d.N;
   g.bk = bk;
@@ -660,6 +684,7 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
   g.out = d.out; g.ldc = d.ldc; g.out_f32 = d.out_f32; g.bias = d.bias; g.res = d.res; g.ldr = d.ldr; g.act = d.act;
   g.split = (d.split_out && !d.out_f32) ? d.N : 0;
   if (g.split && (d.N % 8)) return set_error("gemm: split (fp16x3) output needs N % 8 == 0");
+  if (g.split && d.ldc < 2 * (long long)d.N) return set_error("gemm: split (fp16x3) output rows are [hi(N) | lo(N)]: ldc must be >= 2N");
 
   if (d.mode == 0) {
     g.M = d.M;
@@ -667,9 +692,10 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
     g.num_kb = (d.K + bk - 1) / bk;
     g.m_tiles = (d.M + kTileM - 1) / kTileM;
     g.a_bytes = kTileM * bk * 2;
-    cuuint64_t dims[2] = {cuuint64_t(d.K), cuuint64_t(d.M)};
+    cuuint64_t dims[2] = {cuuint64_t(xk) * cuuint64_t(d.K), cuuint64_t(d.M)};
     cuuint64_t str[1] = {cuuint64_t(d.lda) * 2};
     cuuint32_t box[2] = {cuuint32_t(bk), cuuint32_t(kTileM)};
+    if (d.x3 && d.lda < 2 * (long long)d.K) return set_error("gemm: fp16x3 A rows are [hi(K) | lo(K)]: lda must be >= 2K");
     if (int e = encode(&tmA, d.bf16, 2, d.A, dims, str, box, bk)) return e;
   } else {
     const int s = (d.mode == 2) ? 2 : 1;
@@ -722,14 +748,14 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
       cuuint32_t box[4] = {cuuint32_t(bk), cuuint32_t(btw + 2), cuuint32_t(bth + 2), 1};
       if (int e = encode(&tmA, d.bf16, 4, d.A, dims, str, box, bk)) return e;
     } else if (d.mode == 1) {
-      cuuint64_t dims[4] = {cuuint64_t(d.Cin), cuuint64_t(d.W), cuuint64_t(d.H), cuuint64_t(d.batch)};
+      cuuint64_t dims[4] = {cuuint64_t(xk) * cuuint64_t(d.Cin), cuuint64_t(d.W), cuuint64_t(d.H), cuuint64_t(d.batch)};
       cuuint64_t str[3] = {ld * 2, ld * 2 * d.W, ld * 2 * d.W * d.H};
       cuuint32_t box[4] = {cuuint32_t(bk), cuuint32_t(btw), cuuint32_t(bth), cuuint32_t(g.nb)};
       if (int e = encode(&tmA, d.bf16, 4, d.A, dims, str, box, bk)) return e;
     } else {
       // (x parity, channel) merged in dim0: element (n, 2*yo+py, 2*xo+px, c) at c + px*ld  (+ xo*2ld + py*W*ld + yo*2W*ld)
       g.ldpar = int(d.lda);   // producer adds px * ldA to the channel coordinate
-      cuuint64_t dims[5] = {ld + cuuint64_t(d.Cin), cuuint64_t(d.W / 2), 2, cuuint64_t(d.H / 2), cuuint64_t(d.batch)};
+      cuuint64_t dims[5] = {ld + cuuint64_t(xk) * cuuint64_t(d.Cin), cuuint64_t(d.W / 2), 2, cuuint64_t(d.H / 2), cuuint64_t(d.batch)};
       cuuint64_t str[4] = {ld * 4, ld * 2 * d.W, ld * 4 * d.W, ld * 2 * d.W * d.H};
       cuuint32_t box[5] = {cuuint32_t(bk), cuuint32_t(btw), 1, cuuint32_t(bth), cuuint32_t(g.nb)};
       if (int e = encode(&tmA, d.bf16, 5, d.A, dims, str, box, bk)) return e;
@@ -738,7 +764,7 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
   int bn = 16, ksplit = 1;
   static const bool no_split = getenv("B2P_NO_SPLITK") != nullptr;
   const int slot = no_split ? -1 : ws_slot_for(st);
-  pick_tiling(d.N, g.m_tiles, g.num_kb, halo ? 9 * bk : bk, g.a_bytes, d.bn_max > 0 ? d.bn_max : 256, slot >= 0, &bn, &ksplit);
+  pick_tiling(d.N, g.m_tiles, g.num_kb, halo ? 9 * bk : bk, g.a_bytes, d.bn_max > 0 ? d.bn_max : 256, slot >= 0, d.x3 != 0, &bn, &ksplit);
   g.bn = bn;
   g.ksplit = ksplit;
   g.kb_per = (g.num_kb + ksplit - 1) / ksplit;
@@ -749,12 +775,12 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
   g.b_slot = (g.b_bytes + 1023) & ~1023u;
   g.idesc = make_idesc(bn, d.bf16);
   {
-    cuuint64_t dims[2] = {cuuint64_t(Ktot), cuuint64_t(d.N)};
-    cuuint64_t str[1] = {cuuint64_t(Ktot) * 2};
+    cuuint64_t dims[2] = {cuuint64_t(xk) * cuuint64_t(Ktot), cuuint64_t(d.N)};
+    cuuint64_t str[1] = {cuuint64_t(xk) * cuuint64_t(Ktot) * 2};
     cuuint32_t box[2] = {cuuint32_t(bk), cuuint32_t(bn)};
     if (int e = encode(&tmB, d.bf16, 2, d.B, dims, str, box, bk)) return e;
   }
-  const int stage_bytes = halo ? int(g.b_slot) : kASlot + int(g.b_slot);
+  const int stage_bytes = halo ? int(g.b_slot) : xk * (kASlot + int(g.b_slot));
   g.stagesA = halo ? 2 : 0;
   const int a_region = halo ? g.stagesA * int(g.a_slot) : 0;
   int stages = (g_max_smem - 1024 - 512 - a_region) / stage_bytes;

@@ -171,7 +171,7 @@ __global__ void im2col_u8_kernel(const unsigned char* __restrict__ img, int B, i
     const int ox = int(i % Wo);
     const int oy = int((i / Wo) % Ho);
     const int b = int(i / ((long long)Wo * Ho));
-    __half* o = out + i * (split ? 3 * Kpad : Kpad);
+    __half* o = out + i * (split ? 2 * Kpad : Kpad);
     for (int k0 = 0; k0 < Kpad; k0 += 8) {
       __align__(16) __half v[8];
       __align__(16) __half lo[8];
@@ -190,10 +190,8 @@ __global__ void im2col_u8_kernel(const unsigned char* __restrict__ img, int B, i
         lo[j] = __float2half_rn(f - __half2float(v[j]));
       }
       *reinterpret_cast<uint4*>(o + k0) = *reinterpret_cast<const uint4*>(v);
-      if (split) {   // fp16x3 operand layout [hi | hi | lo], see florence_ops.cu::store_act
-        *reinterpret_cast<uint4*>(o + Kpad + k0) = *reinterpret_cast<const uint4*>(v);
-        *reinterpret_cast<uint4*>(o + 2 * Kpad + k0) = *reinterpret_cast<const uint4*>(lo);
-      }
+      if (split)   // fp16x3 operand layout [hi | lo], see florence_ops.cu::store_act
+        *reinterpret_cast<uint4*>(o + Kpad + k0) = *reinterpret_cast<const uint4*>(lo);
     }
   }
 }

@@ -28,13 +28,13 @@ def _h(t, dev):
 
 
 def _wpack(w2d, dev, x3):
-    """[N, K] fp32 -> fp16 GEMM operand.  x3: [W_hi | W_lo | W_hi] (pairs with activations [A_hi | A_hi | A_lo])."""
+    """[N, K] fp32 -> fp16 GEMM operand.  x3: [W_hi(K) | W_lo(K)] (pairs with activations [A_hi(K) | A_lo(K)])."""
     w2d = w2d.detach().float()
     hi = w2d.half()
     if not x3:
         return hi.contiguous().to(dev)
     lo = (w2d - hi.float()).half()
-    return torch.cat([hi, lo, hi], 1).contiguous().to(dev)
+    return torch.cat([hi, lo], 1).contiguous().to(dev)
 
 
 def _f(t, dev):
@@ -51,8 +51,8 @@ class _Lin:
             b = sd.get(name + ".bias")
         self.w = _wpack(w, dev, x3)
         self.b = _f(b, dev) if b is not None else None
-        self.N, self.K = self.w.shape
-        self.Klog = w.shape[1]
+        self.N = self.w.shape[0]
+        self.K = self.Klog = w.shape[1]          # logical reduction size (the packed row is 2K wide in fp16x3 mode)
 
 
 class _LN:
@@ -80,16 +80,19 @@ class FlorenceWeights:
             w = sd[f"{V}convs.{s}.conv.weight"].float()
             co = w.shape[0]
             m = w.permute(0, 2, 3, 1).reshape(co, -1)   # (ky,kx,c)
+            lin = type("W", (), {})()
             if s == 0:
                 m = torch.cat([m, torch.zeros(co, 160 - m.shape[1])], 1)
                 wp = _wpack(m, dev, x3)
-            else:   # per tap [hi | lo | hi] over the tripled input channels
+                lin.w_col = wp
+            else:
                 t = w.permute(0, 2, 3, 1)                      # [co, 3, 3, ci]
                 hi = t.half()
                 lo = (t - hi.float()).half()
-                wp = (torch.cat([hi, lo, hi], 3) if x3 else hi).reshape(co, -1).contiguous().to(dev)
-            lin = type("W", (), {})()
-            lin.w, lin.b, lin.N, lin.K, lin.Klog = wp, _f(sd[f"{V}convs.{s}.conv.bias"], dev), co, wp.shape[1], m.shape[1]
+                # implicit-GEMM conv: per tap [hi(ci) | lo(ci)]; im2col + GEMM route: [hi: 9*ci | lo: 9*ci]
+                wp = (torch.cat([hi, lo], 3) if x3 else hi).reshape(co, -1).contiguous().to(dev)
+                lin.w_col = _wpack(m, dev, x3)
+            lin.w, lin.b, lin.N, lin.K, lin.Klog = wp, _f(sd[f"{V}convs.{s}.conv.bias"], dev), co, m.shape[1], m.shape[1]
             self.conv_embed.append(lin)
             self.conv_norm.append(_LN(sd, f"{V}convs.{s}.norm", dev))
             stage = []
@@ -160,9 +163,10 @@ class FlorencePlan:
         assert size in (64, 768)
         self.S = size
         self.tag = f"florence{instance}"
+        self.warmed = False
         self.w, self.K, self.dev = w, K, w.device
         self.x3 = w.x3
-        self.KX = 3 if w.x3 else 1
+        self.KX = 2 if w.x3 else 1
         self.T = max_new_tokens
         self.max_len = max_new_tokens + 1
         dev = self.dev
@@ -186,15 +190,15 @@ class FlorencePlan:
 
     # ------------------------------------------------------------------ helpers
     def _e(self, *shape, dt=torch.float32):
-        return torch.empty(shape, dtype=dt, device=self.dev)
+        return torch.zeros(shape, dtype=dt, device=self.dev)   # zeros: recycled allocator blocks may hold NaN patterns
 
     def _act(self, T, C):
-        """fp16 GEMM-operand buffer for T rows of logical width C ([hi | hi | lo] in fp16x3 mode)."""
-        return torch.empty((T, self.KX * C), dtype=torch.float16, device=self.dev)
+        """fp16 GEMM-operand buffer for T rows of logical width C ([hi(C) | lo(C)] in fp16x3 mode)."""
+        return torch.zeros((T, self.KX * C), dtype=torch.float16, device=self.dev)
 
     def _gemm(self, lst, a, lin, out, act=ACT_NONE, res=None, enc=True, split=False):
         M = a.shape[0]
-        assert a.shape[1] == lin.K, (a.shape, lin.K)
+        assert a.shape[1] == self.KX * lin.K, (a.shape, lin.K)
         f = 2 * M * lin.N * lin.Klog
         if enc:
             self.flops_enc += f
@@ -202,7 +206,7 @@ class FlorencePlan:
             self.flops_dec += f
         lst.append(lambda: ops.gemm(a, a.stride(0), lin.w, M, lin.N, lin.K, out, out.stride(0), lin.b, res,
                                     res.stride(0) if res is not None else 0, act, out_f32=(out.dtype == torch.float32),
-                                    split=split))
+                                    split=split, x3=self.x3))
 
     def _ln(self, lst, x, ln, T, C, o16=None, o32=None):
         lst.append(lambda: ops.layernorm(x, ln.g, ln.b, T, C, o16, o32, split=self.x3))
@@ -239,14 +243,14 @@ class FlorencePlan:
                     # 4x4 / 2x2 output maps (64x64-crop mode): a 128-pixel implicit-GEMM tile would be 8x / 32x padding, so
                     # gather the taps explicitly (row copies) and run the dense GEMM on [T, 9*Cs]
                     col = torch.empty((T, 9 * hmap.C), dtype=torch.float16, device=self.dev)
-                    ops_.append(lambda hmap=hmap, col=col: ops.im2col3x3(hmap, 2, col))
+                    ops_.append(lambda hmap=hmap, col=col: ops.im2col3x3(hmap, 2, col, halves=self.KX))
                     xv = xo.buf.view(T, C)
                     lin = type("W", (), {})()
-                    lin.w, lin.b, lin.N, lin.K, lin.Klog = ce.w, ce.b, C, 9 * hmap.C, 9 * Cp
+                    lin.w, lin.b, lin.N, lin.K, lin.Klog = ce.w_col, ce.b, C, 9 * Cp, 9 * Cp
                     self._gemm(ops_, col, lin, xv)
                 else:
                     self.flops_enc += 2 * T * C * 9 * Cp
-                    ops_.append(lambda hmap=hmap, xo=xo, ce=ce: ops.conv3x3(hmap, ce.w, xo, 2, ce.b, None, ACT_NONE, out_f32=True))
+                    ops_.append(lambda hmap=hmap, xo=xo, ce=ce: ops.conv3x3(hmap, ce.w, xo, 2, ce.b, None, ACT_NONE, out_f32=True, x3=x3))
                 x = xo.buf.view(T, C)
             for blk in w.blocks[s]:
                 for kind in ("spatial_block", "channel_block"):
@@ -375,7 +379,7 @@ class FlorencePlan:
             x = self._e(R, D); h = self._act(R, D)
             self._ln(ops_, y, lay["ln3"], R, D, h, x)
         lm = type("W", (), {})()
-        lm.w, lm.b, lm.N, lm.K, lm.Klog = w.E16, None, w.vocab, w.E16.shape[1], D
+        lm.w, lm.b, lm.N, lm.K, lm.Klog = w.E16, None, w.vocab, D, D
         self._gemm(ops_, h, lm, logits, enc=False)
         fb = g.get("forced_bos_token_id")
         fe = g.get("forced_eos_token_id")
@@ -387,13 +391,16 @@ class FlorencePlan:
                     stream=torch.cuda.Stream(device=self.dev), full=ops_ + [lambda: pick(None), lambda: ops.step_advance(step)])
 
     # ------------------------------------------------------------------ running
-    def _run(self, lst, holder, key, tag):
+    def _run(self, lst, holder, key, tag, replay_after_capture=True):
         if not self.use_graph:
             for f in lst:
                 f()
             return
         g = holder[key] if isinstance(holder, dict) else getattr(holder, key)
         if g is None:
+            # first use: one eager pass (lazy one-time setup must not happen inside a capture), capture, and -- unless the
+            # caller keeps the eager results (B2P_EAGER_FIRST, debugging) -- the results come from replaying the graph, so
+            # every real result of the graph path is produced by the same launch mechanism
             for f in lst:
                 f()
             torch.cuda.current_stream().synchronize()
@@ -406,9 +413,32 @@ class FlorencePlan:
                 holder[key] = g
             else:
                 setattr(holder, key, g)
-            return
+            if not replay_after_capture or os.environ.get("B2P_EAGER_FIRST"):
+                return
         g.replay()
         ops.GRAPH_LAUNCHES[0] += len(lst)
+
+    def warm(self):
+        """Build every CUDA graph of this plan on scratch inputs (call with the GPU otherwise idle: see
+        ``PipelinedParser``); real results then only ever come from graph replays."""
+        if not self.use_graph:
+            return
+        self.crops.zero_()
+        self.encode()
+        self.reset_decode(self.K)
+        self.decode_step()
+        self.join()
+        torch.cuda.current_stream().synchronize()
+        self.warmed = True
+
+    def _warm_decode(self):
+        """Capture the decode-step graph(s) on scratch state (one eager step + capture), before any real decoding."""
+        if not self.use_graph or os.environ.get("B2P_EAGER_FIRST") or all(pt["graph"] is not None for pt in self.parts):
+            return
+        self._reset_state(self.K)
+        self.decode_step(_warm=True)
+        self.join()
+        torch.cuda.current_stream().synchronize()
 
     def encode(self, from_resized: bool = False):
         """from_resized: the SxS crops are already in ``crops_in`` (host-side processor did the bicubic resize)."""
@@ -418,6 +448,10 @@ class FlorencePlan:
             self._run(self.enc_ops, self, "g_enc", self.tag)
 
     def reset_decode(self, n_active: int):
+        self._warm_decode()
+        self._reset_state(n_active)
+
+    def _reset_state(self, n_active: int):
         self.seq.zero_()
         self.seq[:, 0] = self.w.gen["decoder_start_token_id"]
         self.finished.zero_()
@@ -436,12 +470,12 @@ class FlorencePlan:
             tot += int(pt["n_unf"].item())
         return tot
 
-    def decode_step(self, dump=None, force_tokens=None):
+    def decode_step(self, dump=None, force_tokens=None, _warm=False):
         """one token for every row; ``force_tokens`` [K] (teacher forcing) overwrites the picked ids."""
         if dump is None and force_tokens is None:
             cur = torch.cuda.current_stream()
             if len(self.parts) == 1:
-                self._run(self.parts[0]["full"], self.parts[0], "graph", self.tag + "_dec0")
+                self._run(self.parts[0]["full"], self.parts[0], "graph", self.tag + "_dec0", replay_after_capture=False)
                 return
             if not self._forked:
                 for pt in self.parts:
@@ -449,7 +483,7 @@ class FlorencePlan:
                 self._forked = True
             for pt in self.parts:
                 with torch.cuda.stream(pt["stream"]):
-                    self._run(pt["full"], pt, "graph", f"{self.tag}_dec{pt['idx']}")
+                    self._run(pt["full"], pt, "graph", f"{self.tag}_dec{pt['idx']}", replay_after_capture=False)
             return
         for pt in self.parts:   # eager path used by the parity tests
             for f in pt["ops"]:

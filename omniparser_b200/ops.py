@@ -28,7 +28,7 @@ def capture_stream(tag, device):
 
 
 GRAPH_LAUNCHES = [0]   # kernels replayed through CUDA graphs (the C-side counter only sees direct launches)
-FLAG_BF16, FLAG_OUT_F32, FLAG_SPLIT = 1, 2, 4
+FLAG_BF16, FLAG_OUT_F32, FLAG_SPLIT, FLAG_X3 = 1, 2, 4, 8
 
 
 def _stream():
@@ -76,8 +76,10 @@ def new_map(B, H, W, Ctot, device, dtype=torch.float16):
 
 
 def gemm(a_ptr, lda, w, M, N, K, out_ptr, ldc, bias=None, res_ptr=None, ldr=0, act=ACT_NONE, out_f32=False,
-         bf16=False, bn_max=0, split=False):
-    flags = (FLAG_BF16 if bf16 else 0) | (FLAG_OUT_F32 if out_f32 else 0) | (FLAG_SPLIT if split else 0) | (bn_max << 8)
+         bf16=False, bn_max=0, split=False, x3=False):
+    """x3: fp16x3 operands -- A rows [hi(K) | lo(K)], w rows [hi(K) | lo(K)], K logical; split: fp16 output as [hi | lo]."""
+    flags = ((FLAG_BF16 if bf16 else 0) | (FLAG_OUT_F32 if out_f32 else 0) | (FLAG_SPLIT if split else 0) |
+             (FLAG_X3 if x3 else 0) | (bn_max << 8))
     _lib.check(_lib.lib().b2p_gemm(_p(a_ptr), lda, _p(w), M, N, K, _p(out_ptr), ldc, _p(bias), _p(res_ptr), ldr, act,
                                    flags, _stream()))
 
@@ -105,9 +107,10 @@ def conv1x1(x: Map, w, out: Map, bias=None, res: Map | None = None, act=ACT_SILU
 
 
 def conv3x3(x: Map, w, out: Map, stride=1, bias=None, res: Map | None = None, act=ACT_SILU, out_f32=False, bn_max=0,
-            split=False):
-    flags = (FLAG_OUT_F32 if out_f32 else 0) | (FLAG_SPLIT if split else 0) | (bn_max << 8)
-    _lib.check(_lib.lib().b2p_conv3x3(_p(x.ptr), x.ld, x.B, x.H, x.W, x.C, stride, _p(w), out.C, _p(out.ptr), out.ld,
+            split=False, x3=False):
+    """x3: fp16x3 operands -- pixels [hi(Cin) | lo(Cin)] (x.C = 2*Cin), w [Cout][9][hi(Cin) | lo(Cin)]."""
+    flags = (FLAG_OUT_F32 if out_f32 else 0) | (FLAG_SPLIT if split else 0) | (FLAG_X3 if x3 else 0) | (bn_max << 8)
+    _lib.check(_lib.lib().b2p_conv3x3(_p(x.ptr), x.ld, x.B, x.H, x.W, x.C // 2 if x3 else x.C, stride, _p(w), out.C, _p(out.ptr), out.ld,
                                       _p(bias), _p(res.ptr if res else None), res.ld if res else 0, act, flags,
                                       _stream()))
 
@@ -125,9 +128,10 @@ def upsample2x(x: Map, y: Map):
     _lib.check(_lib.lib().b2p_upsample2x(_p(x.ptr), x.ld, x.B, x.H, x.W, x.C, _p(y.ptr), y.ld, _stream()))
 
 
-def im2col3x3(x: Map, stride, out):
-    """out [B*Ho*Wo, 9*C] f16 (tap-major) for a 3x3 / pad 1 conv over the NHWC map ``x``."""
-    _lib.check(_lib.lib().b2p_im2col3x3(_p(x.ptr), x.ld, x.B, x.H, x.W, x.C, stride, _p(out), _stream()))
+def im2col3x3(x: Map, stride, out, halves=1):
+    """out [B*Ho*Wo, 9*x.C] f16 (tap-major) for a 3x3 / pad 1 conv over the NHWC map ``x``; halves=2: fp16x3 pixels
+    [hi(C) | lo(C)] (x.C = 2C) -> rows [hi: 9C | lo: 9C]."""
+    _lib.check(_lib.lib().b2p_im2col3x3(_p(x.ptr), x.ld, x.B, x.H, x.W, x.C // halves, stride, halves, _p(out), _stream()))
 
 
 def cbfuse(srcs: list[Map], last: Map, out: Map):
@@ -176,9 +180,9 @@ def crop_resize(imgs, img_hw, img_off, boxes, box_img, n_box, out_hw, out, statu
 
 
 # ------------------------------------------------------------------------------------------ Florence-2 ops
-# `split=True` writes fp16 activations in the fp16x3 operand layout [hi | hi | lo] (row stride 3*C).
+# `split=True` writes fp16 activations in the fp16x3 operand layout [hi(C) | lo(C)] (row stride 2*C).
 def layernorm(x, gamma, beta, T, C, out16=None, out32=None, eps=1e-5, split=False):
-    _lib.check(_lib.lib().b2p_layernorm(_p(x), C, _p(gamma), _p(beta), eps, T, C, _p(out16), 3 * C if split else C,
+    _lib.check(_lib.lib().b2p_layernorm(_p(x), C, _p(gamma), _p(beta), eps, T, C, _p(out16), 2 * C if split else C,
                                         _p(out32), C, int(split), _stream()))
 
 

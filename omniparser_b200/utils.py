@@ -179,6 +179,10 @@ class PipelinedParser:
         with torch.cuda.stream(self.s_det):
             if resident_src is not None:
                 io_["src"].copy_(resident_src, non_blocking=True)
+            elif torch.is_tensor(images) and images.is_pinned():
+                # caller-owned page-locked [B,H,W,3] u8 batch: DMA straight from it (it must stay untouched until the
+                # batch's result has been yielded); pageable numpy screenshots go through the slot's pinned staging copy
+                io_["src"].copy_(images, non_blocking=True)
             else:
                 for i, im in enumerate(images):
                     io_["host"][i].copy_(torch.from_numpy(np.ascontiguousarray(im)))
@@ -262,7 +266,8 @@ class PipelinedParser:
 
     @torch.inference_mode()
     def run(self, batches, resident=None):
-        """batches: iterable of (images, ocr); resident: optional parallel iterable of device u8 tensors [B,H,W,3].
+        """batches: iterable of (images, ocr), images a list of same-size u8 HWC numpy arrays or one page-locked u8 torch
+        tensor [B,H,W,3]; resident: optional parallel iterable of device u8 tensors [B,H,W,3] (skips the H2D copy).
         Stages in flight: detect(i+1) on stream A (submit thread) | host list logic of batch i (this thread) |
         caption(i-1), caption(i-2) on their lane's stream (caption threads).  lanes + 2 io slots keep a batch's resident
         screenshots alive until its crops have been cut.  Results come out in order, ``lanes`` batches behind the glue."""
@@ -283,6 +288,18 @@ class PipelinedParser:
                     slot = (slot + 1) % (self.lanes + 2)
                     fut = self._pool.submit(self._submit, slot, nxt[0], next(rit) if rit is not None else None)
                 g = self._glue(h, cur[1])
+                n = len(g["crop_boxes"])
+                cap_model = self.cmp["model"]
+                if n and not cap_model.plan_ready(n, self.T, self.prompt, instance=g["lane"]):
+                    # first batch of this crop-count bucket on this lane: drain the pipeline and build + capture the
+                    # plan with the GPU idle (buffers and graphs are created once; steady state never comes here)
+                    for p in pending:
+                        p.result()
+                    if fut is not None:
+                        fut.result()
+                    torch.cuda.synchronize()
+                    cap_model.warm_plan(n, self.T, self.prompt, instance=g["lane"], stream=self.s_caps[g["lane"]])
+                    torch.cuda.synchronize()
                 pending.append(self._cap_pool.submit(self._caption, g))
                 if len(pending) > self.lanes:
                     yield pending.popleft().result()

@@ -198,6 +198,12 @@ def test_im2col3x3_exact(B, H, W, C, stride):
     xp = torch.nn.functional.pad(x.cpu().float(), (0, 0, 1, 1, 1, 1))
     ref = torch.stack([xp[:, ky:ky + (Ho - 1) * stride + 1:stride, kx:kx + (Wo - 1) * stride + 1:stride] for ky in range(3) for kx in range(3)], 3)
     assert torch.equal(out.cpu().float(), ref.reshape(B * Ho * Wo, 9 * C))
+    if C % 16 == 0:   # fp16x3 pixels [hi(C/2) | lo(C/2)] -> rows [hi: 9*C/2 | lo: 9*C/2]
+        ops.im2col3x3(ops.Map(x, 0, C), stride, out, halves=2)
+        torch.cuda.synchronize()
+        h = C // 2
+        ref2 = torch.cat([ref[..., :h].reshape(B * Ho * Wo, 9 * h), ref[..., h:].reshape(B * Ho * Wo, 9 * h)], 1)
+        assert torch.equal(out.cpu().float(), ref2)
 
 
 @pytest.mark.parametrize("filt", [0, 1])
@@ -271,21 +277,49 @@ def test_im2col_stem():
         assert got[:, k * k * 3:].abs().max().item() == 0
 
 
-@pytest.mark.parametrize("M,N,K", [(416, 3072, 768), (300, 256, 2048), (1000, 128, 64)])
-def test_gemm_fp16x3_layout(M, N, K):
-    """fp16x3 precision mode: A = [hi | hi | lo], W = [hi | lo | hi] (K-concatenated) gives near-fp32 products, and the
-    split epilogue writes the next operand in the same layout (covers the split-K path for the small-M cases)."""
+def _hilo(t):
+    hi = t.half()
+    return hi, (t - hi.float()).half()
+
+
+@pytest.mark.parametrize("M,N,K", [(416, 3072, 768), (300, 256, 2048), (1000, 128, 64), (416, 768, 3072), (6656, 512, 160), (128, 51290, 768)])
+def test_gemm_fp16x3_operands(M, N, K):
+    """fp16x3 precision mode: A = [hi(K) | lo(K)], W = [hi(K) | lo(K)]; the kernel loads every half once per k-block and
+    issues hi*hi + hi*lo + lo*hi -> near-fp32 products; the split epilogue writes the next operand in the same layout
+    (small-M cases run the split-K path)."""
     g = torch.Generator(device="cpu").manual_seed(M + N + K)
     a = torch.randn(M, K, generator=g)
     w = torch.randn(N, K, generator=g) / K ** 0.5
-    a_hi, w_hi = a.half(), w.half()
-    a3 = torch.cat([a_hi, a_hi, (a - a_hi.float()).half()], 1).to(DEV)
-    w3 = torch.cat([w_hi, (w - w_hi.float()).half(), w_hi], 1).contiguous().to(DEV)
+    a2 = torch.cat(_hilo(a), 1).to(DEV)
+    w2 = torch.cat(_hilo(w), 1).contiguous().to(DEV)
     bias = torch.randn(N, generator=g).to(DEV)
-    out = torch.empty(M, 3 * N, dtype=torch.float16, device=DEV)
-    ops.gemm(a3, 3 * K, w3, M, N, 3 * K, out, 3 * N, bias, None, 0, ops.ACT_GELU, split=True)
-    torch.cuda.synchronize()
     ref = F.gelu(a.double() @ w.double().t() + bias.cpu().double())
-    got = (out[:, :N].float() + out[:, 2 * N:].float()).cpu().double()
-    assert torch.equal(out[:, :N], out[:, N:2 * N])
-    assert (got - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+    tol = 2e-5 * max(1.0, ref.abs().max().item())
+    if N % 8 == 0:
+        out = torch.empty(M, 2 * N, dtype=torch.float16, device=DEV)
+        ops.gemm(a2, 2 * K, w2, M, N, K, out, 2 * N, bias, None, 0, ops.ACT_GELU, split=True, x3=True)
+        torch.cuda.synchronize()
+        got = (out[:, :N].float() + out[:, N:].float()).cpu().double()
+        assert (got - ref).abs().max().item() < tol
+    res = torch.randn(M, N, generator=g).to(DEV)
+    o32 = torch.empty(M, N, dtype=torch.float32, device=DEV)
+    ops.gemm(a2, 2 * K, w2, M, N, K, o32, N, bias, res, N, ops.ACT_GELU, out_f32=True, x3=True)
+    torch.cuda.synchronize()
+    assert (o32.cpu().double() - (ref + res.cpu().double())).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("B,H,W,Ci,Co", [(3, 16, 16, 128, 256), (2, 24, 24, 64, 96), (5, 8, 8, 256, 512)])
+def test_conv3x3_s2_fp16x3_operands(B, H, W, Ci, Co):
+    """stride-2 implicit-GEMM conv with [hi(Ci) | lo(Ci)] pixels and [Co][9][hi | lo] weights vs fp64 conv2d."""
+    g = torch.Generator(device="cpu").manual_seed(B * H + Ci + Co)
+    x = torch.randn(B, H, W, Ci, generator=g)
+    w = torch.randn(Co, Ci, 3, 3, generator=g) / (9 * Ci) ** 0.5
+    bias = torch.randn(Co, generator=g)
+    xm = ops.Map(torch.cat(_hilo(x), 3).contiguous().to(DEV), 0, 2 * Ci)
+    wt = w.permute(0, 2, 3, 1)
+    wp = torch.cat(_hilo(wt), 3).reshape(Co, -1).contiguous().to(DEV)
+    out = ops.new_map(B, H // 2, W // 2, Co, DEV, torch.float32)
+    ops.conv3x3(xm, wp, out, 2, bias.to(DEV), None, ops.ACT_NONE, out_f32=True, x3=True)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), bias.double(), stride=2, padding=1).permute(0, 2, 3, 1)
+    assert (out.buf.cpu().double() - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())

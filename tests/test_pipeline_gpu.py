@@ -100,17 +100,19 @@ def test_get_som_labeled_img_api():
     assert texts2 == [e["content"] for e in elems if e["source"] == "box_yolo_content_yolo"]
 
 
-def test_pipelined_parser_equals_sequential():
-    """The 2-deep pipeline (detect of batch i+1 overlapping glue + caption of batch i, two streams) returns exactly what
-    the one-batch-at-a-time path returns."""
+@pytest.mark.parametrize("lanes", [1, 2])
+def test_pipelined_parser_equals_sequential(lanes):
+    """The pipelined schedule (detect of batch i+1 | host list logic of batch i | `lanes` caption batches in flight, each
+    on its own stream and plan instance) returns exactly what the one-batch-at-a-time path returns, including the first
+    batches (whose plans are built on the fly)."""
     from omniparser_b200.utils import PipelinedParser
     det, cmp_ = ge.standin_models(DEV)
     batches = []
-    for b in range(4):
+    for b in range(6):
         seeds = [40 + 2 * b, 41 + 2 * b]
         batches.append(([synth.screenshot(s) for s in seeds], [synth.ocr_boxes(s) for s in seeds]))
     ref = [parse_screenshots(imgs, det, cmp_, ocr, BOX_TRESHOLD=0.05, iou_threshold=0.7, max_new_tokens=8) for imgs, ocr in batches]
-    pp = PipelinedParser(det, cmp_, BOX_TRESHOLD=0.05, iou_threshold=0.7, max_new_tokens=8)
+    pp = PipelinedParser(det, cmp_, BOX_TRESHOLD=0.05, iou_threshold=0.7, max_new_tokens=8, caption_lanes=lanes)
     for rep in range(2):
         got = list(pp.run(iter(batches)))
         assert len(got) == len(ref)
