@@ -339,7 +339,37 @@ __global__ void mha_kernel(MhaArgs a) {
   }
   float m = -INFINITY, l = 0.f;
   float2 acc = make_float2(0.f, 0.f);
-  for (int j = 0; j < Lk; ++j) {
+  int j = 0;
+  // four keys per iteration: 8 independent row loads in flight and four interleaved butterfly reductions (the one-key loop
+  // below is a ~700-cycle dependent chain per key: at L = 13 the whole kernel was load-latency bound)
+  for (; j + 4 <= Lk; j += 4) {
+    float2 kf[4], vf[4];
+    float s[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      kf[u] = *reinterpret_cast<const float2*>(kb + (long long)(j + u) * ldk + 2 * lane);
+      vf[u] = *reinterpret_cast<const float2*>(vb + (long long)(j + u) * ldk + 2 * lane);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) s[u] = q.x * kf[u].x + q.y * kf[u].y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+    }
+    const float mn = fmaxf(fmaxf(m, fmaxf(s[0], s[1])), fmaxf(s[2], s[3]));
+    const float r = __expf(m - mn);
+    l *= r; acc.x *= r; acc.y *= r;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float p = __expf(s[u] - mn);
+      l += p;
+      acc.x += p * vf[u].x;
+      acc.y += p * vf[u].y;
+    }
+    m = mn;
+  }
+  for (; j < Lk; ++j) {
     const float2 kf = *reinterpret_cast<const float2*>(kb + j * ldk + 2 * lane);
     const float s = warp_sum(q.x * kf.x + q.y * kf.y);
     const float mn = fmaxf(m, s);
@@ -638,7 +668,10 @@ int b2p_window_attn(const float* qkv, const float* qkv_bias, int B, int H, int W
     attr = true;
   }
   if (smem > 64 * 1024) return set_error("window_attn: window too large");
-  launch_pdl(window_attn_kernel<32>, dim3(B * nw * heads), dim3(160), smem, st, qkv, qkv_bias, B, H, W, C, heads, win, (__half*)out, split ? C : 0);
+  // one thread per query of the window: small maps (4x4, 8x8 in the 64x64-crop mode) get small CTAs so more of them fit per SM
+  const int nq = (W < win ? W : win) * (H < win ? H : win);
+  const int threads = nq >= 160 ? 160 : ((nq + 31) / 32) * 32;
+  launch_pdl(window_attn_kernel<32>, dim3(B * nw * heads), dim3(threads), smem, st, qkv, qkv_bias, B, H, W, C, heads, win, (__half*)out, split ? C : 0);
   B2P_CHECK_LAUNCH();
   return 0;
 }

@@ -51,6 +51,7 @@ struct GemmArgs {
   // fp16x3 operands: A rows are [hi(K) | lo(K)] (conv: per pixel [hi(Cin) | lo(Cin)]), W rows [hi | lo] likewise.  Each
   // pipeline stage holds A_hi, A_lo, B_hi, B_lo of ONE logical k-block (each loaded once) and the MMA warp issues the
   // three products hi*hi + hi*lo + lo*hi into the same fp32 accumulator.
+  int mt_fast;   // tile order: 1 = M tiles fastest (concurrent CTAs share a B tile: weights larger than activations, e.g. the LM head)
   int x3, lo_a, lo_b, b_tap;   // lo_a / lo_b: column offset of the lo half in A / B; b_tap: B columns per conv tap
   float* ws;   // split-K partial tiles [tile][slice][128][bn] fp32
   int* counters;   // split-K {arrived, finished} counters per output tile (self-resetting)
@@ -256,8 +257,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         const int ks = item % g.ksplit;
         const int tile = item / g.ksplit;
-        const int nt = tile % g.n_tiles;
-        const int mt = tile / g.n_tiles;
+        const int nt = g.mt_fast ? tile / g.m_tiles : tile % g.n_tiles;
+        const int mt = g.mt_fast ? tile % g.m_tiles : tile / g.n_tiles;
         const int n0 = nt * g.bn;
         int img = 0, y0 = 0, x0 = 0;
         if (g.mode != 0) {
@@ -406,8 +407,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int ks = item % g.ksplit;
       const int tile = item / g.ksplit;
-      const int nt = tile % g.n_tiles;
-      const int mt = tile / g.n_tiles;
+      const int nt = g.mt_fast ? tile / g.m_tiles : tile % g.n_tiles;
+      const int mt = g.mt_fast ? tile % g.m_tiles : tile / g.n_tiles;
       const int n0 = nt * g.bn;
       const int r = grp * 32 + lane;
       long long pix;
@@ -771,6 +772,8 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
   g.ws = slot >= 0 ? g_ws[slot] : nullptr;
   g.counters = slot >= 0 ? g_counters[slot] : nullptr;
   g.n_tiles = (d.N + bn - 1) / bn;
+  // co-scheduled CTAs should share the LARGER operand through L2: weights bigger than activations -> M tiles fastest
+  g.mt_fast = (d.mode == 0 && g.m_tiles > 1 && (long long)d.N > (long long)d.M) ? 1 : 0;
   g.b_bytes = uint32_t(bn) * bk * 2;
   g.b_slot = (g.b_bytes + 1023) & ~1023u;
   g.idesc = make_idesc(bn, d.bf16);
@@ -799,9 +802,9 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
   if (grid <= 0) return 0;
   static const bool dbg = getenv("B2P_DEBUG") != nullptr;
   if (dbg)
-    fprintf(stderr, "b2p_gemm mode=%d M=%d N=%d Ktot=%d bk=%d bn=%d tw=%d th=%d m_tiles=%d n_tiles=%d stages=%d grid=%d act=%d f32=%d res=%d ksplit=%d\n",
+    fprintf(stderr, "b2p_gemm mode=%d M=%d N=%d Ktot=%d bk=%d bn=%d tw=%d th=%d m_tiles=%d n_tiles=%d stages=%d grid=%d act=%d f32=%d res=%d ksplit=%d x3=%d\n",
             g.mode, d.mode == 0 ? d.M : g.m_tiles * 128, d.N, Ktot, bk, bn, g.tw, g.th, g.m_tiles, g.n_tiles, stages, grid,
-            d.act, d.out_f32, d.res != nullptr, ksplit);
+            d.act, d.out_f32, d.res != nullptr, ksplit, g.x3);
   static const bool no_pdl = getenv("B2P_NO_PDL") != nullptr;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);

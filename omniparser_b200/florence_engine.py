@@ -178,7 +178,9 @@ class FlorencePlan:
         self.L = self.n_img + self.n_prompt
         self.seq = torch.zeros((K, self.max_len + 1), dtype=torch.int32, device=dev)
         self.finished = torch.zeros((K,), dtype=torch.int32, device=dev)
-        self.logits = torch.empty((K, w.vocab), dtype=torch.float32, device=dev)
+        # row pitch padded to 8 floats so the LM-head epilogue takes the 16-byte vector store path (51290 is not)
+        self._logits_buf = torch.zeros((K, (w.vocab + 7) // 8 * 8), dtype=torch.float32, device=dev)
+        self.logits = self._logits_buf[:, :w.vocab]
         self.enc_ops, self.dec_ops = [], []
         self.flops_enc = 0   # logical (useful) FLOPs; the fp16x3 mode executes 3x this on the tensor cores
         self.flops_dec = 0

@@ -116,9 +116,14 @@ def test_pipelined_parser_equals_sequential(lanes):
     for rep in range(2):
         got = list(pp.run(iter(batches)))
         assert len(got) == len(ref)
-        for gb, rb in zip(got, ref):
-            for (ge_, gi), (re_, ri) in zip(gb, rb):
-                assert ge_ == re_ and torch.equal(gi, ri)
+        for bi, (gb, rb) in enumerate(zip(got, ref)):
+            for si, ((ge_, gi), (re_, ri)) in enumerate(zip(gb, rb)):
+                same_boxes = [e["bbox"] for e in ge_] == [e["bbox"] for e in re_]
+                assert same_boxes, f"rep {rep} batch {bi} shot {si}: element boxes differ"
+                assert gi.shape == ri.shape and torch.equal(gi, ri), (
+                    f"rep {rep} batch {bi} (lane {bi % lanes}) shot {si}: caption ids differ in "
+                    f"{int((gi != ri).any(1).sum()) if gi.shape == ri.shape else -1} of {ri.shape[0]} rows")
+                assert ge_ == re_
 
 
 def test_edge_cases_no_boxes_and_no_ocr():

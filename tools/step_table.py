@@ -23,10 +23,10 @@ gem = [us(r) for r in data if 'gemm_tcgen05' in r[ki]]
 assert len(gem) == len(shapes), (len(gem), len(shapes))
 agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
 for t, s in zip(gem, shapes):
-    key = (s['mode'], s['M'], s['N'], s['Ktot'], s['bn'], s.get('ksplit', 1), s['m_tiles'] * s['n_tiles'], s['stages'], s['act'], s['f32'], s['res'])
-    a = agg[key]; a[0] += 1; a[1] += t; a[2] += 2.0 * s['M'] * s['N'] * s['Ktot']
-print("mode      M     N   Ktot  bn ks tiles st act f32 res |   n   us_tot  us_each TFLOP/s(exec) %gemm")
+    key = (s['mode'], s['M'], s['N'], s['Ktot'], s['bn'], s.get('ksplit', 1), s['m_tiles'] * s['n_tiles'], s['stages'], s['act'], s['f32'], s['res'], s.get('x3', 0))
+    a = agg[key]; a[0] += 1; a[1] += t; a[2] += 2.0 * s['M'] * s['N'] * s['Ktot'] * (3 if s.get('x3', 0) else 1)
+print("mode      M     N   Ktot  bn ks tiles st act f32 res x3 |   n   us_tot  us_each TFLOP/s(exec) %gemm")
 G = sum(gem)
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 for key, (n, t, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
-    print("%4d %7d %5d %6d %3d %2d %5d %2d %3d %3d %3d | %3d %8.1f %8.1f %8.1f %6.1f" % (*key, n, t, t / n, fl / t / 1e6, 100 * t / G))
+    print("%4d %7d %5d %6d %3d %2d %5d %2d %3d %3d %3d %2d | %3d %8.1f %8.1f %8.1f %6.1f" % (*key, n, t, t / n, fl / t / 1e6, 100 * t / G))
