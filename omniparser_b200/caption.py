@@ -3,7 +3,8 @@
 
 Contract kept: ``model.config.model_type`` / ``model.config.name_or_path`` (contains 'florence'),
 ``model.device``, ``model.generate(input_ids=, pixel_values=, max_new_tokens=20, num_beams=1, do_sample=False)`` ->
-``LongTensor[K, T]``; ``processor(images=, text=, return_tensors="pt"[, do_resize=False])`` -> object with
+``LongTensor[K, T]``; ``processor(images=, text=, return_tensors="pt"[, do_resize=False])`` (HF default True: 768x768
+bicubic crops, the reference's CPU branch) -> object with
 ``.to(device=, dtype=)`` and keys ``input_ids`` / ``pixel_values``; ``processor.batch_decode(ids,
 skip_special_tokens=True)``.
 
