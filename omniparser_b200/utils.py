@@ -292,7 +292,7 @@ class PipelinedParser:
         caption(i-1), caption(i-2) on their lane's stream (caption threads).  lanes + 2 io slots keep a batch's resident
         screenshots alive until its crops have been cut.  Results come out in order, ``lanes`` batches behind the glue."""
         from collections import deque
-        with torch.cuda.device(self.model.device):
+        with self._device_ctx():
             it = iter(batches)
             rit = iter(resident) if resident is not None else None
             cur = next(it, None)
@@ -308,18 +308,7 @@ class PipelinedParser:
                     slot = (slot + 1) % (self.lanes + 2)
                     fut = self._pool.submit(self._submit, slot, nxt[0], next(rit) if rit is not None else None)
                 g = self._glue(h, cur[1])
-                n = len(g["crop_boxes"])
-                cap_model = self.cmp["model"]
-                if n and not cap_model.plan_ready(n, self.T, self.prompt, instance=g["lane"]):
-                    # first batch of this crop-count bucket on this lane: drain the pipeline and build + capture the
-                    # plan with the GPU idle (buffers and graphs are created once; steady state never comes here)
-                    for p in pending:
-                        p.result()
-                    if fut is not None:
-                        fut.result()
-                    torch.cuda.synchronize()
-                    cap_model.warm_plan(n, self.T, self.prompt, instance=g["lane"], stream=self.s_caps[g["lane"]])
-                    torch.cuda.synchronize()
+                self._ensure_plan(g, pending, fut)
                 pending.append(self._cap_pools[g["lane"]].submit(self._caption, g))
                 if len(pending) > self.lanes:
                     yield pending.popleft().result()
@@ -327,6 +316,24 @@ class PipelinedParser:
                 cur, h = nxt, hn
             while pending:
                 yield pending.popleft().result()
+
+    def _device_ctx(self):
+        return torch.cuda.device(self.model.device)
+
+    def _ensure_plan(self, g, pending, fut):
+        """First batch of a crop-count bucket on a lane: drain the pipeline and build + capture the caption plan with
+        the GPU idle (buffers and graphs are created once; steady state never comes here)."""
+        n = len(g["crop_boxes"])
+        cap_model = self.cmp["model"]
+        if not n or cap_model.plan_ready(n, self.T, self.prompt, instance=g["lane"]):
+            return
+        for p in pending:
+            p.result()
+        if fut is not None:
+            fut.result()
+        torch.cuda.synchronize()
+        cap_model.warm_plan(n, self.T, self.prompt, instance=g["lane"], stream=self.s_caps[g["lane"]])
+        torch.cuda.synchronize()
 
 
 # ------------------------------------------------------------------------------------------------ reference API

@@ -1,0 +1,76 @@
+"""Host-side schedule of ``PipelinedParser.run`` (no GPU): stages are stubbed with sleeps that record what overlaps.
+
+Invariants (the second one was violated by a shared caption thread pool: batch i+2 could start on lane 0 while batch i
+was still decoding there, corrupting the lane's plan state):
+  * results come back in order, one per batch;
+  * two batches of the same caption lane are never in flight together, while different lanes do overlap;
+  * a batch's io slot is not handed to a later detection before the batch's caption stage has finished.
+"""
+import contextlib
+import random
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import pytest
+
+from omniparser_b200.utils import PipelinedParser
+
+
+class _Sched(PipelinedParser):
+    def __init__(self, lanes, seed):   # no CUDA objects: only what run() itself touches
+        self.lanes = lanes
+        self._pool = ThreadPoolExecutor(max_workers=1)
+        self._cap_pools = [ThreadPoolExecutor(max_workers=1) for _ in range(lanes)]
+        self._job = 0
+        self.rng = random.Random(seed)
+        self.lock = threading.Lock()
+        self.active_lanes, self.busy_slots = {}, {}
+        self.max_parallel, self.errors = 0, []
+
+    def _device_ctx(self):
+        return contextlib.nullcontext()
+
+    def _ensure_plan(self, g, pending, fut):
+        pass
+
+    def _submit(self, slot, images, resident_src=None):
+        with self.lock:
+            if slot in self.busy_slots:
+                self.errors.append(f"slot {slot} reused while batch {self.busy_slots[slot]} still owns it")
+            self.busy_slots[slot] = images
+        time.sleep(self.rng.uniform(0.0, 0.004))
+        return dict(slot=slot, batch=images)
+
+    def _glue(self, h, ocr):
+        time.sleep(self.rng.uniform(0.0, 0.003))
+        lane = self._job % self.lanes
+        self._job += 1
+        return dict(h=h, lane=lane, crop_boxes=[0])
+
+    def _caption(self, g):
+        lane, batch = g["lane"], g["h"]["batch"]
+        with self.lock:
+            if lane in self.active_lanes:
+                self.errors.append(f"lane {lane}: batch {batch} started while batch {self.active_lanes[lane]} was in flight")
+            self.active_lanes[lane] = batch
+            self.max_parallel = max(self.max_parallel, len(self.active_lanes))
+        time.sleep(self.rng.choice([0.001, 0.004, 0.012]))   # uneven durations: the case that used to interleave
+        with self.lock:
+            del self.active_lanes[lane]
+            del self.busy_slots[g["h"]["slot"]]
+        return batch
+
+
+@pytest.mark.parametrize("lanes", [1, 2, 3])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_schedule_invariants(lanes, seed):
+    s = _Sched(lanes, seed)
+    n = 40
+    out = list(s.run((i, None) for i in range(n)))
+    assert out == list(range(n))
+    assert not s.errors, s.errors[:3]
+    if lanes > 1:
+        assert s.max_parallel > 1, "caption lanes never overlapped"
+    assert list(s.run(iter(()))) == []
+    assert list(s.run([(7, None)])) == [7]
