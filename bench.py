@@ -286,6 +286,11 @@ def run_b200(args):
         return float(t.item()), wall, launches, clk, tms, dict(stats)
 
     if not args.no_pipeline:
+        # every (crop-count bucket, lane) plan is built before anything is timed, whatever --steps / --warmup are
+        counts = []
+        for i in range(N_SETS):
+            counts.append(step(i, True)["n_crops"])
+        pp.prewarm(counts)
         run_steps(max(args.warmup, N_SETS, args.caption_lanes + 4), True)   # warm the pipelined path (second io slot, stream-local scratch)
         run_steps(2, False)
         torch.cuda.synchronize()

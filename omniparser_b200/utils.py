@@ -292,6 +292,7 @@ class PipelinedParser:
         caption(i-1), caption(i-2) on their lane's stream (caption threads).  lanes + 2 io slots keep a batch's resident
         screenshots alive until its crops have been cut.  Results come out in order, ``lanes`` batches behind the glue."""
         from collections import deque
+        self._job = 0   # lane assignment is a function of the position in THIS run (batch i -> lane i % lanes)
         with self._device_ctx():
             it = iter(batches)
             rit = iter(resident) if resident is not None else None
@@ -319,6 +320,18 @@ class PipelinedParser:
 
     def _device_ctx(self):
         return torch.cuda.device(self.model.device)
+
+    def prewarm(self, crop_counts):
+        """Build + capture the caption plans of every lane for the given per-batch crop counts up front (each distinct
+        32-crop bucket costs a plan per lane), so that no batch of a later run() pays for it."""
+        cap_model = self.cmp["model"]
+        with self._device_ctx():
+            torch.cuda.synchronize()
+            for n in crop_counts:
+                for lane in range(self.lanes):
+                    if n and not cap_model.plan_ready(n, self.T, self.prompt, instance=lane):
+                        cap_model.warm_plan(n, self.T, self.prompt, instance=lane, stream=self.s_caps[lane])
+            torch.cuda.synchronize()
 
     def _ensure_plan(self, g, pending, fut):
         """First batch of a crop-count bucket on a lane: drain the pipeline and build + capture the caption plan with
