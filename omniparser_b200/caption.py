@@ -130,6 +130,7 @@ class B200Florence2Model:
         p = self._plans.get((K, max_new_tokens, tuple(prompt_ids), size, instance))
         return p is not None and (p.warmed or not p.use_graph)
 
+    @torch.inference_mode()
     def warm_plan(self, n: int, max_new_tokens: int, prompt_ids: Sequence[int], size: int = 64, instance: int = 0, stream=None):
         """Construct the plan for this crop-count bucket and capture its graphs on scratch inputs."""
         with torch.cuda.device(self.device), torch.cuda.stream(stream if stream is not None else torch.cuda.current_stream()):

@@ -321,6 +321,7 @@ class PipelinedParser:
     def _device_ctx(self):
         return torch.cuda.device(self.model.device)
 
+    @torch.inference_mode()
     def prewarm(self, crop_counts):
         """Build + capture the caption plans of every lane for the given per-batch crop counts up front (each distinct
         32-crop bucket costs a plan per lane), so that no batch of a later run() pays for it."""
