@@ -349,6 +349,41 @@ def run_b200(args):
         verify = {"pipelined_vs_sequential_caption_rows": rows, "mismatched_rows": bad}
         log(f"verify: {verify}")
 
+    # per-stage tensor-core figures of the caption path (F1/F3 encode, F4 decode step), CUDA events over
+    # graph replays of the lane-0 plan; informative only -- a failure here never costs the bench line
+    caption_stages = None
+    try:
+        with torch.inference_mode():
+            n_c = counts[0] if not args.no_pipeline else max(1, st["crops"] // max(args.steps, 1))   # a bucket that exists
+            cplan = cmp_["model"].plan_for(n_c, args.max_new_tokens, pp.prompt)
+            if cplan.use_graph and cplan.warmed or cplan.g_enc is not None:
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                cplan.encode(); torch.cuda.synchronize()
+                ev[0].record()
+                for _ in range(5):
+                    cplan.encode()
+                ev[1].record()
+                cplan.reset_decode(n_c)
+                cplan.decode_step(); torch.cuda.synchronize()
+                nd = max(1, args.max_new_tokens - 1)
+                ev[2].record()
+                for _ in range(nd):
+                    cplan.decode_step()
+                ev[3].record()
+                cplan.join(); torch.cuda.synchronize()
+                enc_ms, dec_ms = ev[0].elapsed_time(ev[1]) / 5, ev[2].elapsed_time(ev[3]) / nd
+                xk = 3 if cplan.x3 else 1
+                caption_stages = {
+                    "rows": cplan.K, "precision": "fp16x3" if cplan.x3 else "fp16",
+                    "encode": {"ms": enc_ms, "logical_tflops": cplan.flops_enc / enc_ms / 1e9, "executed_tflops": xk * cplan.flops_enc / enc_ms / 1e9,
+                               "executed_frac_of_peak": xk * cplan.flops_enc / enc_ms / 1e9 / peak_tf},
+                    "decode_step": {"ms": dec_ms, "logical_tflops": cplan.flops_dec / dec_ms / 1e9, "executed_tflops": xk * cplan.flops_dec / dec_ms / 1e9,
+                                    "executed_frac_of_peak": xk * cplan.flops_dec / dec_ms / 1e9 / peak_tf,
+                                    "note": "~70 launches per step at M = rows: launch/latency bound, see profiles/r1_gemm_notes.md"}}
+                log(f"caption stages: encode {enc_ms:.2f} ms, decode step {dec_ms:.3f} ms")
+    except Exception as exc:   # noqa: BLE001
+        caption_stages = {"error": repr(exc)[:200]}
+
     if rank == 0:
         line = {"metric": "screenshots/sec", "value": value, "unit": "screenshots/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -362,7 +397,7 @@ def run_b200(args):
                              "traffic_note": "DRAM bytes per forward from the committed ncu launch list (caches flushed per kernel), not from this run",
                              "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})", "forward_ms": fwd_ms,
                              "algorithmic_gflop_per_forward": plan.flops / 1e9},
-                "verify": verify, "p50_latency_ms_batch1": lat[len(lat) // 2],
+                "verify": verify, "caption_stages": caption_stages, "p50_latency_ms_batch1": lat[len(lat) // 2],
                 "stage_ms_per_step": {k: 1e3 * float(np.mean([t[k] for t in tms2])) for k in ("detect_s", "glue_s", "caption_s")},
                 "boxes_per_screenshot": st["boxes"] / max(st["n"], 1), "crops_per_screenshot": st["crops"] / max(st["n"], 1)}
         if world == 1 and not args.no_cpu_baseline:
