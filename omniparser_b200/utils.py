@@ -170,7 +170,6 @@ class PipelinedParser:
         # never be in flight together (a shared pool lets batch i+2 start on lane 0 while batch i still decodes there)
         self._cap_pools = [ThreadPoolExecutor(max_workers=1, thread_name_prefix=f"b2p-caption{i}") for i in range(self.lanes)]
         self._tm_lock = threading.Lock()
-        self._dbg_lock = threading.Lock()
         self._job = 0
 
     @torch.inference_mode()
@@ -253,22 +252,6 @@ class PipelinedParser:
                 status = torch.empty((n,), dtype=torch.int32, device=dev)
                 ops.crop_resize(io_["src"], meta["hw"], meta["off"], d_boxes, d_bimg, n, 64, plan.crops, status)
                 ids = cap_model.generate_from_device_crops(plan, n).cpu()
-                if os.environ.get("B2P_PIPE_DEBUG") and lane > 0:
-                    # debugging aid: same crops through the lane-0 plan instance, stage-by-stage comparison
-                    with self._dbg_lock:
-                        torch.cuda.synchronize()
-                        p0 = cap_model.plan_for(n, self.T, self.prompt, instance=0)
-                        crops = plan.crops.clone()
-                        p0.crops.copy_(crops)
-                        ids0 = cap_model.generate_from_device_crops(p0, n).cpu()
-                        plan.crops.copy_(crops)
-                        ids1 = cap_model.generate_from_device_crops(plan, n).cpu()
-                        torch.cuda.synchronize()
-                        d_img = (plan.img_feat - p0.img_feat).abs().max().item()
-                        d_enc = (plan.enc_out32 - p0.enc_out32).abs().max().item()
-                        print(f"[pipe-debug] lane {lane} n={n}: ids==ids0 {torch.equal(ids, ids0)}  ids1(rerun)==ids0 {torch.equal(ids1, ids0)}  "
-                              f"ids1==ids {torch.equal(ids1, ids)}  |img_feat diff| {d_img:.3e}  |enc_out diff| {d_enc:.3e}  "
-                              f"crops sum {int(crops[:n].long().sum())}", flush=True)
         t3 = time.perf_counter()
         texts_all = [t.strip() for t in processor.batch_decode(ids, skip_special_tokens=True)] if ids is not None else []
         out, k = [], 0
