@@ -115,21 +115,26 @@ def remove_overlap_fast(boxes: List[dict], iou_threshold: float, ocr_bbox: List[
             ocr_in_icon = io / oarea[None, :] > 0.80       # is_inside(ocr, icon)
             icon_in_ocr = io / area[:, None] > 0.80        # is_inside(icon, ocr)
     removed = [False] * m
+    if m:
+        # the reference walks the OCR boxes in order and breaks at the first one that contains the icon without being
+        # inside it (:296-298); labels are collected from the OCR boxes inside the icon BEFORE that point
+        stopm = ~ocr_in_icon & icon_in_ocr
+        kstop = np.where(stopm.any(1), stopm.argmax(1), m)                       # [n]
+        lab = ocr_in_icon & (np.arange(m)[None, :] < kstop[:, None])             # [n, m]
+        dropped_v = (kstop < m).tolist()
+        has_lab = lab.any(1).tolist()
+    valid_l = valid.tolist()
     for i in range(n):
-        if not valid[i]:
+        if not valid_l[i]:
             continue
-        labels, dropped = "", False
+        labels = ""
         if m:
-            a, c = ocr_in_icon[i], icon_in_ocr[i]
-            stop = np.flatnonzero(~a & c)
-            kstop = int(stop[0]) if stop.size else m
-            dropped = kstop < m
-            for k in np.flatnonzero(a[:kstop]):
-                labels += ocr_bbox[k]["content"] + " "
-                if not removed[k]:
+            if has_lab[i]:
+                for k in np.flatnonzero(lab[i]).tolist():
+                    labels += ocr_bbox[k]["content"] + " "
                     removed[k] = True
-        if dropped:
-            continue
+            if dropped_v[i]:
+                continue
         filtered.append({"type": "icon", "bbox": boxes[i]["bbox"], "interactivity": True, "content": labels or None,
                          "source": "box_yolo_content_ocr" if labels else "box_yolo_content_yolo"})
     if m and any(removed):
