@@ -192,7 +192,7 @@ def _config(args, per_gpu_batch):
             "l2": f"inputs rotate over {N_SETS} distinct batches ({N_SETS * per_gpu_batch * W * H * 3 / 1e6:.0f} MB/GPU) > 126 MB L2",
             "parallelism": f"dp{args.gpus} (screenshots sharded, one NCCL gather of results per step)",
             "schedule": "one batch at a time" if getattr(args, "no_pipeline", False) else
-                        f"pipeline across steps: detect(i+1) on stream A | host list logic(i) | {args.caption_lanes} caption lanes (batches i-1.. on own streams/plans); fill and drain are inside the timed region"}
+                        f"pipeline across steps: detect(i+1) on stream A | host list logic(i) | {args.caption_lanes} caption lanes (batches i-1.. on own streams/plans), caption group {args.caption_group}; fill and drain are inside the timed region"}
 
 
 # ------------------------------------------------------------------------------------------------ this repo
@@ -241,7 +241,7 @@ def run_b200(args):
 
     from omniparser_b200.utils import PipelinedParser
     pp = PipelinedParser(model, cmp_, BOX_TRESHOLD=args.box_threshold, iou_threshold=0.7, max_new_tokens=args.max_new_tokens,
-                         caption_lanes=args.caption_lanes)
+                         caption_lanes=args.caption_lanes, caption_group=args.caption_group)
 
     def run_steps(n_steps, resident):
         if args.no_pipeline:
@@ -290,7 +290,8 @@ def run_b200(args):
         counts = []
         for i in range(N_SETS):
             counts.append(step(i, True)["n_crops"])
-        pp.prewarm(counts)
+        G = max(1, args.caption_group)   # grouped captioning: every run of up to G consecutive batches can form a group
+        pp.prewarm(sorted({sum(counts[(s0 + j) % N_SETS] for j in range(r)) for s0 in range(N_SETS) for r in range(1, G + 1)}))
         run_steps(max(args.warmup, N_SETS, args.caption_lanes + 4), True)   # warm the pipelined path (second io slot, stream-local scratch)
         run_steps(2, False)
         torch.cuda.synchronize()
@@ -434,6 +435,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--caption-lanes", type=int, default=2, help="caption batches in flight (own stream + plan each)")
+    ap.add_argument("--caption-group", type=int, default=1,
+                    help="opt-in: caption the crops of this many consecutive steps in one Florence-2 pass (PipelinedParser caption_group)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="screenshots per GPU per step")

@@ -142,6 +142,16 @@ def parse_screenshots(images: Sequence[np.ndarray], model: B200YOLOv9Detector, c
     return out
 
 
+class _Member:
+    """Result handle of one batch inside a grouped caption job."""
+
+    def __init__(self, fut, idx):
+        self.fut, self.idx = fut, idx
+
+    def result(self):
+        return self.fut.result()[self.idx]
+
+
 class PipelinedParser:
     """Three-stage software pipeline over batches of same-size screenshots: detection of batch i+1 (stream A), the host
     list logic of batch i and the captioning of batch i-1 (stream B) run concurrently.  Same results as :func:`parse_screenshots`, batch by
@@ -153,7 +163,11 @@ class PipelinedParser:
     """
 
     def __init__(self, model: B200YOLOv9Detector, caption_model_processor: dict, BOX_TRESHOLD=0.01, iou_threshold=0.9,
-                 imgsz=640, max_new_tokens=20, prompt_ids: Sequence[int] = CAPTION_PROMPT_IDS, caption_lanes: int = 2):
+                 imgsz=640, max_new_tokens=20, prompt_ids: Sequence[int] = CAPTION_PROMPT_IDS, caption_lanes: int = 2,
+                 caption_group: int = 1):
+        """caption_group > 1 (opt-in): the crops of ``caption_group`` consecutive batches are captioned in ONE Florence-2
+        pass (the decode steps are latency-bound at a few hundred rows, so their cost per screenshot falls with the row
+        count); results are identical, a batch's result is delayed until its group has been captioned."""
         self.model, self.cmp = model, caption_model_processor
         self.conf, self.iou_thr, self.imgsz, self.T, self.prompt = BOX_TRESHOLD, iou_threshold, imgsz, max_new_tokens, list(prompt_ids)
         dev = model.device
@@ -171,6 +185,7 @@ class PipelinedParser:
         self._cap_pools = [ThreadPoolExecutor(max_workers=1, thread_name_prefix=f"b2p-caption{i}") for i in range(self.lanes)]
         self._tm_lock = threading.Lock()
         self._job = 0
+        self.group = max(1, int(caption_group))
 
     @torch.inference_mode()
     def _submit(self, slot: int, images, resident_src=None):
@@ -221,7 +236,7 @@ class PipelinedParser:
         tm = self.timings
         tm["detect_wait_s"] += t1 - t0; tm["glue_s"] += t2 - t1
         tm["n_boxes"] += sum(counts); tm["n_crops"] += len(crop_boxes); tm["batches"] += 1
-        lane = self._job % self.lanes
+        lane = (self._job // self.group) % self.lanes   # the batches of one caption group share a lane
         self._job += 1
         return dict(h=h, all_elems=all_elems, crop_boxes=crop_boxes, crop_img=crop_img, lane=lane)
 
@@ -264,6 +279,62 @@ class PipelinedParser:
             self.timings["caption_s"] += t3 - t2
         return out
 
+    @torch.inference_mode()
+    def _caption_group(self, gs):
+        """caption_group > 1: one Florence-2 pass over the crops of several batches (same lane); returns the per-batch
+        results in order.  Row blocks of ``plan.crops`` are filled batch by batch from each batch's resident screenshots."""
+        torch.cuda.set_device(self.model.device)
+        model, cap_model, processor = self.model, self.cmp["model"], self.cmp["processor"]
+        lane = gs[0]["lane"]
+        counts = [len(g["crop_boxes"]) for g in gs]
+        n = sum(counts)
+        t2 = time.perf_counter()
+        ids = None
+        if n:
+            dev = model.device
+            with torch.cuda.stream(self.s_caps[lane]):
+                plan = cap_model.plan_for(n, self.T, self.prompt, instance=lane)
+                off = 0
+                for g, ng in zip(gs, counts):
+                    if not ng:
+                        continue
+                    io_, B, H, W = g["h"]["io"], g["h"]["B"], g["h"]["H"], g["h"]["W"]
+                    d_boxes = torch.tensor(g["crop_boxes"], dtype=torch.float32).to(dev, non_blocking=True)
+                    d_bimg = torch.tensor(g["crop_img"], dtype=torch.int32).to(dev, non_blocking=True)
+                    key = ("crop_meta", B, H, W, lane)
+                    meta = model._io.get(key)
+                    if meta is None:
+                        meta = dict(hw=torch.tensor([[H, W]] * B, dtype=torch.int32, device=dev),
+                                    off=torch.tensor([i * H * W * 3 for i in range(B)], dtype=torch.int64, device=dev))
+                        model._io[key] = meta
+                    status = torch.empty((ng,), dtype=torch.int32, device=dev)
+                    ops.crop_resize(io_["src"], meta["hw"], meta["off"], d_boxes, d_bimg, ng, 64, plan.crops[off:], status)
+                    off += ng
+                ids = cap_model.generate_from_device_crops(plan, n).cpu()
+        t3 = time.perf_counter()
+        outs, off = [], 0
+        for g, ng in zip(gs, counts):
+            all_elems, B = g["all_elems"], g["h"]["B"]
+            ids_b = None
+            if ng:
+                ids_b = ids[off:off + ng]
+                # HF would have stopped this batch alone at the first step where all ITS rows had finished
+                done_at = cap_model._first_all_finished(ids_b) if ids_b.shape[1] > 2 else None
+                if done_at is not None:
+                    ids_b = ids_b[:, :done_at + 1]
+                off += ng
+            texts_all = [t.strip() for t in processor.batch_decode(ids_b, skip_special_tokens=True)] if ids_b is not None else []
+            out, k = [], 0
+            for i in range(B):
+                mcap = sum(1 for e in all_elems[i] if e["content"] is None)
+                host_glue.fill_captions(all_elems[i], texts_all[k:k + mcap])
+                out.append((all_elems[i], ids_b[k:k + mcap] if ids_b is not None else torch.zeros((0, 1), dtype=torch.long)))
+                k += mcap
+            outs.append(out)
+        with self._tm_lock:
+            self.timings["caption_s"] += t3 - t2
+        return outs
+
     def _finish(self, h, ocr):
         return self._caption(self._glue(h, ocr))
 
@@ -272,7 +343,7 @@ class PipelinedParser:
         """batches: iterable of (images, ocr), images a list of same-size u8 HWC numpy arrays or one page-locked u8 torch
         tensor [B,H,W,3]; resident: optional parallel iterable of device u8 tensors [B,H,W,3] (skips the H2D copy).
         Stages in flight: detect(i+1) on stream A (submit thread) | host list logic of batch i (this thread) |
-        caption(i-1), caption(i-2) on their lane's stream (caption threads).  lanes + 2 io slots keep a batch's resident
+        caption(i-1), caption(i-2) on their lane's stream (caption threads).  lanes + 2 io slots (more with caption_group) keep a batch's resident
         screenshots alive until its crops have been cut.  Results come out in order, ``lanes`` batches behind the glue."""
         from collections import deque
         self._job = 0   # lane assignment is a function of the position in THIS run (batch i -> lane i % lanes)
@@ -285,16 +356,27 @@ class PipelinedParser:
             slot = 0
             h = self._submit(slot, cur[0], next(rit) if rit is not None else None)
             pending = deque()
+            grp = []
             while cur is not None:
                 nxt = next(it, None)
                 fut = None
                 if nxt is not None:
-                    slot = (slot + 1) % (self.lanes + 2)
+                    # slots alive at once: lanes*group in caption + up to group-1 glued batches waiting for their group
+                    # + the batch in the host list logic + the batch in detection  (= lanes + 2 when group == 1)
+                    slot = (slot + 1) % (self.lanes * self.group + self.group + 1)
                     fut = self._pool.submit(self._submit, slot, nxt[0], next(rit) if rit is not None else None)
                 g = self._glue(h, cur[1])
-                self._ensure_plan(g, pending, fut)
-                pending.append(self._cap_pools[g["lane"]].submit(self._caption, g))
-                if len(pending) > self.lanes:
+                if self.group == 1:
+                    self._ensure_plan(g, pending, fut)
+                    pending.append(self._cap_pools[g["lane"]].submit(self._caption, g))
+                else:
+                    grp.append(g)
+                    if len(grp) == self.group or nxt is None:
+                        self._ensure_plan(dict(crop_boxes=[b for x in grp for b in x["crop_boxes"]], lane=grp[0]["lane"]), pending, fut)
+                        fc = self._cap_pools[grp[0]["lane"]].submit(self._caption_group, grp)
+                        pending.extend(_Member(fc, j) for j in range(len(grp)))
+                        grp = []
+                while len(pending) > self.lanes * self.group:
                     yield pending.popleft().result()
                 hn = fut.result() if fut is not None else None
                 cur, h = nxt, hn
