@@ -27,6 +27,11 @@ typedef struct CUstream_st* b2p_stream_t; /* == cudaStream_t */
 const char* b2p_last_error(void);
 long long b2p_launch_count(void); /* kernels launched by this library since load (bench.py gpu_launches) */
 int b2p_abi_version(void);
+/* Debugging aid, not on the hot path: with B2P_TRACE=1 in the environment every GEMM/conv launch runs an instrumented
+ * instantiation of the kernel that leaves globaltimer stamps per CTA; this returns the launches recorded since the
+ * last call: stamps [n][160][16] (ns; slots: entry, prologue, dependency wait, first TMA, first full stage, first
+ * accumulator issued, first epilogue start, last epilogue end, exit), meta [n][8] = {mode, M, N, K, bn, ksplit, x3, grid}. */
+int b2p_trace_read(unsigned long long* stamps, int* meta, int max_launches);
 
 /* ---- dense contractions (tcgen05 + TMA + TMEM), ref:util/yolov9.py:120-121 and ref:util/utils.py:125 ----
  * flags: bit0 operands bf16 (else fp16) | bit1 output fp32 (else fp16) | bit2 fp16 output in the "fp16x3" operand

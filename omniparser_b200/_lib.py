@@ -22,6 +22,7 @@ vp, i32, i64, f32, f64 = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_doubl
 PROTOTYPES = {
     "b2p_last_error": (C.c_char_p, []),
     "b2p_launch_count": (i64, []),
+    "b2p_trace_read": (i32, [vp, vp, i32]),
     "b2p_abi_version": (i32, []),
     "b2p_gemm": (i32, [vp, i64, vp, i32, i32, i32, vp, i64, vp, vp, i64, i32, i32, vp]),
     "b2p_conv3x3": (i32, [vp, i64, i32, i32, i32, i32, i32, vp, i32, vp, i64, vp, vp, i64, i32, i32, vp]),

@@ -38,6 +38,7 @@ struct ConvGemm {
 };
 
 int gemm_launch(const ConvGemm& d, cudaStream_t st);
+int trace_read(unsigned long long* stamps, int* meta, int max_launches);   // B2P_TRACE=1 debugging aid
 
 // Programmatic dependent launch for the small SIMT kernels: launched with the stream-serialization attribute they may
 // be scheduled while the preceding (persistent, early-triggering) GEMM drains; each such kernel calls pdl_wait() before

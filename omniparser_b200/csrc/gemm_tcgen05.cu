@@ -55,6 +55,7 @@ struct GemmArgs {
   int x3, lo_a, lo_b, b_tap;   // lo_a / lo_b: column offset of the lo half in A / B; b_tap: B columns per conv tap
   float* ws;   // split-K partial tiles [tile][slice][128][bn] fp32
   int* counters;   // split-K {arrived, finished} counters per output tile (self-resetting)
+  unsigned long long* trace;   // B2P_TRACE build of the kernel only: [CTA][16] globaltimer stamps (see trace_stamp)
 };
 
 // Shared-memory matrix descriptor (PTX ISA "tcgen05 matrix descriptor"), K-major operand, swizzled:
@@ -192,8 +193,19 @@ __device__ __forceinline__ void epi_store16(const GemmArgs& g, const EpiCtx& e, 
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+// Phase stamps of the traced instantiation (B2P_TRACE=1, tools/trace_gemm.py): where a launch's microseconds go.
+enum { kTrEntry = 0, kTrPrologue, kTrDepWait, kTrFirstTma, kTrFirstFull, kTrFirstAccDone, kTrFirstEpiStart, kTrLastEpiEnd, kTrExit };
+template <bool kTrace>
+__device__ __forceinline__ void trace_stamp(const GemmArgs& g, int slot) {
+  if constexpr (kTrace) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g.trace[blockIdx.x * 16 + slot] = t;
+  }
+}
+
+template <bool kTrace>
+__device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t a_part = g.x3 ? 2u * kASlot : uint32_t(kASlot);                     // [A_hi][A_lo] | [A]
@@ -215,6 +227,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // the stream may start launching right away; its CTAs run their prologue on SMs as they free up and then block in
   // griddepcontrol.wait until this grid has completed and flushed.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (threadIdx.x == 0) trace_stamp<kTrace>(g, kTrEntry);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -243,8 +256,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) trace_stamp<kTrace>(g, kTrPrologue);
   // everything above touched only this CTA's shared/tensor memory; global reads/writes start below
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (threadIdx.x == 0) trace_stamp<kTrace>(g, kTrDepWait);
 
   const int total_items = g.m_tiles * g.n_tiles * g.ksplit;   // item = (mt * n_tiles + nt) * ksplit + ks
   const uint32_t smem_base = smem_u32(smem);
@@ -278,6 +293,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t fa = bar_afull + 8 * stageA;
             mbar_expect_tx(fa, g.a_bytes);
             tma_load_4d(smem_base + stageA * g.a_slot, &tmA, fa, cb * g.bk, x0 - 1, y0 - 1, img);
+            if constexpr (kTrace) { if (item == blockIdx.x && cb == kb0) trace_stamp<kTrace>(g, kTrFirstTma); }
             if (++stageA == g.stagesA) { stageA = 0; phaseA ^= 1; }
             for (int tap = 0; tap < 9; ++tap) {
               mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -318,6 +334,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           tma_load_2d(sb, &tmB, fb, bcol, n0);
           if (g.x3) tma_load_2d(sb + g.b_slot, &tmB, fb, bcol + g.lo_b, n0);
+          if constexpr (kTrace) { if (item == blockIdx.x && kb == kb0) trace_stamp<kTrace>(g, kTrFirstTma); }
           if (++stage == g.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -343,6 +360,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int tap = 0; tap < 9; ++tap) {
               mbar_wait(bar_full + 8 * stage, phase);
               tc_fence_after();
+              if constexpr (kTrace) { if (item == blockIdx.x && cb == kb0 && tap == 0) trace_stamp<kTrace>(g, kTrFirstFull); }
               const int ky = tap / 3, kx = tap - ky * 3;
               const uint32_t sa = sa0 + uint32_t(ky * g.tw + kx) * uint32_t(2 * g.bk);   // shifted view of the halo tile
               const uint32_t sb = smem_base + a_region + stage * stage_bytes;
@@ -360,6 +378,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (++stageA == g.stagesA) { stageA = 0; phaseA ^= 1; }
           }
           umma_commit(bar_tfull + 8 * acc);
+          if constexpr (kTrace) { if (item == blockIdx.x) trace_stamp<kTrace>(g, kTrFirstAccDone); }
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
           continue;
@@ -367,6 +386,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
+          if constexpr (kTrace) { if (item == blockIdx.x && kb == kb0) trace_stamp<kTrace>(g, kTrFirstFull); }
           const uint32_t sa = smem_base + stage * stage_bytes;
           const uint32_t sb = sa + a_part;
           const uint64_t da = g.desc_hi | uint64_t((sa & 0x3FFFF) >> 4);
@@ -389,6 +409,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (++stage == g.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(bar_tfull + 8 * acc);
+        if constexpr (kTrace) { if (item == blockIdx.x) trace_stamp<kTrace>(g, kTrFirstAccDone); }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -432,6 +453,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
+      if constexpr (kTrace) { if (item == blockIdx.x && threadIdx.x == 64) trace_stamp<kTrace>(g, kTrFirstEpiStart); }
       const uint32_t t_row = tmem_base + (uint32_t(grp * 32) << 16) + uint32_t(acc * 256);
       if (g.ksplit == 1) {
         for (int c = cq * 16; c < g.bn; c += 64) {
@@ -524,6 +546,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if constexpr (kTrace) { if (threadIdx.x == 64) trace_stamp<kTrace>(g, kTrLastEpiEnd); }
   }
 
   tc_fence_before();
@@ -532,6 +555,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
+  if (threadIdx.x == 0) trace_stamp<kTrace>(g, kTrExit);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+  gemm_body<false>(tmA, tmB, g);
+}
+
+// Same kernel with globaltimer stamps at the phase boundaries (selected by B2P_TRACE=1; never used otherwise).
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel_trace(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+  gemm_body<true>(tmA, tmB, g);
 }
 
 // ------------------------------------------------------------------------------------------- host side
@@ -589,6 +624,14 @@ static constexpr int kMaxCounterTiles = 1 << 12;   // split-K only ever covers <
 
 static int g_max_smem = 0;
 
+// B2P_TRACE=1 (debugging aid, tools/trace_gemm.py): launches go through gemm_tcgen05_kernel_trace and leave per-CTA
+// globaltimer stamps; b2p_trace_read() hands them out together with the launch shapes.
+static constexpr int kTraceCap = 1024, kTraceCtas = 160, kTraceSlots = 16;
+static unsigned long long* g_trace = nullptr;
+static int g_trace_n = 0;
+static int g_trace_meta[kTraceCap][8];
+static std::mutex g_trace_mu;
+
 static int device_setup() {
   if (g_num_sms) return 0;
   int dev = 0;
@@ -600,6 +643,12 @@ static int device_setup() {
   g_max_smem = int(p.sharedMemPerBlockOptin);
   if (cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem) != cudaSuccess)
     return set_error("cudaFuncSetAttribute(max dynamic smem) failed");
+  if (getenv("B2P_TRACE")) {
+    if (cudaFuncSetAttribute(gemm_tcgen05_kernel_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem) != cudaSuccess ||
+        cudaMalloc(&g_trace, sizeof(unsigned long long) * kTraceCap * kTraceCtas * kTraceSlots) != cudaSuccess)
+      return set_error("B2P_TRACE: setup of the traced kernel failed");
+    cudaMemset(g_trace, 0, sizeof(unsigned long long) * kTraceCap * kTraceCtas * kTraceSlots);
+  }
   for (int i = 0; i < kWsSlots; ++i) {
     if (cudaMalloc(&g_ws[i], kWsBytes) != cudaSuccess || cudaMalloc(&g_counters[i], 2 * kMaxCounterTiles * sizeof(int)) != cudaSuccess)
       return set_error("cudaMalloc for the split-K workspace failed");
@@ -816,11 +865,40 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = no_pdl ? 0 : 1;
-  cudaError_t ce = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel, tmA, tmB, g);
+  bool traced = false;
+  if (g_trace && grid <= kTraceCtas) {
+    std::lock_guard<std::mutex> lk(g_trace_mu);
+    if (g_trace_n < kTraceCap) {
+      const int m[8] = {g.mode, d.mode == 0 ? d.M : g.m_tiles * 128, d.N, Ktot, bn, ksplit, g.x3, grid};
+      for (int i = 0; i < 8; ++i) g_trace_meta[g_trace_n][i] = m[i];
+      g.trace = g_trace + size_t(g_trace_n) * kTraceCtas * kTraceSlots;
+      ++g_trace_n;
+      traced = true;
+    }
+  }
+  cudaError_t ce = traced ? cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel_trace, tmA, tmB, g)
+                          : cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel, tmA, tmB, g);
   if (ce == cudaSuccess) ce = cudaGetLastError();
   if (ce != cudaSuccess) return set_error(cudaGetErrorString(ce));
   count_launch();
   return 0;
+}
+
+// -> number of traced launches since the last call; stamps [n][kTraceCtas = 160][16] (ns, 0 = not written), meta [n][8] =
+// {mode, M, N, K, bn, ksplit, x3, grid}.  Synchronises the device.
+int trace_read(unsigned long long* stamps, int* meta, int max_launches) {
+  if (!g_trace) return set_error("tracing is off (set B2P_TRACE=1 before the first GEMM launch)");
+  cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lk(g_trace_mu);
+  const int n = g_trace_n < max_launches ? g_trace_n : max_launches;
+  const size_t per = size_t(kTraceCtas) * kTraceSlots;
+  if (n > 0 && cudaMemcpy(stamps, g_trace, sizeof(unsigned long long) * per * n, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return set_error("trace_read: copy failed");
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < 8; ++j) meta[i * 8 + j] = g_trace_meta[i][j];
+  cudaMemset(g_trace, 0, sizeof(unsigned long long) * per * kTraceCap);
+  g_trace_n = 0;
+  return n;
 }
 
 }  // namespace b2p
