@@ -292,7 +292,7 @@ def run_b200(args):
             counts.append(step(i, True)["n_crops"])
         G = max(1, args.caption_group)   # grouped captioning: every run of up to G consecutive batches can form a group
         pp.prewarm(sorted({sum(counts[(s0 + j) % N_SETS] for j in range(r)) for s0 in range(N_SETS) for r in range(1, G + 1)}))
-        run_steps(max(args.warmup, N_SETS, args.caption_lanes + 4), True)   # warm the pipelined path (second io slot, stream-local scratch)
+        run_steps(max(args.warmup, N_SETS, args.caption_lanes + 4, args.caption_lanes * G + G + 2), True)   # warm the pipelined path (every io slot, stream-local scratch)
         run_steps(2, False)
         torch.cuda.synchronize()
         log("pipelined warm-up done")
