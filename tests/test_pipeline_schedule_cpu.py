@@ -90,3 +90,36 @@ def test_schedule_invariants(lanes, seed, group):
         assert s.max_parallel > 1, "caption lanes never overlapped"
     assert list(s.run(iter(()))) == []
     assert list(s.run([(7, None)])) == [7]
+
+
+def test_group_trim_matches_per_batch_stop():
+    """Grouped captioning generates until EVERY row of the group has finished; a batch captioned alone would have stopped
+    at the first step where all of ITS rows had finished (HF semantics), so its slice is trimmed there."""
+    import torch
+    from omniparser_b200.caption import B200Florence2Model
+    m = object.__new__(B200Florence2Model)
+    m.gen = dict(eos_token_id=2, pad_token_id=1)
+    g = torch.Generator().manual_seed(0)
+    for _ in range(50):
+        T = 9
+        rows = []
+        for _r in range(7):
+            L = int(torch.randint(2, T + 3, (1,), generator=g))          # eos position (may be beyond T: unfinished)
+            body = torch.randint(5, 100, (T,), generator=g)
+            row = torch.cat([torch.tensor([2]), body])                    # decoder start, then tokens
+            if L <= T:
+                row[L] = 2
+                row[L + 1:] = 1
+            rows.append(row)
+        seq = torch.stack(rows)
+        # what the group pass returns: truncated where ALL rows are done
+        d_all = m._first_all_finished(seq)
+        grp = seq[:, :d_all + 1] if d_all is not None else seq
+        for sl in (slice(0, 3), slice(3, 7)):
+            alone = seq[sl]
+            d = m._first_all_finished(alone)
+            alone = alone[:, :d + 1] if d is not None else alone
+            part = grp[sl]
+            dp = m._first_all_finished(part)
+            part = part[:, :dp + 1] if dp is not None else part
+            assert torch.equal(part, alone)
