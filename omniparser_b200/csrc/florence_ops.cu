@@ -386,78 +386,6 @@ __global__ void mha_kernel(MhaArgs a) {
   store_act(orow, h * 64 + 2 * lane + 1, a.split, acc.y * inv);
 }
 
-// Small-L variant (64x64-crop mode: L = 13 encoder tokens, <= 21 decoder positions): one THREAD per (batch, head,
-// query) with q and the output accumulator in registers; K/V rows are read as float4 (the queries of one (b, h) share
-// them through L1).  Replaces 5 warp shuffles per key of mha_kernel with straight FMAs.
-__global__ void __launch_bounds__(128) mha_small_kernel(MhaArgs a) {
-  pdl_wait();
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int total = a.B * a.heads * a.Lq;
-  if (tid >= total) return;
-  const int qi = tid % a.Lq;
-  const int h = (tid / a.Lq) % a.heads;
-  const int b = tid / (a.Lq * a.heads);
-  const int HD = a.heads * 64;
-  float4 q[16], acc[16];
-  const float4* qp = reinterpret_cast<const float4*>(a.q + ((long long)b * a.Lq + qi) * a.ldq + h * 64);
-#pragma unroll
-  for (int d = 0; d < 16; ++d) {
-    q[d] = qp[d];
-    q[d].x *= 0.125f; q[d].y *= 0.125f; q[d].z *= 0.125f; q[d].w *= 0.125f;
-    acc[d] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  int Lk = a.Lk;
-  const float *kb, *vb;
-  long long ldk;
-  if (a.kcache) {
-    const int t = *a.step;
-    const float4* kn = reinterpret_cast<const float4*>(a.knew + (long long)b * a.ldnew + h * 64);
-    const float4* vn = reinterpret_cast<const float4*>(a.vnew + (long long)b * a.ldnew + h * 64);
-    float4* kc = reinterpret_cast<float4*>(a.kcache + ((long long)b * a.tmax + t) * HD + h * 64);
-    float4* vc = reinterpret_cast<float4*>(a.vcache + ((long long)b * a.tmax + t) * HD + h * 64);
-#pragma unroll
-    for (int d = 0; d < 16; ++d) { kc[d] = kn[d]; vc[d] = vn[d]; }
-    Lk = t + 1;
-    kb = a.kcache + (long long)b * a.tmax * HD + h * 64;
-    vb = a.vcache + (long long)b * a.tmax * HD + h * 64;
-    ldk = HD;
-  } else {
-    kb = a.k + (long long)b * a.Lk * a.ldk + h * 64;
-    vb = a.v + (long long)b * a.Lk * a.ldk + h * 64;
-    ldk = a.ldk;
-  }
-  float m = -INFINITY, l = 0.f;
-  for (int j = 0; j < Lk; ++j) {
-    const float4* kr = reinterpret_cast<const float4*>(kb + j * ldk);
-    float s = 0.f;
-#pragma unroll
-    for (int d = 0; d < 16; ++d) {
-      const float4 kk = kr[d];
-      s += (q[d].x * kk.x + q[d].y * kk.y) + (q[d].z * kk.z + q[d].w * kk.w);
-    }
-    if (s > m) {
-      const float r = __expf(m - s);
-      l *= r;
-#pragma unroll
-      for (int d = 0; d < 16; ++d) { acc[d].x *= r; acc[d].y *= r; acc[d].z *= r; acc[d].w *= r; }
-      m = s;
-    }
-    const float p = __expf(s - m);
-    l += p;
-    const float4* vr = reinterpret_cast<const float4*>(vb + j * ldk);
-#pragma unroll
-    for (int d = 0; d < 16; ++d) {
-      const float4 vv = vr[d];
-      acc[d].x += p * vv.x; acc[d].y += p * vv.y; acc[d].z += p * vv.z; acc[d].w += p * vv.w;
-    }
-  }
-  const float inv = 1.f / l;
-  __half* orow = a.out + ((long long)b * a.Lq + qi) * a.ldo;
-#pragma unroll
-  for (int d = 0; d < 16; ++d)
-    store_act4(orow, h * 64 + 4 * d, a.split, make_float4(acc[d].x * inv, acc[d].y * inv, acc[d].z * inv, acc[d].w * inv));
-}
-
 // ---------------------------------------------------------------------------------------- embeddings
 // Encoder input: row (b, i) = (i < n_img ? image_feat[b][i] : E[prompt[i - n_img]]) + P[i + 2]
 // (hf:models/florence2/modeling_florence2.py:742-761; learned positions with offset 2, hf:models/bart/
@@ -690,8 +618,8 @@ int b2p_mha(const float* q, long long ldq, const float* k, const float* v, long 
   a.q = q; a.ldq = ldq; a.k = k; a.v = v; a.ldk = ldk;
   a.B = B; a.Lq = Lq; a.Lk = Lk; a.heads = heads; a.out = (__half*)out; a.ldo = ldo; a.split = split ? heads * 64 : 0;
   const int total = B * heads * Lq;
-  // mha_small_kernel (thread per query) measured 2.3x SLOWER than the warp-per-query kernel here (its per-thread 256-B
-  // rows are uncoalesced: profiles/r1_step_table_v3.txt); kept for reference, not dispatched.
+  // (a thread-per-query variant measured 2.3x slower here: its per-thread 256-B rows are uncoalesced,
+  // profiles/r1_step_table_v3.txt, and was removed)
   launch_pdl(mha_kernel, dim3((total + 7) / 8), dim3(256), 0, st, a);
   B2P_CHECK_LAUNCH();
   return 0;
