@@ -20,7 +20,8 @@ def pipe():
     return OraclePipeline()
 
 
-@pytest.mark.parametrize("name", ["synth_seed0", "synth_seed3_odd"])
+# synth_seed5_3240x2160: the geometry of ref:imgs/demo_image.jpg (BASELINE configs[0]: letterbox 640x426 -> canvas 640x448)
+@pytest.mark.parametrize("name", ["synth_seed0", "synth_seed3_odd", "synth_seed5_3240x2160"])
 def test_oracle_pipeline_equals_reference_golden(pipe, name):
     g = json.loads((GOLD / f"{name}.json").read_text())
     w, h = g["case"]["size"]
