@@ -29,7 +29,11 @@ def _same_elements(got, ref, ids_got, ids_ref):
     assert ids_got.tolist() == (ids_ref.tolist() if torch.is_tensor(ids_ref) else ids_ref)
 
 
-@pytest.mark.parametrize("name", ["synth_seed0", "synth_seed3_odd"])
+_UNVALIDATED = pytest.mark.skipif(not os.environ.get("B2P_TEST_UNVALIDATED"),
+                                  reason="added after the round-1 GPU budget was spent; B2P_TEST_UNVALIDATED=1 runs it")
+
+
+@pytest.mark.parametrize("name", ["synth_seed0", "synth_seed3_odd", pytest.param("synth_seed5_3240x2160", marks=_UNVALIDATED)])
 def test_after_detection_equals_reference_golden(name):
     det, cmp_ = ge.standin_models(DEV)
     g = json.loads((GOLD / f"{name}.json").read_text())
@@ -127,8 +131,7 @@ def test_pipelined_parser_equals_sequential(lanes):
                 assert ge_ == re_
 
 
-@pytest.mark.skipif(not os.environ.get("B2P_TEST_CAPTION_GROUP"), reason="opt-in feature (caption_group > 1), not yet validated on hardware: "
-                    "set B2P_TEST_CAPTION_GROUP=1 to run")
+@_UNVALIDATED
 @pytest.mark.parametrize("lanes,group", [(1, 2), (2, 2), (2, 3)])
 def test_grouped_captioning_equals_sequential(lanes, group):
     """caption_group > 1: the crops of several batches go through Florence-2 in one pass; per-batch results unchanged."""

@@ -5,7 +5,7 @@
 # mbarrier / split-K waits trap after ~2 s instead of hanging).
 mkdir -p gpurun_out
 # 1. grouped captioning: numerics, then throughput at group 2 with 2 and 1 lanes
-B2P_TEST_CAPTION_GROUP=1 timeout 300 python -m pytest tests/test_pipeline_gpu.py -m gpu -q -k grouped > gpurun_out/r2_group_test.log 2>&1
+B2P_TEST_UNVALIDATED=1 timeout 400 python -m pytest tests/test_pipeline_gpu.py -m gpu -q -k "grouped or 3240" > gpurun_out/r2_group_test.log 2>&1
 tail -3 gpurun_out/r2_group_test.log
 for L in 2 1; do
   timeout 150 python bench.py --no-cpu-baseline --caption-group 2 --caption-lanes $L > gpurun_out/r2_bench_group2_l$L.json 2> gpurun_out/r2_bench_group2_l$L.err
