@@ -67,3 +67,50 @@ def test_build_elements_matches_reference(seed):
         ref = sorted(ref, key=lambda x: x['content'] is None)
         got, _ = host_glue.build_elements(icons.tolist(), ocr_bbox, texts, W, H, thr)
         assert got == ref
+
+
+def _dense_case(seed):
+    """Adversarial for the OCR-containment walk (ref:util/utils.py:283-305): big icons holding several OCR boxes, OCR boxes
+    holding icons, in random order, so labels are collected, the walk breaks early, and OCR elements get removed."""
+    rng = np.random.default_rng(1000 + seed)
+    icons, ob = [], []
+    for _ in range(12):                                   # big icons
+        x, y = rng.uniform(0.02, 0.7, 2)
+        icons.append([x, y, x + rng.uniform(0.08, 0.25), y + rng.uniform(0.06, 0.2)])
+    for b in list(icons):                                 # OCR boxes inside big icons (pixels)
+        for _ in range(int(rng.integers(0, 4))):
+            x0 = b[0] * W + rng.uniform(2, 20); y0 = b[1] * H + rng.uniform(2, 15)
+            ob.append([int(x0), int(y0), int(x0 + rng.uniform(20, 60)), int(y0 + rng.uniform(8, 18))])
+    for _ in range(10):                                   # large OCR boxes with small icons inside them
+        x0, y0 = int(rng.integers(0, W - 400)), int(rng.integers(0, H - 120))
+        ob.append([x0, y0, x0 + int(rng.integers(150, 380)), y0 + int(rng.integers(40, 100))])
+        icons.append([(x0 + 10) / W, (y0 + 8) / H, (x0 + 40) / W, (y0 + 30) / H])
+    for _ in range(40):                                   # clutter
+        x, y = rng.uniform(0, 0.9, 2)
+        icons.append([x, y, x + rng.uniform(0.0, 0.06), y + rng.uniform(0.0, 0.06)])
+    order = rng.permutation(len(ob))
+    ob = [ob[i] for i in order]
+    icons = [icons[i] for i in rng.permutation(len(icons))]
+    texts = [f"w{i}" for i in range(len(ob))]
+    return torch.tensor(icons, dtype=torch.float32), ob, texts
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_dense_overlaps_fast_equals_loops_and_reference(seed):
+    icons, ob, texts = _dense_case(seed)
+    whwh = torch.Tensor([W, H, W, H])
+    oratio = (torch.tensor(ob) / whwh).tolist()
+    for thr in (0.7, 0.9):
+        fast, _ = host_glue.build_elements(icons.tolist(), oratio, texts, W, H, thr)
+        slow, _ = host_glue.build_elements(icons.tolist(), oratio, texts, W, H, thr, fast=False)
+        assert fast == slow
+        assert any(e["source"] == "box_yolo_content_ocr" for e in fast), "case does not exercise label collection"
+        if reference_available():
+            from oracle.shims import import_reference
+            ru, _ = import_reference()
+            ocr_elem = [{'type': 'text', 'bbox': box, 'interactivity': False, 'content': txt, 'source': 'box_ocr_content_ocr'}
+                        for box, txt in zip(oratio, texts) if ru.int_box_area(box, W, H) > 0]
+            xyxy_elem = [{'type': 'icon', 'bbox': box, 'interactivity': True, 'content': None} for box in icons.tolist()
+                         if ru.int_box_area(box, W, H) > 0]
+            ref = ru.remove_overlap_new(boxes=xyxy_elem, iou_threshold=thr, ocr_bbox=copy.deepcopy(ocr_elem))
+            assert fast == sorted(ref, key=lambda x: x['content'] is None)
