@@ -207,6 +207,7 @@ def run_b200(args):
     from omniparser_b200 import _lib, ops, shard
     from omniparser_b200.utils import ParseTimings, parse_screenshots
     _lib.lib()   # raises if the CUDA extension is missing: no fallback
+    torch.set_num_threads(max(1, host_threads() // max(1, world)))   # CPU-side model generation: stay inside the core quota
     log("building stand-in models")
     model, cmp_ = ge.standin_models(dev, args.precision)
     log("models ready; generating inputs")
