@@ -124,6 +124,67 @@ __global__ void dwconv_ln_kernel(const float* __restrict__ x, int B, int H, int 
   }
 }
 
+// Tiled variant (opt-in, split bit 1 / B2P_DWCONV_TILE=1; written at the end of round 1, not yet run on hardware): one CTA
+// per image stages the whole H x W x C map in shared memory once, so the nine taps read smem instead of re-reading L2 nine
+// times (the per-token kernel above moves ~36 B per element through L2: 24 us per launch where HBM needs 5).  Same
+// arithmetic in the same order as dwconv_ln_kernel => bit-identical outputs (tests/test_ops_gpu.py, gated).
+__global__ void dwconv_ln_tile_kernel(const float* __restrict__ x, int H, int W, int C, const float* __restrict__ w9c,
+                                      const float* __restrict__ bias, float* __restrict__ y, const float* __restrict__ g,
+                                      const float* __restrict__ bt, float eps, __half* __restrict__ o16, int split) {
+  pdl_wait();
+  extern __shared__ float4 xs4[];   // [H*W][C/4]
+  const int HW = H * W, C4 = C >> 2;
+  const long long tok0 = (long long)blockIdx.x * HW;
+  const float4* xin = reinterpret_cast<const float4*>(x + tok0 * C);
+  for (int i = threadIdx.x; i < HW * C4; i += blockDim.x) xs4[i] = xin[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int t = warp; t < HW; t += nw) {
+    const int xx = t % W, yy = t / W;
+    const long long tok = tok0 + t;
+    float4 v[8];
+    float s = 0.f;
+    int n = 0;
+    for (int c = lane; c < C4; c += 32, ++n) {
+      float4 acc = reinterpret_cast<const float4*>(bias)[c];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int sy = yy + ky - 1;
+        if (sy < 0 || sy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int sx = xx + kx - 1;
+          if (sx < 0 || sx >= W) continue;
+          const float4 xv = xs4[(t + (ky - 1) * W + (kx - 1)) * C4 + c];
+          const float4 wv = reinterpret_cast<const float4*>(w9c + (ky * 3 + kx) * C)[c];
+          acc.x += xv.x * wv.x; acc.y += xv.y * wv.y; acc.z += xv.z * wv.z; acc.w += xv.w * wv.w;
+        }
+      }
+      const float4 xc = xs4[t * C4 + c];
+      acc.x += xc.x; acc.y += xc.y; acc.z += xc.z; acc.w += xc.w;
+      reinterpret_cast<float4*>(y + tok * C)[c] = acc;
+      v[n] = acc;
+      s += (acc.x + acc.y) + (acc.z + acc.w);
+    }
+    const float mean = warp_sum(s) / float(C);
+    float q = 0.f;
+    for (int i = 0; i < n; ++i) {
+      const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / float(C) + eps);
+    n = 0;
+    __half* orow = o16 + tok * (split ? 2 * C : C);
+    for (int c = lane; c < C4; c += 32, ++n) {
+      const float4 gg = reinterpret_cast<const float4*>(g)[c], bb = reinterpret_cast<const float4*>(bt)[c];
+      float4 o;
+      o.x = (v[n].x - mean) * rstd * gg.x + bb.x; o.y = (v[n].y - mean) * rstd * gg.y + bb.y;
+      o.z = (v[n].z - mean) * rstd * gg.z + bb.z; o.w = (v[n].w - mean) * rstd * gg.w + bb.w;
+      store_act4(orow, 4 * c, split, o);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------- depthwise 3x3 + residual
 // y = dwconv3x3(x) + bias + x   (hf:models/florence2/modeling_florence2.py:281,293 and :431,443)
 __global__ void dwconv3x3_res_kernel(const float* __restrict__ x, int B, int H, int W, int C,
@@ -572,8 +633,22 @@ int b2p_dwconv_ln(const float* x, int B, int H, int W, int C, const float* w9c, 
                   const float* gamma, const float* beta, float eps, void* out16, int split, cudaStream_t st) {
   if (C % 4 || C > 1024) return set_error("dwconv_ln: C must be a multiple of 4 and <= 1024");
   const long long T = (long long)B * H * W;
+  const size_t tile_bytes = size_t(H) * W * C * sizeof(float);
+  if ((split & 2) && tile_bytes <= 200 * 1024 && B > 0) {   // opt-in tiled variant (see dwconv_ln_tile_kernel)
+    static bool attr = false;
+    if (!attr) {
+      if (cudaFuncSetAttribute(dwconv_ln_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        return set_error("dwconv_ln: cudaFuncSetAttribute failed");
+      attr = true;
+    }
+    const int threads = (H * W >= 16) ? 512 : 256;
+    launch_pdl(dwconv_ln_tile_kernel, dim3(B), dim3(threads), tile_bytes, st, x, H, W, C, w9c, bias, y, gamma, beta, eps, (__half*)out16,
+               (split & 1) ? C : 0);
+    B2P_CHECK_LAUNCH();
+    return 0;
+  }
   const int wpb = 8;
-  launch_pdl(dwconv_ln_kernel, dim3(int((T + wpb - 1) / wpb)), dim3(wpb * 32), 0, st, x, B, H, W, C, w9c, bias, y, gamma, beta, eps, (__half*)out16, split ? C : 0);
+  launch_pdl(dwconv_ln_kernel, dim3(int((T + wpb - 1) / wpb)), dim3(wpb * 32), 0, st, x, B, H, W, C, w9c, bias, y, gamma, beta, eps, (__half*)out16, (split & 1) ? C : 0);
   B2P_CHECK_LAUNCH();
   return 0;
 }

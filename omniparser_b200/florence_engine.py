@@ -163,6 +163,7 @@ class FlorencePlan:
         assert size in (64, 768)
         self.S = size
         self.tag = f"florence{instance}"
+        self.dw_tile = bool(os.environ.get("B2P_DWCONV_TILE"))   # opt-in smem-tiled dwconv+LN (unvalidated)
         self.warmed = False
         self.w, self.K, self.dev = w, K, w.device
         self.x3 = w.x3
@@ -260,7 +261,7 @@ class FlorencePlan:
                     x1 = self._e(T, C)
                     h = self._act(T, C)
                     ops_.append(lambda x=x, x1=x1, h=h, e=e, H=H, C=C: ops.dwconv_ln(x, K, H, H, C, e["dw1_w"], e["dw1_b"], x1,
-                                                                                 e["n1"].g, e["n1"].b, h, split=x3))
+                                                                                 e["n1"].g, e["n1"].b, h, split=x3, tile=self.dw_tile))
                     qkv = self._e(T, 3 * C)
                     self._gemm(ops_, h, e["qkv"], qkv)
                     a = self._act(T, C)
@@ -275,7 +276,7 @@ class FlorencePlan:
                     x3_ = self._e(T, C)
                     h2 = self._act(T, C)
                     ops_.append(lambda x2=x2, x3_=x3_, h2=h2, e=e, H=H, C=C: ops.dwconv_ln(x2, K, H, H, C, e["dw2_w"], e["dw2_b"], x3_,
-                                                                                      e["n2"].g, e["n2"].b, h2, split=x3))
+                                                                                      e["n2"].g, e["n2"].b, h2, split=x3, tile=self.dw_tile))
                     f = self._act(T, 4 * C)
                     self._gemm(ops_, h2, e["fc1"], f, act=ACT_GELU, split=x3)
                     x4 = self._e(T, C)

@@ -190,10 +190,11 @@ def dwconv3x3_res(x, B, H, W, C, w9c, bias, y):
     _lib.check(_lib.lib().b2p_dwconv3x3_res(_p(x), B, H, W, C, _p(w9c), _p(bias), _p(y), _stream()))
 
 
-def dwconv_ln(x, B, H, W, C, w9c, bias, y, gamma, beta, out16, eps=1e-5, split=False):
-    """y = dwconv3x3(x) + bias + x (fp32) and out16 = LayerNorm(y) as the next GEMM operand, one kernel."""
+def dwconv_ln(x, B, H, W, C, w9c, bias, y, gamma, beta, out16, eps=1e-5, split=False, tile=False):
+    """y = dwconv3x3(x) + bias + x (fp32) and out16 = LayerNorm(y) as the next GEMM operand, one kernel.  tile: opt-in
+    smem-tiled variant (one CTA per image, maps up to 200 KB; not yet validated on hardware)."""
     _lib.check(_lib.lib().b2p_dwconv_ln(_p(x), B, H, W, C, _p(w9c), _p(bias), _p(y), _p(gamma), _p(beta), eps, _p(out16),
-                                        int(split), _stream()))
+                                        int(bool(split)) | (2 if tile else 0), _stream()))
 
 
 def window_attn(qkv32, qkv_bias, B, H, W, C, heads, out, win=12, split=False):
