@@ -351,6 +351,49 @@ __global__ void __launch_bounds__(256) channel_attn_kernel(const float* __restri
   }
 }
 
+// Small-N variant (opt-in, split bit 1 / B2P_CHATTN_SMALL=1; written at the end of round 1, not yet run on hardware): for
+// the 4x4 / 2x2 maps of the 64x64-crop mode (N <= 16 tokens) the 256-thread CTA above is almost all synchronisation; here
+// ONE WARP owns a (batch, group) pair, 4 pairs per CTA.  Same sums in the same order => bit-identical outputs.
+__global__ void __launch_bounds__(128) channel_attn_small_kernel(const float* __restrict__ qkv, int B, int N, int C, int groups,
+                                                                 __half* __restrict__ out, int split) {
+  pdl_wait();
+  constexpr int D = 32, NMAX = 16;
+  __shared__ float sm[4][2 * NMAX + D][D + 1];   // per warp: q rows [0,N), k rows [NMAX, NMAX+N), P rows [2*NMAX, 2*NMAX+32)
+  const int w = threadIdx.x >> 5, j = threadIdx.x & 31;
+  const int pair = blockIdx.x * 4 + w;
+  if (pair >= B * groups) return;
+  const int g = pair % groups, b = pair / groups;
+  float (*qs)[D + 1] = sm[w];
+  float (*ks)[D + 1] = sm[w] + NMAX;
+  float (*P)[D + 1] = sm[w] + 2 * NMAX;
+  const float* base = qkv + (long long)b * N * 3 * C;
+  for (int n = 0; n < N; ++n) {
+    qs[n][j] = base[(long long)n * 3 * C + g * D + j];
+    ks[n][j] = base[(long long)n * 3 * C + C + g * D + j];
+  }
+  __syncwarp();
+  const float sc = rsqrtf(float(N));
+  for (int i = 0; i < D; ++i) {
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += qs[n][i] * ks[n][j];
+    const float v = s * sc;
+    const float m = warp_max(v);
+    const float e = __expf(v - m);
+    P[i][j] = e / warp_sum(e);
+  }
+  __syncwarp();
+  float pr[D];
+#pragma unroll
+  for (int jj = 0; jj < D; ++jj) pr[jj] = P[j][jj];
+  for (int n = 0; n < N; ++n) {
+    const float vj = base[(long long)n * 3 * C + 2 * C + g * D + j];
+    float acc = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < D; ++jj) acc += pr[jj] * __shfl_sync(0xffffffffu, vj, jj);
+    store_act(out + ((long long)b * N + n) * (split ? 2 * C : C), g * D + j, split, acc);
+  }
+}
+
 // ---------------------------------------------------------------------------------------- BART attention
 // One warp per (batch, head, query).  d_head = 64 (2 values per lane), scale applied to q (hf:models/bart/
 // modeling_bart.py:143-258).  K/V row b*Lk + j at k + (b*Lk + j)*ldk + h*64.  Decoder self-attention: the current
@@ -681,7 +724,12 @@ int b2p_window_attn(const float* qkv, const float* qkv_bias, int B, int H, int W
 
 int b2p_channel_attn(const float* qkv, int B, int N, int C, int groups, void* out, int split, cudaStream_t st) {
   if (C / groups != 32) return set_error("channel_attn: channels per group must be 32");
-  launch_pdl(channel_attn_kernel, dim3(B * groups), dim3(256), 0, st, qkv, N, C, groups, (__half*)out, split ? C : 0);
+  if ((split & 2) && N <= 16 && B > 0) {   // opt-in small-N variant (see channel_attn_small_kernel)
+    launch_pdl(channel_attn_small_kernel, dim3((B * groups + 3) / 4), dim3(128), 0, st, qkv, B, N, C, groups, (__half*)out, (split & 1) ? C : 0);
+    B2P_CHECK_LAUNCH();
+    return 0;
+  }
+  launch_pdl(channel_attn_kernel, dim3(B * groups), dim3(256), 0, st, qkv, N, C, groups, (__half*)out, (split & 1) ? C : 0);
   B2P_CHECK_LAUNCH();
   return 0;
 }

@@ -164,6 +164,7 @@ class FlorencePlan:
         self.S = size
         self.tag = f"florence{instance}"
         self.dw_tile = bool(os.environ.get("B2P_DWCONV_TILE"))   # opt-in smem-tiled dwconv+LN (unvalidated)
+        self.ca_small = bool(os.environ.get("B2P_CHATTN_SMALL"))   # opt-in warp-per-group channel attention for N <= 16 (unvalidated)
         self.warmed = False
         self.w, self.K, self.dev = w, K, w.device
         self.x3 = w.x3
@@ -270,7 +271,7 @@ class FlorencePlan:
                         ops_.append(lambda qkv=qkv, a=a, e=e, H=H, C=C, hd=hd: ops.window_attn(qkv, e["qkv"].b, K, H, H, C, hd, a, split=x3))
                     else:
                         gr = w.groups[s]
-                        ops_.append(lambda qkv=qkv, a=a, H=H, C=C, gr=gr: ops.channel_attn(qkv, K, H * H, C, gr, a, split=x3))
+                        ops_.append(lambda qkv=qkv, a=a, H=H, C=C, gr=gr: ops.channel_attn(qkv, K, H * H, C, gr, a, split=x3, small=self.ca_small))
                     x2 = self._e(T, C)
                     self._gemm(ops_, a, e["proj"], x2, res=x1)
                     x3_ = self._e(T, C)

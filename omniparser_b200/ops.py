@@ -201,8 +201,9 @@ def window_attn(qkv32, qkv_bias, B, H, W, C, heads, out, win=12, split=False):
     _lib.check(_lib.lib().b2p_window_attn(_p(qkv32), _p(qkv_bias), B, H, W, C, heads, win, _p(out), int(split), _stream()))
 
 
-def channel_attn(qkv32, B, N, C, groups, out, split=False):
-    _lib.check(_lib.lib().b2p_channel_attn(_p(qkv32), B, N, C, groups, _p(out), int(split), _stream()))
+def channel_attn(qkv32, B, N, C, groups, out, split=False, small=False):
+    """small: opt-in warp-per-(batch, group) variant for N <= 16 tokens (not yet validated on hardware)."""
+    _lib.check(_lib.lib().b2p_channel_attn(_p(qkv32), B, N, C, groups, _p(out), int(bool(split)) | (2 if small else 0), _stream()))
 
 
 def mha(q, ldq, k, v, ldk, B, Lq, Lk, heads, out, ldo, split=False):

@@ -375,3 +375,20 @@ def test_dwconv_ln_tiled_variant_bit_identical(B, H, C, split):
         torch.cuda.synchronize()
         outs.append((y.cpu(), o16.cpu()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("B2P_TEST_UNVALIDATED"), reason="opt-in kernel written after the round-1 GPU budget "
+                    "was spent: B2P_TEST_UNVALIDATED=1 runs it")
+@pytest.mark.parametrize("B,N,C", [(7, 16, 512), (5, 4, 1024), (3, 9, 256)])
+@pytest.mark.parametrize("split", [False, True])
+def test_channel_attn_small_variant_bit_identical(B, N, C, split):
+    """warp-per-(batch, group) channel attention for N <= 16 tokens == the 256-thread-CTA kernel, bit for bit."""
+    g = torch.Generator().manual_seed(B * N + C)
+    qkv = torch.randn(B * N, 3 * C, generator=g).to(DEV)
+    outs = []
+    for small in (False, True):
+        o = torch.zeros(B * N, (2 if split else 1) * C, dtype=torch.float16, device=DEV)
+        ops.channel_attn(qkv, B, N, C, C // 32, o, split=split, small=small)
+        torch.cuda.synchronize()
+        outs.append(o.cpu())
+    assert torch.equal(outs[0], outs[1])

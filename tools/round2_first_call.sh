@@ -19,9 +19,9 @@ if grep -q " passed" gpurun_out/r2_cta2_test.log && ! grep -q "failed\|error" gp
   grep "leg:\|verify\|caption stages" gpurun_out/r2_bench_cta2.err
   B2P_CTA2=1 timeout 100 python tools/prof_gemm.py > gpurun_out/r2_prof_gemm_cta2.log 2>&1; tail -8 gpurun_out/r2_prof_gemm_cta2.log
 fi
-# 2b. smem-tiled dwconv+LN: bit-identical with the per-token kernel?  then the bench with it
-B2P_TEST_UNVALIDATED=1 timeout 120 python -m pytest tests/test_ops_gpu.py -m gpu -q -k dwconv_ln_tiled > gpurun_out/r2_dwtile_test.log 2>&1; tail -2 gpurun_out/r2_dwtile_test.log
-B2P_DWCONV_TILE=1 timeout 150 python bench.py --no-cpu-baseline > gpurun_out/r2_bench_dwtile.json 2> gpurun_out/r2_bench_dwtile.err; grep "leg:\|verify\|caption stages" gpurun_out/r2_bench_dwtile.err
+# 2b. smem-tiled dwconv+LN and warp-per-group channel attention: bit-identical with the validated kernels?  then the bench with both
+B2P_TEST_UNVALIDATED=1 timeout 120 python -m pytest tests/test_ops_gpu.py -m gpu -q -k "dwconv_ln_tiled or channel_attn_small" > gpurun_out/r2_dwtile_test.log 2>&1; tail -2 gpurun_out/r2_dwtile_test.log
+B2P_DWCONV_TILE=1 B2P_CHATTN_SMALL=1 timeout 150 python bench.py --no-cpu-baseline > gpurun_out/r2_bench_dwtile.json 2> gpurun_out/r2_bench_dwtile.err; grep "leg:\|verify\|caption stages" gpurun_out/r2_bench_dwtile.err
 # 3. where the microseconds of a GEMM launch go (instrumented kernel instantiation)
 B2P_TRACE=1 B2P_NO_GRAPH=1 timeout 240 python tools/trace_gemm.py step > gpurun_out/r2_trace_step.txt 2>&1
 tail -45 gpurun_out/r2_trace_step.txt
