@@ -304,7 +304,7 @@ def run_b200(args):
     value = world * B * args.steps / (ms_res / 1e3)
     e2e = world * B * args.steps / (ms_e2e / 1e3)
 
-    # roofline of the dominant kernel: gemm_tcgen05_kernel inside the YOLOv9-E forward (241 of its 252 launches,
+    # roofline of the dominant kernel: gemm_tcgen05_kernel inside the YOLOv9-E forward (233 of its 252 launches,
     # ~95 % of its device time, profiles/); algorithmic FLOPs of the forward / CUDA-event time of the graph replay.
     plan = model._get_io(B, H, W, 640, 300)["plan"]
     for _ in range(3):
@@ -394,7 +394,7 @@ def run_b200(args):
                         "d2h_bytes_per_step": B * (4 + 300 * 16) + st["crops"] // max(args.steps, 1) * (args.max_new_tokens + 1) * 8,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clocks,
-                "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (YOLOv9-E forward, batch %d: 241 GEMM/conv launches + 11 pooling launches)" % B,
+                "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (YOLOv9-E forward, batch %d: 233 GEMM/conv launches + 19 im2col/pooling/upsample/CBFuse launches)" % B,
                              "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
                              "traffic_note": "DRAM bytes per forward from the committed ncu launch list (caches flushed per kernel), not from this run",
                              "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})", "forward_ms": fwd_ms,

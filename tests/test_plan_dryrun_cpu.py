@@ -1,0 +1,151 @@
+"""CPU dry run of the launch plans: the C library is replaced by a recorder that type-checks every call against the ctypes
+prototypes (``_lib.PROTOTYPES`` = include/b200parse.h) and re-states the argument checks of the C side (row pitches vs
+logical sizes, fp16x3 flags), so a slip in the host-side plumbing (argument order, a stride that still assumes another
+operand layout, a flag that is not forwarded) fails here and not only on the GPU box.  No arithmetic runs."""
+import contextlib
+import ctypes as C
+
+import pytest
+import torch
+
+from omniparser_b200 import _lib, ops
+from standin import florence as FS
+
+
+class _Stream:
+    cuda_stream = 0
+
+    def __init__(self, *a, **k):
+        pass
+
+    def synchronize(self):
+        pass
+
+    def wait_stream(self, other):
+        pass
+
+
+class _Recorder:
+    def __init__(self):
+        self.calls = []
+
+    def __getattr__(self, name):
+        res, argtypes = _lib.PROTOTYPES[name]
+
+        def f(*args):
+            assert len(args) == len(argtypes), f"{name}: {len(args)} arguments, prototype has {len(argtypes)}"
+            vals = []
+            for t, a in zip(argtypes, args):
+                t.from_param(a)                      # raises if the Python value cannot become this C type
+                vals.append(a.value if hasattr(a, "value") else a)
+            self.calls.append((name, vals))
+            _check(name, vals)
+            return 0
+        return f
+
+
+def _check(name, a):
+    """the argument checks gemm_launch / the SIMT launchers make on the device side, restated"""
+    if name == "b2p_gemm":
+        _A, lda, _B, M, N, K, _out, ldc, _bias, _res, ldr, act, flags, _st = a
+        x3, split, f32 = bool(flags & 8), bool(flags & 4), bool(flags & 2)
+        assert M > 0 and N > 0 and K % 8 == 0
+        assert lda >= (2 if x3 else 1) * K, ("A row pitch", lda, K, x3)
+        assert ldc >= (2 * N if split else N), ("out row pitch", ldc, N, split)
+        assert not (split and f32)
+        if x3:
+            assert K % 32 == 0
+        assert act in (0, 1, 2)
+    elif name == "b2p_conv3x3":
+        _in, ld_in, batch, H, W, Cin, stride, _w, Cout, _out, ldc, _bias, _res, ldr, act, flags, _st = a
+        x3 = bool(flags & 8)
+        assert stride in (1, 2) and Cin % 32 == 0 and ld_in >= (2 if x3 else 1) * Cin and ldc >= Cout
+        if stride == 2:
+            assert H % 2 == 0 and W % 2 == 0
+    elif name == "b2p_layernorm":
+        _x, ldx, _g, _b, eps, T, Cc, o16, ld16, o32, ld32, split, _st = a
+        assert ldx >= Cc and (o16 is None or ld16 >= (2 if split else 1) * Cc) and (o32 is None or ld32 >= Cc)
+    elif name in ("b2p_dwconv_ln", "b2p_channel_attn", "b2p_window_attn", "b2p_mha", "b2p_mha_cached", "b2p_projector_prep"):
+        split = a[-2]
+        assert split in (0, 1, 2, 3)
+
+
+@pytest.fixture()
+def rec(monkeypatch):
+    r = _Recorder()
+    monkeypatch.setattr(_lib, "_lib", r)
+    monkeypatch.setattr(ops, "_stream", lambda: C.c_void_p(0))
+    monkeypatch.setattr(torch.cuda, "device", lambda *a, **k: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "Stream", _Stream)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _Stream())
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    return r
+
+
+@pytest.fixture(scope="module")
+def florence():
+    return FS.florence_standin(0)
+
+
+@pytest.mark.parametrize("prec", ["fp16x3", "fp16"])
+def test_florence_plan_64(rec, florence, prec):
+    from omniparser_b200.florence_engine import FlorencePlan, FlorenceWeights
+    w = FlorenceWeights(florence.state_dict(), torch.device("cpu"), FS.GEN, prec)
+    p = FlorencePlan(w, 2, 4, FS.PROMPT_IDS, use_graph=False, size=64)
+    p.encode()
+    n_enc = len(rec.calls)
+    p.reset_decode(2)
+    p.decode_step()
+    n_dec = len(rec.calls) - n_enc
+    names = [c[0] for c in rec.calls]
+    assert n_enc == 232 and n_dec == 71                                   # launch counts quoted in DESIGN.md / profiles
+    assert names.count("b2p_im2col3x3") == 2 and names.count("b2p_conv3x3") == 1   # 4x4 / 2x2 patch-embeds via im2col + GEMM
+    x3_flags = {bool(c[1][12] & 8) for c in rec.calls if c[0] == "b2p_gemm"}
+    assert x3_flags == {prec == "fp16x3"}
+    # every decode step ends with the LM head into the padded logits pitch, the pick and the step counter
+    assert names[-3:] == ["b2p_gemm", "b2p_greedy_pick", "b2p_step_advance"]
+    lm = rec.calls[-3][1]
+    assert lm[4] == 51290 and lm[7] % 8 == 0 and lm[7] >= 51290
+
+
+def test_florence_plan_768(rec, florence):
+    from omniparser_b200.florence_engine import FlorencePlan, FlorenceWeights
+    w = FlorenceWeights(florence.state_dict(), torch.device("cpu"), FS.GEN, "fp16x3")
+    p = FlorencePlan(w, 1, 2, FS.PROMPT_IDS, use_graph=False, size=768)
+    assert p.n_img == 577 and p.L == 585
+    p.encode()
+    names = [c[0] for c in rec.calls]
+    assert names[0] == "b2p_resize_u8" and names.count("b2p_conv3x3") == 3 and "b2p_im2col3x3" not in names
+    n_all = len(names)
+    rec.calls.clear()
+    p.encode(from_resized=True)          # processor already resized on the host: same plan minus the device resize
+    assert len(rec.calls) == n_all - 1 and rec.calls[0][0] == "b2p_im2col_u8"
+
+
+def test_opt_in_kernel_flags_are_forwarded(rec, florence, monkeypatch):
+    from omniparser_b200.florence_engine import FlorencePlan, FlorenceWeights
+    monkeypatch.setenv("B2P_DWCONV_TILE", "1")
+    monkeypatch.setenv("B2P_CHATTN_SMALL", "1")
+    w = FlorenceWeights(florence.state_dict(), torch.device("cpu"), FS.GEN, "fp16x3")
+    p = FlorencePlan(w, 2, 2, FS.PROMPT_IDS, use_graph=False, size=64)
+    p.encode()
+    assert {c[1][-2] for c in rec.calls if c[0] == "b2p_dwconv_ln"} == {3}
+    assert {c[1][-2] for c in rec.calls if c[0] == "b2p_channel_attn"} == {3}
+    rec.calls.clear()
+    monkeypatch.delenv("B2P_DWCONV_TILE")
+    monkeypatch.delenv("B2P_CHATTN_SMALL")
+    p = FlorencePlan(w, 2, 2, FS.PROMPT_IDS, use_graph=False, size=64)
+    p.encode()
+    assert {c[1][-2] for c in rec.calls if c[0] in ("b2p_dwconv_ln", "b2p_channel_attn")} == {1}   # the validated default
+
+
+def test_yolo_plan(rec):
+    from omniparser_b200.yolo_engine import YoloPlan, YoloWeights
+    from standin.yolo_weights import yolo_standin
+    w = YoloWeights(yolo_standin(0).state_dict(), torch.device("cpu"))
+    plan = YoloPlan(w, 2, 384, 640, use_graph=False)
+    plan.run()
+    names = [c[0] for c in rec.calls]
+    assert len(names) == plan.n_launches == 252
+    assert names.count("b2p_gemm") + names.count("b2p_conv3x3") == 233   # the figure quoted in bench.py / DESIGN.md
+    assert all(not (c[1][12] & 8) for c in rec.calls if c[0] == "b2p_gemm")      # detector: plain fp16 operands
