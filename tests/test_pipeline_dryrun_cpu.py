@@ -123,3 +123,26 @@ def test_pipelined_parser_host_plumbing(env, florence, lanes, group):
         dst, n_box = a[7], a[5]
         owner = [p for ptr, p in base.items() if ptr <= dst < ptr + p.crops.numel()]
         assert len(owner) == 1 and (dst - owner[0].crops.data_ptr()) % (64 * 64 * 3) == 0 and n_box in (2 * 3, 2 * 4)
+
+
+@pytest.mark.parametrize("caption_size", [64, 768])
+def test_parse_screenshots_host_plumbing(env, florence, monkeypatch, caption_size):
+    """the one-batch-at-a-time entry point, both caption modes (768: device resize + chunked generate)"""
+    from omniparser_b200 import caption
+    from omniparser_b200.caption import B200Florence2Processor
+    from omniparser_b200.utils import ParseTimings, parse_screenshots
+    monkeypatch.setattr(caption, "BUCKET_768", 1)        # one crop per chunk keeps the CPU-side buffers small
+    det = _FakeDetector()
+    cmp_ = dict(model=_cap_model(florence), processor=B200Florence2Processor())
+    (imgs, ocr), = _batches(1)
+    boxes = [[[10.0, 10.0, 60.0, 70.0], [100.0, 40.0, 150.0, 90.0], [300.0, 100.0, 380.0, 180.0]], []]
+    tm = ParseTimings()
+    out = parse_screenshots(imgs, det, cmp_, ocr, BOX_TRESHOLD=0.05, iou_threshold=0.7, max_new_tokens=2, timings=tm,
+                            _det_override=boxes, caption_size=caption_size)
+    assert [ids.shape[0] for _, ids in out] == [3, 0] and tm["n_crops"] == 3
+    names = [c[0] for c in env.calls]
+    assert names.count("b2p_crop_resize") == 1
+    if caption_size == 768:
+        assert names.count("b2p_resize_u8") == 3 and names.count("b2p_encoder_embed") == 3      # three chunks of one crop
+    else:
+        assert "b2p_resize_u8" not in names and names.count("b2p_encoder_embed") == 1
