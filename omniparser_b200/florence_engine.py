@@ -420,7 +420,7 @@ class FlorencePlan:
             if not replay_after_capture or os.environ.get("B2P_EAGER_FIRST"):
                 return
         g.replay()
-        ops.GRAPH_LAUNCHES[0] += len(lst)
+        ops.count_graph_launches(len(lst))
 
     def warm(self):
         """Build every CUDA graph of this plan on scratch inputs (call with the GPU otherwise idle: see

@@ -28,6 +28,13 @@ def capture_stream(tag, device):
 
 
 GRAPH_LAUNCHES = [0]   # kernels replayed through CUDA graphs (the C-side counter only sees direct launches)
+_GRAPH_LAUNCHES_LOCK = threading.Lock()
+
+
+def count_graph_launches(n: int):
+    """the detect and caption threads of the pipelined parser replay graphs concurrently"""
+    with _GRAPH_LAUNCHES_LOCK:
+        GRAPH_LAUNCHES[0] += n
 FLAG_BF16, FLAG_OUT_F32, FLAG_SPLIT, FLAG_X3 = 1, 2, 4, 8
 
 
