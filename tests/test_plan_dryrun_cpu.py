@@ -149,3 +149,37 @@ def test_yolo_plan(rec):
     assert len(names) == plan.n_launches == 252
     assert names.count("b2p_gemm") + names.count("b2p_conv3x3") == 233   # the figure quoted in bench.py / DESIGN.md
     assert all(not (c[1][12] & 8) for c in rec.calls if c[0] == "b2p_gemm")      # detector: plain fp16 operands
+
+
+class _Graph:
+    replays = 0
+
+    def replay(self):
+        _Graph.replays += 1
+
+
+def test_graph_paths(rec, florence, monkeypatch):
+    """first-use capture, warm(), replay bookkeeping (CUDA graphs replaced by a stub that counts replays)"""
+    from omniparser_b200.florence_engine import FlorencePlan, FlorenceWeights
+    from omniparser_b200.yolo_engine import YoloPlan, YoloWeights
+    from standin.yolo_weights import yolo_standin
+    monkeypatch.setattr(torch.cuda, "CUDAGraph", _Graph)
+    monkeypatch.setattr(torch.cuda, "graph", lambda *a, **k: contextlib.nullcontext())
+    monkeypatch.delenv("B2P_NO_GRAPH", raising=False)
+    _Graph.replays = 0
+    g0 = ops.GRAPH_LAUNCHES[0]
+    w = FlorenceWeights(florence.state_dict(), torch.device("cpu"), FS.GEN, "fp16x3")
+    p = FlorencePlan(w, 2, 3, FS.PROMPT_IDS, use_graph=True, size=64)
+    assert p.use_graph and not p.warmed
+    p.warm()                                            # encode: eager + capture + replay; decode: eager + capture, then one replay
+    assert p.warmed and p.g_enc is not None and all(pt["graph"] is not None for pt in p.parts)
+    n_eager = len(rec.calls)
+    assert n_eager == 2 * (232 + 71)                    # every op ran once eagerly and once inside the (stubbed) capture
+    p.encode(); p.reset_decode(2); p.decode_step(); p.decode_step()
+    assert _Graph.replays == 2 + 3 and ops.GRAPH_LAUNCHES[0] - g0 == 2 * 232 + 3 * 71
+    assert sum(1 for c in rec.calls[n_eager:] if c[0].startswith("b2p_")) == 0     # steady state: graph replays only
+    yw = YoloWeights(yolo_standin(0).state_dict(), torch.device("cpu"))
+    yp = YoloPlan(yw, 1, 384, 640, use_graph=True)
+    g1 = ops.GRAPH_LAUNCHES[0]
+    yp.run(); yp.run()
+    assert ops.GRAPH_LAUNCHES[0] - g1 == 2 * 252
