@@ -47,13 +47,33 @@ int b2p_conv3x3(const void* in, long long ld_in, int batch, int H, int W, int Ci
                 int Cout, void* out, long long ldc, const float* bias, const void* residual, long long ldr, int act,
                 int flags, b2p_stream_t stream);
 
-/* ---- YOLOv9-E graph helpers (inside the TorchScript archive, ref:util/yolov9.py:120-121) ---- */
+/* `_planes` forms (fp16x3 operands that are channel slices of a wider [hi(Ctot) | lo(Ctot)] pixel / row): explicit
+ * lo-plane offsets in elements -- lo_a: A's lo half at column lo_a + k (default K / Cin); lo_out: with flags bit2 the
+ * output's lo half at column lo_out + n (default N); lo_res: the fp16 residual is a hi/lo pair whose lo half sits at
+ * column lo_res + n (default 0: the residual has no lo half).  This is what the parity-grade (fp16x3) detector mode uses:
+ * every YOLOv9-E feature map stays a hi/lo pair inside its concat buffer (ref:util/yolov9.py:120-121 in fp32). */
+int b2p_gemm_planes(const void* A, long long lda, const void* B, int M, int N, int K, void* out, long long ldc,
+                    const float* bias, const void* residual, long long ldr, int act, int flags, long long lo_a,
+                    long long lo_out, long long lo_res, b2p_stream_t stream);
+int b2p_conv3x3_planes(const void* in, long long ld_in, int batch, int H, int W, int Cin, int stride, const void* weight,
+                       int Cout, void* out, long long ldc, const float* bias, const void* residual, long long ldr, int act,
+                       int flags, long long lo_a, long long lo_out, long long lo_res, b2p_stream_t stream);
+
+/* ---- YOLOv9-E graph helpers (inside the TorchScript archive, ref:util/yolov9.py:120-121) ----
+ * `_x3` forms: every map is an fp16 hi/lo pair (lo plane `lo*` elements after the hi plane, 0 = plain fp16); the
+ * arithmetic runs on the exact fp32 sums hi + lo and the result is re-split. */
 int b2p_adown_pool(const void* x, long long ldx, int B, int H, int W, int C, void* x1, long long ld1, void* x2,
                    long long ld2, b2p_stream_t stream);
+int b2p_adown_pool_x3(const void* x, long long ldx, int B, int H, int W, int C, void* x1, long long ld1, void* x2,
+                      long long ld2, long long lox, long long lo1, long long lo2, b2p_stream_t stream);
 int b2p_maxpool_s1(const void* x, long long ldx, int B, int H, int W, int C, int k, void* y, long long ldy,
                    b2p_stream_t stream);
+int b2p_maxpool_s1_x3(const void* x, long long ldx, int B, int H, int W, int C, int k, void* y, long long ldy,
+                      long long lox, long long loy, b2p_stream_t stream);
 int b2p_upsample2x(const void* x, long long ldx, int B, int H, int W, int C, void* y, long long ldy,
                    b2p_stream_t stream);
+int b2p_upsample2x_x3(const void* x, long long ldx, int B, int H, int W, int C, void* y, long long ldy, long long lox,
+                      long long loy, b2p_stream_t stream);
 /* explicit 3x3 / pad-1 im2col of an NHWC f16 map -> [B*Ho*Wo][9*C] (tap-major), for convs whose output map is far
  * smaller than one 128-pixel implicit-GEMM tile (DaViT patch-embed convs of the 64x64-crop mode, hf:modeling_florence2.py
  * ConvEmbed, reached from ref:util/utils.py:125 generate) */
@@ -62,6 +82,9 @@ int b2p_im2col3x3(const void* x, long long ldx, int B, int H, int W, int C, int 
 int b2p_cbfuse(int nsrc, const void* const* srcs_host, const long long* lds_host, const int* shifts_host,
                const void* last, long long ldl, int B, int H, int W, int C, void* y, long long ldy,
                b2p_stream_t stream);
+int b2p_cbfuse_x3(int nsrc, const void* const* srcs_host, const long long* lds_host, const int* shifts_host,
+                  const long long* los_host, const void* last, long long ldl, int B, int H, int W, int C, void* y,
+                  long long ldy, long long lol, long long loy, b2p_stream_t stream);
 
 /* ---- detector pre/post-processing ----
  * b2p_letterbox: PIL Image.resize(LANCZOS) + paste on a 114 canvas, ref:util/yolov9.py:73-84 (bit-exact).

@@ -26,7 +26,13 @@ PROTOTYPES = {
     "b2p_abi_version": (i32, []),
     "b2p_gemm": (i32, [vp, i64, vp, i32, i32, i32, vp, i64, vp, vp, i64, i32, i32, vp]),
     "b2p_conv3x3": (i32, [vp, i64, i32, i32, i32, i32, i32, vp, i32, vp, i64, vp, vp, i64, i32, i32, vp]),
+    "b2p_gemm_planes": (i32, [vp, i64, vp, i32, i32, i32, vp, i64, vp, vp, i64, i32, i32, i64, i64, i64, vp]),
+    "b2p_conv3x3_planes": (i32, [vp, i64, i32, i32, i32, i32, i32, vp, i32, vp, i64, vp, vp, i64, i32, i32, i64, i64, i64, vp]),
     "b2p_adown_pool": (i32, [vp, i64, i32, i32, i32, i32, vp, i64, vp, i64, vp]),
+    "b2p_adown_pool_x3": (i32, [vp, i64, i32, i32, i32, i32, vp, i64, vp, i64, i64, i64, i64, vp]),
+    "b2p_maxpool_s1_x3": (i32, [vp, i64, i32, i32, i32, i32, i32, vp, i64, i64, i64, vp]),
+    "b2p_upsample2x_x3": (i32, [vp, i64, i32, i32, i32, i32, vp, i64, i64, i64, vp]),
+    "b2p_cbfuse_x3": (i32, [i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(i32), C.POINTER(i64), vp, i64, i32, i32, i32, i32, vp, i64, i64, i64, vp]),
     "b2p_maxpool_s1": (i32, [vp, i64, i32, i32, i32, i32, i32, vp, i64, vp]),
     "b2p_upsample2x": (i32, [vp, i64, i32, i32, i32, i32, vp, i64, vp]),
     "b2p_cbfuse": (i32, [i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(i32), vp, i64, i32, i32, i32, i32, vp, i64, vp]),

@@ -219,41 +219,50 @@ class B200Florence2Model:
 
 
 def load_florence_state(path: str | Path):
-    """Read ``model.safetensors`` (+ ``generation_config.json``) from a local directory (ref:README.md:45-46)."""
+    """Read ``model.safetensors`` (+ ``generation_config.json`` / ``config.json``) from a local directory
+    (ref:README.md:45-46; what ``AutoModelForCausalLM.from_pretrained`` reads at ref:util/utils.py:66-68)."""
     from safetensors.torch import load_file
 
     p = Path(path)
+    if not (p / "model.safetensors").is_file():
+        raise FileNotFoundError(f"{p}/model.safetensors not found (no network here: pass a local weights directory)")
     sd = load_file(str(p / "model.safetensors"))
     gen = {}
     for name in ("generation_config.json", "config.json"):
         f = p / name
         if f.is_file():
             cfg = json.loads(f.read_text())
-            for k in DEFAULT_GEN:
-                if k in cfg and k not in gen:
-                    gen[k] = cfg[k]
+            for src in (cfg, cfg.get("text_config") or {}):
+                for k in DEFAULT_GEN:
+                    if k in src and src[k] is not None and k not in gen:
+                        gen[k] = src[k]
     return rename_remote_code(sd), gen
 
 
+_VT_LEAF = (   # microsoft/Florence-2 remote-code DaViT leaf names -> transformers-native names
+    (".window_attn.norm.", ".norm1."), (".channel_attn.norm.", ".norm1."), (".ffn.norm.", ".norm2."),
+    (".window_attn.fn.", ".window_attn."), (".channel_attn.fn.", ".channel_attn."),
+    (".conv1.fn.dw.", ".conv1."), (".conv2.fn.dw.", ".conv2."),
+    (".ffn.fn.net.fc1.", ".ffn.fc1."), (".ffn.fn.net.fc2.", ".ffn.fc2."),
+)
+
+
 def rename_remote_code(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
-    """microsoft/Florence-2 remote-code parameter names -> transformers-native names.  Only prefix
-    and leaf renames; untestable offline (no real checkpoint here) and therefore conservative: native names pass
-    through unchanged."""
+    """microsoft/Florence-2 remote-code parameter names -> transformers-native names (recalled layout,
+    exercised by exporting the seeded stand-in under those names: tests/test_loaders_cpu.py).  Native names pass
+    through.  Every key must be recognised: an unknown key raises instead of loading as a silently different network."""
     if any(k.startswith("model.vision_tower.") for k in sd):
-        return sd
+        return dict(sd)
     out = {}
     for k, v in sd.items():
-        nk = k
-        if k.startswith("vision_tower."):
+        if k.startswith("vision_tower.convs."):
+            nk = "model." + k.replace(".proj.weight", ".conv.weight").replace(".proj.bias", ".conv.bias")
+        elif k.startswith("vision_tower.blocks."):
             nk = "model." + k
-            nk = nk.replace(".convs.", ".convs.").replace(".proj.weight", ".conv.weight").replace(".proj.bias", ".conv.bias") \
-                if ".convs." in nk else nk
-            nk = nk.replace(".window_attn.fn.", ".window_attn.").replace(".channel_attn.fn.", ".channel_attn.")
-            nk = nk.replace(".conv1.fn.dw.", ".conv1.").replace(".conv2.fn.dw.", ".conv2.")
-            nk = nk.replace(".ffn.fn.net.fc1.", ".ffn.fc1.").replace(".ffn.fn.net.fc2.", ".ffn.fc2.")
-            nk = nk.replace(".window_attn.norm.", ".norm1.").replace(".channel_attn.norm.", ".norm1.").replace(".ffn.norm.", ".norm2.")
+            for a, b in _VT_LEAF:
+                nk = nk.replace(a, b)
         elif k == "image_projection":
-            nk, v = "model.multi_modal_projector.image_projection.weight", v.t().contiguous()
+            nk, v = "model.multi_modal_projector.image_projection.weight", v.t().contiguous()   # raw (1024, 768) Parameter
         elif k.startswith("image_proj_norm."):
             nk = "model.multi_modal_projector." + k
         elif k.startswith("image_pos_embed."):
@@ -264,5 +273,54 @@ def rename_remote_code(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
             nk = "model.language_model." + k[len("language_model.model."):]
         elif k == "language_model.lm_head.weight":
             nk = "lm_head.weight"
+        elif k == "language_model.final_logits_bias":
+            nk = "final_logits_bias"
+        else:
+            raise KeyError(f"unrecognised Florence-2 checkpoint parameter: {k}")
+        if nk in out:
+            raise KeyError(f"two checkpoint parameters map to {nk}")
         out[nk] = v
     return out
+
+
+def find_tokenizer_dir(model_name_or_path=None, tokenizer_path=None) -> Optional[Path]:
+    """Where the BART byte-level BPE files of the Florence-2 processor can be found offline.  The reference loads the
+    processor from the hub id ``microsoft/Florence-2-base`` (ref:util/utils.py:64); ``weights/icon_caption_florence``
+    itself holds only config + safetensors.  Search order: explicit ``tokenizer_path`` / $B2P_FLORENCE_PROCESSOR, the
+    weights directory, a sibling ``Florence-2-base`` directory, the local Hugging Face hub cache."""
+    import os
+    cands = []
+    for c in (tokenizer_path, os.environ.get("B2P_FLORENCE_PROCESSOR"), model_name_or_path):
+        if c:
+            cands.append(Path(c))
+    if model_name_or_path:
+        cands.append(Path(model_name_or_path).parent / "Florence-2-base")
+    hub = Path(os.environ.get("HF_HOME", Path.home() / ".cache" / "huggingface")) / "hub" / "models--microsoft--Florence-2-base" / "snapshots"
+    if hub.is_dir():
+        cands.extend(sorted(hub.iterdir(), reverse=True))
+    for c in cands:
+        if (c / "tokenizer.json").is_file() or ((c / "vocab.json").is_file() and (c / "merges.txt").is_file()):
+            return c
+    return None
+
+
+class _FastTokenizer:
+    """``tokenizer.json`` through the `tokenizers` library (the added Florence-2 tokens live in that file)."""
+
+    def __init__(self, path: Path):
+        from tokenizers import Tokenizer
+        self.tk = Tokenizer.from_file(str(path))
+
+    def batch_decode(self, ids, skip_special_tokens=True, **kw):
+        return self.tk.decode_batch([list(map(int, r)) for r in ids], skip_special_tokens=skip_special_tokens)
+
+
+def load_tokenizer(d: Path):
+    """BART byte-level BPE detokeniser for ``processor.batch_decode`` (ref:util/utils.py:128)."""
+    d = Path(d)
+    if (d / "tokenizer.json").is_file():
+        return _FastTokenizer(d / "tokenizer.json")
+    from transformers import BartTokenizer
+    vocab = json.loads((d / "vocab.json").read_text())
+    merges = [tuple(ln.split(" ")) for ln in (d / "merges.txt").read_text().splitlines() if ln and not ln.startswith("#version")]
+    return BartTokenizer(vocab=vocab, merges=merges)

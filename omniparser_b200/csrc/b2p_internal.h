@@ -35,6 +35,11 @@ struct ConvGemm {
   int split_out;       // fp16 output written as [hi(N) | lo(N)] (row stride ldc >= 2N): operand of a fp16x3 GEMM
   int x3;              // fp16x3 operands: A rows [hi(K) | lo(K)] (conv: per pixel [hi(Cin) | lo(Cin)]), B rows likewise;
                        // K / Cin are the LOGICAL sizes.  out = A_hi*B_hi + A_hi*B_lo + A_lo*B_hi, fp32 accumulate
+  // fp16x3 "lo planes" (elements; 0 = the packed default): a channel slice of a wider [hi(Ctot) | lo(Ctot)] pixel / row
+  // has its lo half Ctot elements after its hi half, not K (or N) elements after it.
+  long long lo_a;      // A: lo half at column lo_a + k            (default K / Cin)
+  long long lo_out;    // split_out: lo half at column lo_out + n  (default N)
+  long long lo_res;    // fp16 residual is a hi/lo pair, lo at column lo_res + n (default: residual has no lo half)
 };
 
 int gemm_launch(const ConvGemm& d, cudaStream_t st);

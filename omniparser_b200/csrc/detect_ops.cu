@@ -27,12 +27,35 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 __device__ __forceinline__ uint4 ld8(const __half* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ void st8(__half* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+// fp16x3 ("parity-grade") maps keep every value as an fp16 hi/lo pair: hi at p, lo at p + lo (lo = channel count of the
+// owning buffer; 0 = plain fp16 map).  hi + lo is exact in fp32 (22 significant bits).
+__device__ __forceinline__ void ldf8(const __half* p, long long lo, float (&f)[8]) {
+  unpack8(ld8(p), f);
+  if (lo) {
+    float g[8];
+    unpack8(ld8(p + lo), g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] += g[k];
+  }
+}
+__device__ __forceinline__ void stf8(__half* p, long long lo, const float (&f)[8]) {
+  const uint4 hi = pack8(f);
+  st8(p, hi);
+  if (lo) {
+    float h[8], r[8];
+    unpack8(hi, h);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = f[k] - h[k];
+    st8(p + lo, pack8(r));
+  }
+}
 
 // ADown front half (common.py::ADown.forward): a = avg_pool2d(x, 2, 1) (size (H-1)x(W-1)); x1 = a[:, :C/2],
 // x2 = max_pool2d(a[:, C/2:], 3, 2, 1).  x1 is stored as an HxW map whose last row/column are zero, which is
 // exactly the zero padding the following 3x3 stride-2 pad-1 conv would see (keeps H, W even for the TMA view).
 __global__ void adown_pool_kernel(const __half* __restrict__ x, long long ldx, int B, int H, int W, int C,
-                                  __half* __restrict__ x1, long long ld1, __half* __restrict__ x2, long long ld2) {
+                                  __half* __restrict__ x1, long long ld1, __half* __restrict__ x2, long long ld2,
+                                  long long lox, long long lo1, long long lo2) {
   pdl_wait();   // PDL: inputs come from the previous kernel in the stream
   const int c8n = C / 16;   // vectors per half
   const long long n1 = (long long)B * H * W * c8n;
@@ -49,11 +72,11 @@ __global__ void adown_pool_kernel(const __half* __restrict__ x, long long ldx, i
       if (yy < H - 1 && xx < W - 1) {
         const __half* s = x + (((long long)b * H + yy) * W + xx) * ldx + cv * 8;
         float a[8], bq[8], c[8], d[8];
-        unpack8(ld8(s), a); unpack8(ld8(s + ldx), bq); unpack8(ld8(s + (long long)W * ldx), c); unpack8(ld8(s + (long long)(W + 1) * ldx), d);
+        ldf8(s, lox, a); ldf8(s + ldx, lox, bq); ldf8(s + (long long)W * ldx, lox, c); ldf8(s + (long long)(W + 1) * ldx, lox, d);
 #pragma unroll
         for (int k = 0; k < 8; ++k) o[k] = ((a[k] + bq[k]) + (c[k] + d[k])) * 0.25f;
       }
-      st8(x1 + (((long long)b * H + yy) * W + xx) * ld1 + cv * 8, pack8(o));
+      stf8(x1 + (((long long)b * H + yy) * W + xx) * ld1 + cv * 8, lo1, o);
     } else {
       const long long j = i - n1;
       const int cv = int(j % c8n);
@@ -72,19 +95,19 @@ __global__ void adown_pool_kernel(const __half* __restrict__ x, long long ldx, i
           if (xx < 0 || xx >= W - 1) continue;
           const __half* s = x + (((long long)b * H + yy) * W + xx) * ldx + C / 2 + cv * 8;
           float a[8], bq[8], c[8], d[8];
-          unpack8(ld8(s), a); unpack8(ld8(s + ldx), bq); unpack8(ld8(s + (long long)W * ldx), c); unpack8(ld8(s + (long long)(W + 1) * ldx), d);
+          ldf8(s, lox, a); ldf8(s + ldx, lox, bq); ldf8(s + (long long)W * ldx, lox, c); ldf8(s + (long long)(W + 1) * ldx, lox, d);
 #pragma unroll
           for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], ((a[k] + bq[k]) + (c[k] + d[k])) * 0.25f);
         }
       }
-      st8(x2 + (((long long)b * Ho + oy) * Wo + ox) * ld2 + cv * 8, pack8(m));
+      stf8(x2 + (((long long)b * Ho + oy) * Wo + ox) * ld2 + cv * 8, lo2, m);
     }
   }
 }
 
 // MaxPool2d(k, stride 1, pad k/2) on a channel slice (SPPELAN, k = 5).
 __global__ void maxpool_s1_kernel(const __half* __restrict__ x, long long ldx, int B, int H, int W, int C, int k,
-                                  __half* __restrict__ y, long long ldy) {
+                                  __half* __restrict__ y, long long ldy, long long lox, long long loy) {
   pdl_wait();   // PDL: inputs come from the previous kernel in the stream
   const int cvn = C / 8;
   const long long n = (long long)B * H * W * cvn;
@@ -95,6 +118,25 @@ __global__ void maxpool_s1_kernel(const __half* __restrict__ x, long long ldx, i
     const int xx = int(p % W); p /= W;
     const int yy = int(p % H);
     const int b = int(p / H);
+    if (lox) {   // hi/lo pairs: max over the exact fp32 values
+      float mf[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) mf[q] = -INFINITY;
+      for (int dy = -r; dy <= r; ++dy) {
+        const int sy = yy + dy;
+        if (sy < 0 || sy >= H) continue;
+        for (int dx = -r; dx <= r; ++dx) {
+          const int sx = xx + dx;
+          if (sx < 0 || sx >= W) continue;
+          float t[8];
+          ldf8(x + (((long long)b * H + sy) * W + sx) * ldx + cv * 8, lox, t);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) mf[q] = fmaxf(mf[q], t[q]);
+        }
+      }
+      stf8(y + (((long long)b * H + yy) * W + xx) * ldy + cv * 8, loy, mf);
+      continue;
+    }
     __half2 m[4];
     const __half2 ninf = __float2half2_rn(-INFINITY);
 #pragma unroll
@@ -121,7 +163,7 @@ __global__ void maxpool_s1_kernel(const __half* __restrict__ x, long long ldx, i
 
 // nn.Upsample(scale_factor=2, mode='nearest') into a channel slice.
 __global__ void upsample2x_kernel(const __half* __restrict__ x, long long ldx, int B, int H, int W, int C,
-                                  __half* __restrict__ y, long long ldy) {
+                                  __half* __restrict__ y, long long ldy, long long lox, long long loy) {
   pdl_wait();   // PDL: inputs come from the previous kernel in the stream
   const int cvn = C / 8;
   const int Ho = 2 * H, Wo = 2 * W;
@@ -134,15 +176,18 @@ __global__ void upsample2x_kernel(const __half* __restrict__ x, long long ldx, i
     const int b = int(p / Ho);
     st8(y + (((long long)b * Ho + yy) * Wo + xx) * ldy + cv * 8,
         ld8(x + (((long long)b * H + (yy >> 1)) * W + (xx >> 1)) * ldx + cv * 8));
+    if (lox)
+      st8(y + (((long long)b * Ho + yy) * Wo + xx) * ldy + loy + cv * 8,
+          ld8(x + (((long long)b * H + (yy >> 1)) * W + (xx >> 1)) * ldx + lox + cv * 8));
   }
 }
 
-struct FuseSrc { const __half* p; long long ld; int shift; int H, W; };
+struct FuseSrc { const __half* p; long long ld; int shift; int H, W; long long lo; };
 struct FuseArgs { FuseSrc s[5]; int n; };
 
 // CBFuse (common.py::CBFuse): out = sum_i nearest_upsample(src_i) + last, summed in that order in fp32.
 __global__ void cbfuse_kernel(FuseArgs a, const __half* __restrict__ last, long long ldl, int B, int H, int W, int C,
-                              __half* __restrict__ y, long long ldy) {
+                              __half* __restrict__ y, long long ldy, long long lol, long long loy) {
   pdl_wait();   // PDL: inputs come from the previous kernel in the stream
   const int cvn = C / 8;
   const long long n = (long long)B * H * W * cvn;
@@ -156,7 +201,7 @@ __global__ void cbfuse_kernel(FuseArgs a, const __half* __restrict__ last, long 
     bool first = true;
     for (int s = 0; s < a.n; ++s) {
       const FuseSrc& f = a.s[s];
-      unpack8(ld8(f.p + (((long long)b * f.H + (yy >> f.shift)) * f.W + (xx >> f.shift)) * f.ld + cv * 8), t);
+      ldf8(f.p + (((long long)b * f.H + (yy >> f.shift)) * f.W + (xx >> f.shift)) * f.ld + cv * 8, f.lo, t);
       if (first) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] = t[k];
@@ -166,10 +211,10 @@ __global__ void cbfuse_kernel(FuseArgs a, const __half* __restrict__ last, long 
         for (int k = 0; k < 8; ++k) acc[k] += t[k];
       }
     }
-    unpack8(ld8(last + (((long long)b * H + yy) * W + xx) * ldl + cv * 8), t);
+    ldf8(last + (((long long)b * H + yy) * W + xx) * ldl + cv * 8, lol, t);
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = first ? t[k] : acc[k] + t[k];
-    st8(y + (((long long)b * H + yy) * W + xx) * ldy + cv * 8, pack8(acc));
+    stf8(y + (((long long)b * H + yy) * W + xx) * ldy + cv * 8, loy, acc);
   }
 }
 
@@ -185,29 +230,47 @@ using namespace b2p;
 
 extern "C" {
 
+// `_x3` forms: every map is an fp16 hi/lo pair (lo plane `lo*` elements after the hi plane); the arithmetic is done
+// on the exact fp32 sums and the result is re-split.  lo == 0 everywhere reproduces the plain fp16 kernels.
+int b2p_adown_pool_x3(const void* x, long long ldx, int B, int H, int W, int C, void* x1, long long ld1, void* x2,
+                      long long ld2, long long lox, long long lo1, long long lo2, cudaStream_t st) {
+  if ((H & 1) || (W & 1) || (C % 16)) return set_error("adown_pool: H, W must be even and C a multiple of 16");
+  if ((lox != 0) != (lo1 != 0) || (lox != 0) != (lo2 != 0) || (lox | lo1 | lo2) % 8) return set_error("adown_pool: lo planes must be all set (8-aligned) or all 0");
+  const long long n = (long long)B * H * W * (C / 16) + (long long)B * (H / 2) * (W / 2) * (C / 16);
+  launch_pdl(adown_pool_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, (const __half*)x, ldx, B, H, W, C, (__half*)x1, ld1, (__half*)x2, ld2,
+             lox, lo1, lo2);
+  B2P_CHECK_LAUNCH();
+  return 0;
+}
 int b2p_adown_pool(const void* x, long long ldx, int B, int H, int W, int C, void* x1, long long ld1, void* x2,
                    long long ld2, cudaStream_t st) {
-  if ((H & 1) || (W & 1) || (C % 16)) return set_error("adown_pool: H, W must be even and C a multiple of 16");
-  const long long n = (long long)B * H * W * (C / 16) + (long long)B * (H / 2) * (W / 2) * (C / 16);
-  launch_pdl(adown_pool_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, (const __half*)x, ldx, B, H, W, C, (__half*)x1, ld1, (__half*)x2, ld2);
-  B2P_CHECK_LAUNCH();
-  return 0;
+  return b2p_adown_pool_x3(x, ldx, B, H, W, C, x1, ld1, x2, ld2, 0, 0, 0, st);
 }
 
-int b2p_maxpool_s1(const void* x, long long ldx, int B, int H, int W, int C, int k, void* y, long long ldy, cudaStream_t st) {
+int b2p_maxpool_s1_x3(const void* x, long long ldx, int B, int H, int W, int C, int k, void* y, long long ldy, long long lox,
+                      long long loy, cudaStream_t st) {
   if (C % 8) return set_error("maxpool_s1: C must be a multiple of 8");
+  if ((lox != 0) != (loy != 0) || (lox | loy) % 8) return set_error("maxpool_s1: lo planes must be both set (8-aligned) or both 0");
   const long long n = (long long)B * H * W * (C / 8);
-  launch_pdl(maxpool_s1_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, (const __half*)x, ldx, B, H, W, C, k, (__half*)y, ldy);
+  launch_pdl(maxpool_s1_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, (const __half*)x, ldx, B, H, W, C, k, (__half*)y, ldy, lox, loy);
   B2P_CHECK_LAUNCH();
   return 0;
 }
+int b2p_maxpool_s1(const void* x, long long ldx, int B, int H, int W, int C, int k, void* y, long long ldy, cudaStream_t st) {
+  return b2p_maxpool_s1_x3(x, ldx, B, H, W, C, k, y, ldy, 0, 0, st);
+}
 
-int b2p_upsample2x(const void* x, long long ldx, int B, int H, int W, int C, void* y, long long ldy, cudaStream_t st) {
+int b2p_upsample2x_x3(const void* x, long long ldx, int B, int H, int W, int C, void* y, long long ldy, long long lox,
+                      long long loy, cudaStream_t st) {
   if (C % 8) return set_error("upsample2x: C must be a multiple of 8");
+  if ((lox != 0) != (loy != 0) || (lox | loy) % 8) return set_error("upsample2x: lo planes must be both set (8-aligned) or both 0");
   const long long n = (long long)B * 4 * H * W * (C / 8);
-  launch_pdl(upsample2x_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, (const __half*)x, ldx, B, H, W, C, (__half*)y, ldy);
+  launch_pdl(upsample2x_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, (const __half*)x, ldx, B, H, W, C, (__half*)y, ldy, lox, loy);
   B2P_CHECK_LAUNCH();
   return 0;
+}
+int b2p_upsample2x(const void* x, long long ldx, int B, int H, int W, int C, void* y, long long ldy, cudaStream_t st) {
+  return b2p_upsample2x_x3(x, ldx, B, H, W, C, y, ldy, 0, 0, st);
 }
 
 // Explicit im2col of an NHWC fp16 map for a 3x3 / pad 1 conv: out[(b,yo,xo)][tap*C + c] = x[b][yo*s+ky-1][xo*s+kx-1][c] (0 outside).
@@ -250,10 +313,11 @@ int b2p_im2col3x3(const void* x, long long ldx, int B, int H, int W, int C, int 
 
 // srcs[i]: pointer to the selected CBLinear split (already offset to its first channel), lds[i] its pixel stride,
 // shifts[i] = log2(target size / source size).
-int b2p_cbfuse(int nsrc, const void* const* srcs, const long long* lds, const int* shifts, const void* last,
-               long long ldl, int B, int H, int W, int C, void* y, long long ldy, cudaStream_t st) {
+int b2p_cbfuse_x3(int nsrc, const void* const* srcs, const long long* lds, const int* shifts, const long long* los, const void* last,
+                  long long ldl, int B, int H, int W, int C, void* y, long long ldy, long long lol, long long loy, cudaStream_t st) {
   if (nsrc < 0 || nsrc > 5) return set_error("cbfuse: at most 5 upsampled sources");
   if (C % 8) return set_error("cbfuse: C must be a multiple of 8");
+  if ((lol != 0) != (loy != 0) || (lol | loy) % 8) return set_error("cbfuse: lo planes must be all set (8-aligned) or all 0");
   FuseArgs a{};
   a.n = nsrc;
   for (int i = 0; i < nsrc; ++i) {
@@ -262,11 +326,17 @@ int b2p_cbfuse(int nsrc, const void* const* srcs, const long long* lds, const in
     a.s[i].shift = shifts[i];
     a.s[i].H = H >> shifts[i];
     a.s[i].W = W >> shifts[i];
+    a.s[i].lo = los ? los[i] : 0;
+    if ((a.s[i].lo != 0) != (lol != 0) || a.s[i].lo % 8) return set_error("cbfuse: lo planes must be all set (8-aligned) or all 0");
   }
   const long long n = (long long)B * H * W * (C / 8);
-  launch_pdl(cbfuse_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, a, (const __half*)last, ldl, B, H, W, C, (__half*)y, ldy);
+  launch_pdl(cbfuse_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, a, (const __half*)last, ldl, B, H, W, C, (__half*)y, ldy, lol, loy);
   B2P_CHECK_LAUNCH();
   return 0;
+}
+int b2p_cbfuse(int nsrc, const void* const* srcs, const long long* lds, const int* shifts, const void* last,
+               long long ldl, int B, int H, int W, int C, void* y, long long ldy, cudaStream_t st) {
+  return b2p_cbfuse_x3(nsrc, srcs, lds, shifts, nullptr, last, ldl, B, H, W, C, y, ldy, 0, 0, st);
 }
 
 }  // extern "C"

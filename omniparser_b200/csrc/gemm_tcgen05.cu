@@ -47,7 +47,8 @@ struct GemmArgs {
   const void* res;
   long long ldr;
   int act, vec_ok;
-  int split;   // > 0: fp16 output in the fp16x3 operand layout [hi | lo] with logical width `split`
+  int split;   // > 0: fp16 output in the fp16x3 operand layout: hi at column n, lo at column split + n (lo-plane offset)
+  int res_lo;  // > 0: the fp16 residual is a hi/lo pair too, lo at column res_lo + n
   // fp16x3 operands: A rows are [hi(K) | lo(K)] (conv: per pixel [hi(Cin) | lo(Cin)]), W rows [hi | lo] likewise.  Each
   // pipeline stage holds A_hi, A_lo, B_hi, B_lo of ONE logical k-block (each loaded once) and the MMA warp issues the
   // three products hi*hi + hi*lo + lo*hi into the same fp32 accumulator.
@@ -143,6 +144,20 @@ __device__ __forceinline__ void epi_store16(const GemmArgs& g, const EpiCtx& e, 
             x[8 * q + 2 * k + 1] += f.y;
           }
         }
+        if (g.res_lo) {
+          const uint4* rl = reinterpret_cast<const uint4*>(e.resh + pix * g.ldr + g.res_lo + nb);
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const uint4 t = rl[q];
+            const __half2* hp = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = __half22float2(hp[k]);
+              x[8 * q + 2 * k] += f.x;
+              x[8 * q + 2 * k + 1] += f.y;
+            }
+          }
+        }
       }
     }
     if (g.out_f32) {
@@ -180,7 +195,10 @@ __device__ __forceinline__ void epi_store16(const GemmArgs& g, const EpiCtx& e, 
         if (g.bias) t += __ldg(g.bias + n);
         t = act_fn(t, g.act);
         if (valid) {
-          if (g.res) t += g.out_f32 ? e.resf[pix * g.ldr + n] : __half2float(e.resh[pix * g.ldr + n]);
+          if (g.res) {
+            t += g.out_f32 ? e.resf[pix * g.ldr + n] : __half2float(e.resh[pix * g.ldr + n]);
+            if (g.res_lo) t += __half2float(e.resh[pix * g.ldr + g.res_lo + n]);
+          }
           if (g.out_f32) e.outf[pix * g.ldc + n] = t;
           else {
             const __half hh = __float2half_rn(t);
@@ -897,7 +915,11 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
   if (d.x3 && d.bf16) return set_error("gemm: fp16x3 operands are fp16");
   const int xk = d.x3 ? 2 : 1;   // operand rows carry [hi | lo]
   g.x3 = d.x3 ? 1 : 0;
-  g.lo_a = kred; g.lo_b = kred;
+  // lo-plane offset of A: [hi(K) | lo(K)] rows by default; a channel slice of a wider [hi(Ctot) | lo(Ctot)] pixel passes Ctot
+  const long long lo_a = d.x3 ? (d.lo_a > 0 ? d.lo_a : (long long)kred) : 0;
+  const long long a_span = d.x3 ? lo_a + kred : (long long)kred;   // columns of A the tensor map must cover
+  if (d.x3 && (lo_a % 8 != 0 || lo_a < kred)) return set_error("gemm: fp16x3 lo-plane offset of A must be a multiple of 8 and >= K");
+  g.lo_a = int(lo_a); g.lo_b = kred;
   g.b_tap = xk * d.Cin;
   g.mode = halo ? 3 : d.mode;
   g.N = d.N;
@@ -905,9 +927,11 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
   g.cin = d.Cin;
   g.desc_hi = make_desc_hi(bk);
   g.out = d.out; g.ldc = d.ldc; g.out_f32 = d.out_f32; g.bias = d.bias; g.res = d.res; g.ldr = d.ldr; g.act = d.act;
-  g.split = (d.split_out && !d.out_f32) ? d.N : 0;
-  if (g.split && (d.N % 8)) return set_error("gemm: split (fp16x3) output needs N % 8 == 0");
-  if (g.split && d.ldc < 2 * (long long)d.N) return set_error("gemm: split (fp16x3) output rows are [hi(N) | lo(N)]: ldc must be >= 2N");
+  g.split = (d.split_out && !d.out_f32) ? int(d.lo_out > 0 ? d.lo_out : d.N) : 0;
+  if (g.split && ((d.N % 8) || (g.split % 8))) return set_error("gemm: split (fp16x3) output needs N % 8 == 0 and an 8-aligned lo-plane offset");
+  if (g.split && (g.split < d.N || d.ldc < (long long)g.split + d.N)) return set_error("gemm: split (fp16x3) output rows are [hi(N) .. | lo(N) ..]: ldc must be >= lo offset + N");
+  g.res_lo = (d.res && !d.out_f32 && d.lo_res > 0) ? int(d.lo_res) : 0;
+  if (g.res_lo % 8) return set_error("gemm: residual lo-plane offset must be a multiple of 8");
 
   if (d.mode == 0) {
     g.M = d.M;
@@ -915,15 +939,16 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
     g.num_kb = (d.K + bk - 1) / bk;
     g.m_tiles = (d.M + kTileM - 1) / kTileM;
     g.a_bytes = kTileM * bk * 2;
-    cuuint64_t dims[2] = {cuuint64_t(xk) * cuuint64_t(d.K), cuuint64_t(d.M)};
+    cuuint64_t dims[2] = {cuuint64_t(a_span), cuuint64_t(d.M)};
     cuuint64_t str[1] = {cuuint64_t(d.lda) * 2};
     cuuint32_t box[2] = {cuuint32_t(bk), cuuint32_t(kTileM)};
-    if (d.x3 && d.lda < 2 * (long long)d.K) return set_error("gemm: fp16x3 A rows are [hi(K) | lo(K)]: lda must be >= 2K");
+    if (d.x3 && d.lda < a_span) return set_error("gemm: fp16x3 A rows are [hi(K) .. | lo(K) ..]: lda must be >= lo offset + K");
     if (int e = encode(&tmA, d.bf16, 2, d.A, dims, str, box, bk)) return e;
   } else {
     const int s = (d.mode == 2) ? 2 : 1;
     if (s == 2 && ((d.H & 1) || (d.W & 1))) return set_error("conv3x3 s2: H and W must be even");
     if (d.lda % 8 != 0) return set_error("conv3x3: input pixel stride must be a multiple of 8 channels");
+    if (d.x3 && d.lda < a_span) return set_error("conv3x3: fp16x3 pixels are [hi(Cin) .. | lo(Cin) ..]: pixel stride must be >= lo offset + Cin");
     g.Ho = d.H / s; g.Wo = d.W / s; g.batch = d.batch;
     g.cin_blocks = d.Cin / bk;
     g.num_kb = 9 * g.cin_blocks;
@@ -971,14 +996,14 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
       cuuint32_t box[4] = {cuuint32_t(bk), cuuint32_t(btw + 2), cuuint32_t(bth + 2), 1};
       if (int e = encode(&tmA, d.bf16, 4, d.A, dims, str, box, bk)) return e;
     } else if (d.mode == 1) {
-      cuuint64_t dims[4] = {cuuint64_t(xk) * cuuint64_t(d.Cin), cuuint64_t(d.W), cuuint64_t(d.H), cuuint64_t(d.batch)};
+      cuuint64_t dims[4] = {cuuint64_t(a_span), cuuint64_t(d.W), cuuint64_t(d.H), cuuint64_t(d.batch)};
       cuuint64_t str[3] = {ld * 2, ld * 2 * d.W, ld * 2 * d.W * d.H};
       cuuint32_t box[4] = {cuuint32_t(bk), cuuint32_t(btw), cuuint32_t(bth), cuuint32_t(g.nb)};
       if (int e = encode(&tmA, d.bf16, 4, d.A, dims, str, box, bk)) return e;
     } else {
       // (x parity, channel) merged in dim0: element (n, 2*yo+py, 2*xo+px, c) at c + px*ld  (+ xo*2ld + py*W*ld + yo*2W*ld)
       g.ldpar = int(d.lda);   // producer adds px * ldA to the channel coordinate
-      cuuint64_t dims[5] = {ld + cuuint64_t(xk) * cuuint64_t(d.Cin), cuuint64_t(d.W / 2), 2, cuuint64_t(d.H / 2), cuuint64_t(d.batch)};
+      cuuint64_t dims[5] = {ld + cuuint64_t(a_span), cuuint64_t(d.W / 2), 2, cuuint64_t(d.H / 2), cuuint64_t(d.batch)};
       cuuint64_t str[4] = {ld * 4, ld * 2 * d.W, ld * 4 * d.W, ld * 2 * d.W * d.H};
       cuuint32_t box[5] = {cuuint32_t(bk), cuuint32_t(btw), 1, cuuint32_t(bth), cuuint32_t(g.nb)};
       if (int e = encode(&tmA, d.bf16, 5, d.A, dims, str, box, bk)) return e;

@@ -48,7 +48,12 @@ class B200YOLOv9Detector:
     CAND_CAP = 16384
 
     def __init__(self, model_path: Union[str, Path, None] = None, device: Union[str, torch.device, None] = None,
-                 state_dict: Dict[str, torch.Tensor] | None = None, use_graph: bool = True):
+                 state_dict: Dict[str, torch.Tensor] | None = None, use_graph: bool = True, precision: str | None = None):
+        """precision: "fp16" (default; the reference's own CUDA path is fp16 autocast, ref:util/yolov9.py:110-113) or
+        "fp16x3" (parity grade: reproduces the fp32 CPU path's kept boxes; ~3x the tensor work).  Default from the
+        environment variable B2P_DETECTOR_PRECISION."""
+        import os
+        self.precision = precision or os.environ.get("B2P_DETECTOR_PRECISION", "fp16")
         self.device = torch.device(device or "cuda")
         if self.device.type != "cuda" or not torch.cuda.is_available():
             # ref:util/yolov9.py:40-41 raises when CUDA is requested but unavailable; this build has no CPU path.
@@ -66,7 +71,7 @@ class B200YOLOv9Detector:
         if any(k.startswith("model.") for k in state_dict):
             state_dict = rename_upstream(state_dict)
         with torch.cuda.device(self.device):
-            self.weights = YoloWeights(state_dict, self.device)
+            self.weights = YoloWeights(state_dict, self.device, precision=self.precision)
         self.model = self.weights   # attribute the reference exposes (inspected in demo.ipynb)
         self.use_graph = use_graph
         self._plans: Dict[tuple, YoloPlan] = {}

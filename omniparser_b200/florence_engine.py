@@ -65,6 +65,8 @@ class FlorenceWeights:
         """precision: "fp16x3" (parity grade: fp16 hi/lo operand split, three tensor-core products per term,
         fp32 accumulate -> near-fp32 GEMMs) or "fp16" (single fp16 product; ~5e-3 logit drift)."""
         assert precision in ("fp16", "fp16x3")
+        from .yolo_engine import _TrackedState
+        sd = _TrackedState(sd)
         dev = device
         self.device = dev
         self.x3 = x3 = precision == "fp16x3"
@@ -143,6 +145,16 @@ class FlorenceWeights:
         for c in range(3):
             lut[c] = (np.arange(256, dtype=np.float32) * np.float32(1.0 / 255.0) - np.float32(IMAGENET_MEAN[c])) / np.float32(IMAGENET_STD[c])
         self.lut = torch.from_numpy(lut).to(dev)
+        # the whole checkpoint must have been consumed; tied copies of the embedding are checked, not silently dropped
+        shared = sd[L + "shared.weight"]
+        for tied in (L + "encoder.embed_tokens.weight", L + "decoder.embed_tokens.weight", "lm_head.weight"):
+            if tied in sd and not (sd[tied].shape == shared.shape and torch.equal(sd[tied], shared)):
+                raise ValueError(f"{tied} is not tied to the shared embedding: untied heads are not on this path")
+        if "final_logits_bias" in sd and bool((sd["final_logits_bias"] != 0).any()):
+            raise ValueError("non-zero final_logits_bias is not supported (Florence-2 checkpoints carry zeros)")
+        left = sorted(k for k in sd if k not in sd.used)
+        if left:
+            raise KeyError(f"Florence-2 checkpoint has {len(left)} parameters this loader does not know: {left[:8]} ...")
 
     def pos_table(self, h, w):
         col, row, temporal = self._pos_tables

@@ -52,11 +52,14 @@ def _p(t):
 
 @dataclass
 class Map:
-    """NHWC channel slice: element (b, y, x, c) lives at ptr + 2*(((b*H + y)*W + x)*ld + c) bytes (fp16)."""
+    """NHWC channel slice: element (b, y, x, c) lives at ptr + 2*(((b*H + y)*W + x)*ld + c) bytes (fp16).
+    ``lo`` > 0 (parity-grade fp16x3 maps): every value is an fp16 hi/lo pair, the lo half ``lo`` elements after the hi
+    half (pixel layout [hi(Ctot) | lo(Ctot)], so a channel slice keeps the same ``lo`` = Ctot)."""
 
     buf: torch.Tensor   # owning buffer [B, H, W, ld]
     c0: int
     C: int
+    lo: int = 0
 
     @property
     def B(self): return self.buf.shape[0]
@@ -71,14 +74,21 @@ class Map:
 
     def slice(self, c0, C_):
         assert 0 <= c0 and c0 + C_ <= self.C
-        return Map(self.buf, self.c0 + c0, C_)
+        return Map(self.buf, self.c0 + c0, C_, self.lo)
 
     def torch(self):
         """NCHW float32 copy (tests / debugging only)."""
-        return self.buf[..., self.c0:self.c0 + self.C].permute(0, 3, 1, 2).float()
+        t = self.buf[..., self.c0:self.c0 + self.C].permute(0, 3, 1, 2).float()
+        if self.lo:
+            t = t + self.buf[..., self.lo + self.c0:self.lo + self.c0 + self.C].permute(0, 3, 1, 2).float()
+        return t
 
 
-def new_map(B, H, W, Ctot, device, dtype=torch.float16):
+def new_map(B, H, W, Ctot, device, dtype=torch.float16, x3=False):
+    """x3: hi/lo-pair map, pixel layout [hi(Ctot) | lo(Ctot)]."""
+    if x3:
+        assert dtype == torch.float16 and Ctot % 8 == 0
+        return Map(torch.empty((B, H, W, 2 * Ctot), device=device, dtype=dtype), 0, Ctot, Ctot)
     return Map(torch.empty((B, H, W, Ctot), device=device, dtype=dtype), 0, Ctot)
 
 
@@ -109,13 +119,26 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias=None, res=None, act=ACT_NONE, 
 
 def conv1x1(x: Map, w, out: Map, bias=None, res: Map | None = None, act=ACT_SILU, out_f32=False):
     M = x.B * x.H * x.W
+    if x.lo:   # parity-grade hi/lo maps: fp16x3 operands, hi/lo output unless it is fp32
+        flags = FLAG_X3 | (FLAG_OUT_F32 if out_f32 else FLAG_SPLIT)
+        _lib.check(_lib.lib().b2p_gemm_planes(_p(x.ptr), x.ld, _p(w), M, out.C, x.C, _p(out.ptr), out.ld, _p(bias),
+                                              _p(res.ptr if res else None), res.ld if res else 0, act, flags, x.lo,
+                                              0 if out_f32 else out.lo, res.lo if res else 0, _stream()))
+        return
     gemm(x.ptr, x.ld, w, M, out.C, x.C, out.ptr, out.ld, bias, res.ptr if res else None, res.ld if res else 0, act,
          out_f32=out_f32)
 
 
 def conv3x3(x: Map, w, out: Map, stride=1, bias=None, res: Map | None = None, act=ACT_SILU, out_f32=False, bn_max=0,
             split=False, x3=False):
-    """x3: fp16x3 operands -- pixels [hi(Cin) | lo(Cin)] (x.C = 2*Cin), w [Cout][9][hi(Cin) | lo(Cin)]."""
+    """x3: fp16x3 operands -- pixels [hi(Cin) | lo(Cin)] (x.C = 2*Cin), w [Cout][9][hi(Cin) | lo(Cin)].
+    Hi/lo-pair maps (``x.lo``): the same operand mode with explicit lo planes (x.C stays the logical Cin)."""
+    if x.lo:
+        flags = FLAG_X3 | (FLAG_OUT_F32 if out_f32 else FLAG_SPLIT) | (bn_max << 8)
+        _lib.check(_lib.lib().b2p_conv3x3_planes(_p(x.ptr), x.ld, x.B, x.H, x.W, x.C, stride, _p(w), out.C, _p(out.ptr), out.ld,
+                                                 _p(bias), _p(res.ptr if res else None), res.ld if res else 0, act, flags,
+                                                 x.lo, 0 if out_f32 else out.lo, res.lo if res else 0, _stream()))
+        return
     flags = (FLAG_OUT_F32 if out_f32 else 0) | (FLAG_SPLIT if split else 0) | (FLAG_X3 if x3 else 0) | (bn_max << 8)
     _lib.check(_lib.lib().b2p_conv3x3(_p(x.ptr), x.ld, x.B, x.H, x.W, x.C // 2 if x3 else x.C, stride, _p(w), out.C, _p(out.ptr), out.ld,
                                       _p(bias), _p(res.ptr if res else None), res.ld if res else 0, act, flags,
@@ -123,15 +146,25 @@ def conv3x3(x: Map, w, out: Map, stride=1, bias=None, res: Map | None = None, ac
 
 
 def adown_pool(x: Map, x1: Map, x2: Map):
+    if x.lo:
+        _lib.check(_lib.lib().b2p_adown_pool_x3(_p(x.ptr), x.ld, x.B, x.H, x.W, x.C, _p(x1.ptr), x1.ld, _p(x2.ptr), x2.ld,
+                                                x.lo, x1.lo, x2.lo, _stream()))
+        return
     _lib.check(_lib.lib().b2p_adown_pool(_p(x.ptr), x.ld, x.B, x.H, x.W, x.C, _p(x1.ptr), x1.ld, _p(x2.ptr), x2.ld,
                                          _stream()))
 
 
 def maxpool_s1(x: Map, y: Map, k=5):
+    if x.lo:
+        _lib.check(_lib.lib().b2p_maxpool_s1_x3(_p(x.ptr), x.ld, x.B, x.H, x.W, x.C, k, _p(y.ptr), y.ld, x.lo, y.lo, _stream()))
+        return
     _lib.check(_lib.lib().b2p_maxpool_s1(_p(x.ptr), x.ld, x.B, x.H, x.W, x.C, k, _p(y.ptr), y.ld, _stream()))
 
 
 def upsample2x(x: Map, y: Map):
+    if x.lo:
+        _lib.check(_lib.lib().b2p_upsample2x_x3(_p(x.ptr), x.ld, x.B, x.H, x.W, x.C, _p(y.ptr), y.ld, x.lo, y.lo, _stream()))
+        return
     _lib.check(_lib.lib().b2p_upsample2x(_p(x.ptr), x.ld, x.B, x.H, x.W, x.C, _p(y.ptr), y.ld, _stream()))
 
 
@@ -146,6 +179,11 @@ def cbfuse(srcs: list[Map], last: Map, out: Map):
     ptrs = (C.c_void_p * max(n, 1))(*[s.ptr for s in srcs])
     lds = (C.c_longlong * max(n, 1))(*[s.ld for s in srcs])
     shifts = (C.c_int * max(n, 1))(*[(last.H // s.H).bit_length() - 1 for s in srcs])
+    if last.lo:
+        los = (C.c_longlong * max(n, 1))(*[s.lo for s in srcs])
+        _lib.check(_lib.lib().b2p_cbfuse_x3(n, ptrs, lds, shifts, los, _p(last.ptr), last.ld, last.B, last.H, last.W, last.C,
+                                            _p(out.ptr), out.ld, last.lo, out.lo, _stream()))
+        return
     _lib.check(_lib.lib().b2p_cbfuse(n, ptrs, lds, shifts, _p(last.ptr), last.ld, last.B, last.H, last.W, last.C,
                                      _p(out.ptr), out.ld, _stream()))
 

@@ -22,35 +22,45 @@ import torch
 from PIL import Image
 
 from . import host_glue, ops
-from .caption import (CAPTION_PROMPT_IDS, B200Florence2Model, B200Florence2Processor, load_florence_state)
+from .caption import (CAPTION_PROMPT_IDS, B200Florence2Model, B200Florence2Processor, find_tokenizer_dir, load_florence_state,
+                      load_tokenizer)
 from .detector import B200YOLOv9Detector
 
 
-def get_yolo_model(model_path=None, device=None):
-    """ref:util/utils.py:72-85.  Only the YOLOv9-E ``icon_detect_v3`` branch exists here (no ultralytics fallback)."""
+def get_yolo_model(model_path=None, device=None, precision=None):
+    """ref:util/utils.py:72-85.  Only the YOLOv9-E ``icon_detect_v3`` branch exists here (no ultralytics fallback).
+    ``precision`` (extension): "fp16" (default, the reference's CUDA autocast precision) or "fp16x3" (parity grade: the
+    fp32 CPU path's boxes); default from B2P_DETECTOR_PRECISION."""
     if model_path is None:
         local = Path(__file__).resolve().parents[1] / "weights/icon_detect_v3/model.pt"
         if local.is_file():
             model_path = local
     if model_path is None:
         raise FileNotFoundError("weights/icon_detect_v3/model.pt not found and no network access: pass model_path")
-    return B200YOLOv9Detector(model_path=model_path, device=device)
+    return B200YOLOv9Detector(model_path=model_path, device=device, precision=precision)
 
 
 def get_caption_model_processor(model_name, model_name_or_path="microsoft/Florence-2-base", device=None,
-                                precision: str = "fp16x3"):
+                                precision: str = "fp16x3", tokenizer_path=None, allow_id_captions: Optional[bool] = None):
     """ref:util/utils.py:48-69 (florence2 branch).  ``model_name_or_path`` must be a local directory holding
-    ``model.safetensors`` (+ ``generation_config.json``; optionally ``vocab.json``/``merges.txt`` for strings)."""
+    ``model.safetensors`` (+ ``generation_config.json``).  The detokeniser (the reference takes it from the hub id
+    ``microsoft/Florence-2-base``, :64) is looked up offline by :func:`caption.find_tokenizer_dir`; if none is found
+    this raises -- captions made of id tags (``<25924> <13>``) are only produced when the caller opts in with
+    ``allow_id_captions=True`` / B2P_ALLOW_ID_CAPTIONS=1."""
     if model_name != "florence2":
         raise NotImplementedError(f"caption model {model_name!r}: only the florence2 branch is on the B200 hot path")
     if not device:
         device = "cuda"
+    if allow_id_captions is None:
+        allow_id_captions = bool(os.environ.get("B2P_ALLOW_ID_CAPTIONS"))
+    tdir = find_tokenizer_dir(model_name_or_path, tokenizer_path)
+    if tdir is None and not allow_id_captions:
+        raise FileNotFoundError(
+            "no Florence-2 tokenizer files (tokenizer.json or vocab.json + merges.txt) found for the caption processor: "
+            "pass tokenizer_path=, set B2P_FLORENCE_PROCESSOR, or put them next to the weights "
+            "(allow_id_captions=True returns token-id tags instead of strings)")
     sd, gen = load_florence_state(model_name_or_path)
-    tok = None
-    p = Path(model_name_or_path)
-    if (p / "vocab.json").is_file() and (p / "merges.txt").is_file():
-        from transformers import BartTokenizer
-        tok = BartTokenizer(str(p / "vocab.json"), str(p / "merges.txt"))
+    tok = load_tokenizer(tdir) if tdir is not None else None
     model = B200Florence2Model(sd, device, gen, precision, name_or_path=str(model_name_or_path))
     if "florence" not in model.config.name_or_path.lower():
         model.config.name_or_path = "florence2:" + model.config.name_or_path   # ref:util/utils.py:109 looks for 'florence'

@@ -24,9 +24,36 @@ BN_EPS = 1e-3
 
 
 # --------------------------------------------------------------------------------------------- weight folding
+class _TrackedState(dict):
+    """state_dict that remembers which keys were read, so a loader can prove it consumed the whole archive."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.used = set()
+
+    def __getitem__(self, k):
+        self.used.add(k)
+        return super().__getitem__(k)
+
+    def get(self, k, default=None):
+        if k in self:
+            return self[k]
+        return default
+
+
+# keys of an upstream archive that carry no learned arithmetic of the deployed graph
+_IGNORED_SUFFIXES = ("num_batches_tracked", "anchors", "strides")
+_DFL_SUFFIXES = ("dfl.conv.weight", "detect.proj")   # the DFL expectation weights: must be arange(reg_max), checked
+
+
 def _fold_conv_bn(sd, prefix):
-    """conv (no bias) + BatchNorm(eval) -> (weight fp32 [Co,Ci,k,k], bias fp32 [Co])."""
+    """conv (no bias) + BatchNorm(eval) -> (weight fp32 [Co,Ci,k,k], bias fp32 [Co]).  An archive exported with
+    conv+BN already fused (no ``.bn.*`` keys, ``.conv.bias`` present) is taken as is."""
     w = sd[prefix + ".conv.weight"].float()
+    if prefix + ".bn.weight" not in sd:
+        if prefix + ".conv.bias" not in sd:
+            raise KeyError(f"{prefix}: neither BatchNorm parameters nor a fused conv bias in the archive")
+        return w, sd[prefix + ".conv.bias"].float()
     g, b = sd[prefix + ".bn.weight"].float(), sd[prefix + ".bn.bias"].float()
     mu, var = sd[prefix + ".bn.running_mean"].float(), sd[prefix + ".bn.running_var"].float()
     s = g / torch.sqrt(var + BN_EPS)
@@ -34,6 +61,9 @@ def _fold_conv_bn(sd, prefix):
 
 
 def _fold_repconv(sd, prefix):
+    if prefix + ".conv1.conv.weight" not in sd and prefix + ".conv.weight" in sd:
+        # archive exported after RepConvN.fuse_convs(): one re-parameterised 3x3 conv with bias
+        return sd[prefix + ".conv.weight"].float(), sd[prefix + ".conv.bias"].float()
     w3, b3 = _fold_conv_bn(sd, prefix + ".conv1")
     w1, b1 = _fold_conv_bn(sd, prefix + ".conv2")
     w = w3.clone()
@@ -52,22 +82,33 @@ def _dense_from_grouped(w, groups):
     return d
 
 
-def _pack(w, device, kpad=None):
-    """[Co,Ci,kh,kw] -> fp16 [Co, kh*kw*Ci] ordered (ky,kx,c), optionally zero-padded along K."""
+def _pack(w, device, kpad=None, x3=False):
+    """[Co,Ci,kh,kw] -> fp16 [Co, kh*kw*Ci] ordered (ky,kx,c), optionally zero-padded along K.
+    x3 (parity-grade fp16x3 operands): every tap becomes [hi(Ci) | lo(Ci)], hi = fp16(w), lo = fp16(w - hi); with
+    ``kpad`` (the im2col'ed stem) the whole row is [hi(kpad) | lo(kpad)]."""
     co = w.shape[0]
-    m = w.permute(0, 2, 3, 1).reshape(co, -1)
-    if kpad is not None and kpad > m.shape[1]:
-        m = torch.cat([m, torch.zeros(co, kpad - m.shape[1], dtype=m.dtype)], 1)
-    return m.contiguous().to(device=device, dtype=torch.float16)
+    t = w.permute(0, 2, 3, 1).float()
+    if not x3:
+        m = t.reshape(co, -1)
+        if kpad is not None and kpad > m.shape[1]:
+            m = torch.cat([m, torch.zeros(co, kpad - m.shape[1], dtype=m.dtype)], 1)
+        return m.contiguous().to(device=device, dtype=torch.float16)
+    hi = t.half()
+    lo = (t - hi.float()).half()
+    if kpad is not None:
+        mh, ml = hi.reshape(co, -1), lo.reshape(co, -1)
+        z = torch.zeros(co, kpad - mh.shape[1], dtype=torch.float16)
+        return torch.cat([mh, z, ml, z], 1).contiguous().to(device)
+    return torch.cat([hi, lo], 3).reshape(co, -1).contiguous().to(device)
 
 
 class _W:
     """Packed weights of one fused conv: fp16 K-major matrix + fp32 bias."""
 
-    def __init__(self, w, b, device, kpad=None):
+    def __init__(self, w, b, device, kpad=None, x3=False):
         self.k = w.shape[2]
         self.cout, self.cin = w.shape[0], w.shape[1]
-        self.w = _pack(w, device, kpad)
+        self.w = _pack(w, device, kpad, x3)
         self.b = b.contiguous().to(device=device, dtype=torch.float32)
         self.flops_per_pixel = 2 * w.shape[0] * w.shape[1] * w.shape[2] * w.shape[3]
 
@@ -76,15 +117,25 @@ class YoloWeights:
     """Folded + packed parameters, from a state_dict in oracle/yolov9e.py naming (``l{N}.…``, ``detect.…``);
     upstream archives name the same tensors ``model.{N}.…`` / ``model.42.…`` (see :func:`rename_upstream`)."""
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device, nc: int | None = None):
-        sd = {k: v.detach().cpu() for k, v in state_dict.items()}
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device, nc: int | None = None, precision: str = "fp16"):
+        """precision "fp16": fp16 operands / fp16 feature maps, fp32 accumulate (what the reference's CUDA path does under
+        autocast, ref:util/yolov9.py:110-113).  "fp16x3": parity grade -- every feature map is an fp16 hi/lo pair and every
+        conv issues hi*hi + hi*lo + lo*hi into the fp32 accumulator (22-bit operands), to reproduce the fp32 CPU path
+        (ref:util/yolov9.py:114 nullcontext branch) box for box."""
+        assert precision in ("fp16", "fp16x3")
+        sd = _TrackedState({k: v.detach().cpu() for k, v in state_dict.items()})
         self.device = device
+        self.precision = precision
+        self.x3 = x3 = precision == "fp16x3"
+
+        def _Wx(w, b, device, kpad=None):   # packs in the operand mode of this weight set
+            return _W(w, b, device, kpad, x3)
         self.nc = nc if nc is not None else sd["detect.cv3.0.2.weight"].shape[0]
         W = {}
 
         def conv(name):
             w, b = _fold_conv_bn(sd, name)
-            W[name] = _W(w, b, device)
+            W[name] = _Wx(w, b, device)
 
         def elan(name):
             conv(name + ".cv1")
@@ -92,11 +143,11 @@ class YoloWeights:
                 p = f"{name}.{br}.0"   # RepNCSP
                 w1, b1 = _fold_conv_bn(sd, p + ".cv1")
                 w2, b2 = _fold_conv_bn(sd, p + ".cv2")
-                W[p + ".cv12"] = _W(torch.cat([w1, w2], 0), torch.cat([b1, b2], 0), device)   # merged 1x1 pair
+                W[p + ".cv12"] = _Wx(torch.cat([w1, w2], 0), torch.cat([b1, b2], 0), device)   # merged 1x1 pair
                 i = 0
                 while f"{p}.m.{i}.cv2.conv.weight" in sd:
                     w, b = _fold_repconv(sd, f"{p}.m.{i}.cv1")
-                    W[f"{p}.m.{i}.cv1"] = _W(w, b, device)
+                    W[f"{p}.m.{i}.cv1"] = _Wx(w, b, device)
                     conv(f"{p}.m.{i}.cv2")
                     i += 1
                 W[p + ".n"] = i
@@ -109,12 +160,12 @@ class YoloWeights:
             conv(name + ".cv2")
 
         def cbl(name):
-            W[name] = _W(sd[name + ".conv.weight"].float(), sd[name + ".conv.bias"].float(), device)
+            W[name] = _Wx(sd[name + ".conv.weight"].float(), sd[name + ".conv.bias"].float(), device)
 
         # stem: l1 and l15 both read the image -> one GEMM with N = 128, K = 27 padded to 32
         w1, b1 = _fold_conv_bn(sd, "l1")
         w15, b15 = _fold_conv_bn(sd, "l15")
-        W["stem"] = _W(torch.cat([w1, w15], 0), torch.cat([b1, b15], 0), device, kpad=32)
+        W["stem"] = _Wx(torch.cat([w1, w15], 0), torch.cat([b1, b15], 0), device, kpad=32)
         conv("l2"); conv("l17")
         for n in (3, 5, 7, 9, 19, 22, 25, 28, 32, 35, 38, 41):
             elan(f"l{n}")
@@ -126,26 +177,41 @@ class YoloWeights:
         for i in range(3):
             wb, bb = _fold_conv_bn(sd, f"detect.cv2.{i}.0")
             wc, bc = _fold_conv_bn(sd, f"detect.cv3.{i}.0")
-            W[f"head{i}.first"] = _W(torch.cat([wb, wc], 0), torch.cat([bb, bc], 0), device)
+            W[f"head{i}.first"] = _Wx(torch.cat([wb, wc], 0), torch.cat([bb, bc], 0), device)
             wg, bg = _fold_conv_bn(sd, f"detect.cv2.{i}.1")
-            W[f"head{i}.box1"] = _W(_dense_from_grouped(wg, 4), bg, device)
-            W[f"head{i}.box2"] = _W(_dense_from_grouped(sd[f"detect.cv2.{i}.2.weight"].float(), 4),
+            W[f"head{i}.box1"] = _Wx(_dense_from_grouped(wg, 4), bg, device)
+            W[f"head{i}.box2"] = _Wx(_dense_from_grouped(sd[f"detect.cv2.{i}.2.weight"].float(), 4),
                                     sd[f"detect.cv2.{i}.2.bias"].float(), device)
             conv(f"detect.cv3.{i}.1")
-            W[f"head{i}.cls2"] = _W(sd[f"detect.cv3.{i}.2.weight"].float(), sd[f"detect.cv3.{i}.2.bias"].float(), device)
+            W[f"head{i}.cls2"] = _Wx(sd[f"detect.cv3.{i}.2.weight"].float(), sd[f"detect.cv3.{i}.2.bias"].float(), device)
             self.c_box = wb.shape[0]
             self.c_cls = wc.shape[0]
         self.W = W
+        # every tensor of the archive must have been consumed (a mis-named or unexpected parameter is an error, not a
+        # silently different network), and the shapes must chain (checked layer by layer in YoloPlan._c1/_c3)
+        for k in sd:
+            if k.endswith(_DFL_SUFFIXES):   # the decode kernel hard-codes softmax(16 bins) . arange(16) (ref:util/yolov9.py head)
+                t = sd[k].float().flatten()
+                if t.numel() != 16 or not torch.equal(t, torch.arange(16.0)):
+                    raise ValueError(f"{k}: DFL projection is not arange(16); this build's decode kernel assumes reg_max = 16")
+        left = sorted(k for k in sd if k not in sd.used and not k.endswith(_IGNORED_SUFFIXES))
+        if left:
+            raise KeyError(f"YOLOv9-E archive has {len(left)} parameters this loader does not know: {left[:8]} ...")
 
 
 def rename_upstream(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
-    """Map WongKinYiu/yolov9 parameter names (``model.N.*``; detect head = ``model.42``) to oracle naming."""
+    """Map WongKinYiu/yolov9 parameter names (``model.N.*``; the detect head is the LAST module, ``model.42`` in
+    yolov9-e) to the ``l{N}.`` / ``detect.`` naming used here.  Keys outside ``model.*`` are an error."""
+    idx = sorted({int(k.split(".")[1]) for k in sd if k.startswith("model.") and k.split(".")[1].isdigit()})
+    if not idx:
+        raise KeyError("no model.N.* parameters in the archive")
+    head = idx[-1]
     out = {}
     for k, v in sd.items():
         if not k.startswith("model."):
-            continue
+            raise KeyError(f"unexpected parameter outside model.*: {k}")
         n, rest = k[len("model."):].split(".", 1)
-        out[("detect." if n == "42" else f"l{n}.") + rest] = v
+        out[("detect." if int(n) == head else f"l{n}.") + rest] = v
     return out
 
 
@@ -159,6 +225,7 @@ class YoloPlan:
         self.dev = weights.device
         self.ops: List = []
         self.flops = 0
+        self.x3 = weights.x3
         self.taps: Dict[str, Map] = {}
         self.canvas = torch.empty((B, Hc, Wc, 3), dtype=torch.uint8, device=self.dev)
         lut = (np.arange(256, dtype=np.float32) / np.float32(255.0))[None].repeat(3, 0)   # ref:util/yolov9.py:85
@@ -169,7 +236,7 @@ class YoloPlan:
 
     # -- helpers that append launches
     def _fm(self, C, H, W):
-        return ops.new_map(self.B, H, W, C, self.dev)
+        return ops.new_map(self.B, H, W, C, self.dev, x3=self.x3)
 
     def _c1(self, x: Map, wname, out: Map, act=ACT_SILU, out_f32=False):
         w = self.wts.W[wname]
@@ -222,12 +289,14 @@ class YoloPlan:
         B, H1, W1 = self.B, self.Hc // 2, self.Wc // 2
         wts = self.wts
         # stem
-        self.A0 = torch.empty((B * H1 * W1, 32), dtype=torch.float16, device=self.dev)
-        self.ops.append(lambda: ops.im2col_u8(self.canvas, B, self.Hc, self.Wc, 3, 2, 1, 32, self.lut, self.A0))
+        KX = 2 if self.x3 else 1
+        self.A0 = torch.empty((B * H1 * W1, KX * 32), dtype=torch.float16, device=self.dev)
+        self.ops.append(lambda: ops.im2col_u8(self.canvas, B, self.Hc, self.Wc, 3, 2, 1, 32, self.lut, self.A0, split=self.x3))
         S = self._fm(128, H1, W1)
         ws = wts.W["stem"]
         self.flops += 2 * 128 * 27 * B * H1 * W1
-        self.ops.append(lambda: ops.gemm(self.A0, 32, ws.w, B * H1 * W1, 128, 32, S.ptr, 128, ws.b, None, 0, ACT_SILU))
+        A0m = ops.Map(self.A0.view(B, H1, W1, KX * 32), 0, 32, 32 if self.x3 else 0)   # im2col rows as a 1x1 "map"
+        self.ops.append(lambda: ops.conv1x1(A0m, ws.w, S, ws.b, None, ACT_SILU))
         x1, x15 = S.slice(0, 64), S.slice(64, 64)
         H2, W2, H3, W3, H4, W4, H5, W5 = H1 // 2, W1 // 2, H1 // 4, W1 // 4, H1 // 8, W1 // 8, H1 // 16, W1 // 16
         x2 = self._fm(128, H2, W2); self._c3(x1, "l2", x2, stride=2)

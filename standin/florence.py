@@ -84,3 +84,54 @@ def input_ids_for(n_crops: int, n_image_tokens: int = 5) -> torch.Tensor:
     """image placeholders first, then the prompt (hf:models/florence2/processing_florence2.py:182-187)."""
     row = [IMAGE_TOKEN] * n_image_tokens + PROMPT_IDS
     return torch.tensor([row] * n_crops, dtype=torch.long)
+
+
+
+
+def to_remote_code_names(sd):
+    """Native ``transformers`` Florence-2 parameter names -> the microsoft/Florence-2 remote-code names (SURVEY.md §8c,
+    recalled layout) a real ``icon_caption_florence/model.safetensors`` uses.  Fixture for the loader tests: the inverse
+    of ``omniparser_b200.caption.rename_remote_code``, written independently of it."""
+    out = {}
+    for k, v in sd.items():
+        if k.startswith("model.vision_tower.convs."):
+            nk = k[len("model."):].replace(".conv.weight", ".proj.weight").replace(".conv.bias", ".proj.bias")
+        elif k.startswith("model.vision_tower.blocks."):
+            nk = k[len("model."):]
+            kind = "window_attn" if ".spatial_block." in nk else "channel_attn"
+            nk = nk.replace(".norm1.", f".{kind}.norm.").replace(".norm2.", ".ffn.norm.")
+            nk = nk.replace(f".{kind}.qkv.", f".{kind}.fn.qkv.").replace(f".{kind}.proj.", f".{kind}.fn.proj.")
+            nk = nk.replace(".conv1.", ".conv1.fn.dw.").replace(".conv2.", ".conv2.fn.dw.")
+            nk = nk.replace(".ffn.fc1.", ".ffn.fn.net.fc1.").replace(".ffn.fc2.", ".ffn.fn.net.fc2.")
+        elif k == "model.multi_modal_projector.image_projection.weight":
+            nk, v = "image_projection", v.t().contiguous()
+        elif k.startswith("model.multi_modal_projector.image_proj_norm."):
+            nk = k[len("model.multi_modal_projector."):]
+        elif k.startswith("model.multi_modal_projector.image_position_embed."):
+            nk = "image_pos_embed." + k[len("model.multi_modal_projector.image_position_embed."):]
+        elif k.startswith("model.multi_modal_projector.visual_temporal_embed."):
+            nk = k[len("model.multi_modal_projector."):]
+        elif k.startswith("model.language_model."):
+            nk = "language_model.model." + k[len("model.language_model."):]
+        elif k == "lm_head.weight":
+            nk = "language_model.lm_head.weight"
+        else:
+            raise KeyError(k)
+        out[nk] = v
+    out["language_model.final_logits_bias"] = torch.zeros((1, sd["lm_head.weight"].shape[0]))
+    return out
+
+
+def export_remote_code_dir(model, path) -> None:
+    """Write ``model.safetensors`` (remote-code names) + ``config.json`` + ``generation_config.json`` the way
+    ``weights/icon_caption_florence`` is laid out (ref:README.md:45-46)."""
+    import json
+    import os
+    from safetensors.torch import save_file
+    os.makedirs(str(path), exist_ok=True)
+    sd = {k: v.detach().clone().contiguous() for k, v in to_remote_code_names(model.state_dict()).items()}
+    save_file(sd, os.path.join(str(path), "model.safetensors"))
+    with open(os.path.join(str(path), "generation_config.json"), "w") as f:
+        json.dump(dict(GEN, num_beams=3, early_stopping=True), f)
+    with open(os.path.join(str(path), "config.json"), "w") as f:
+        json.dump({"model_type": "florence2", "text_config": {"decoder_start_token_id": 2}}, f)

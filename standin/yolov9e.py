@@ -289,3 +289,28 @@ def export_torchscript(model: YOLOv9E, path, example_hw=(64, 64)) -> None:
     with torch.no_grad():
         ts = torch.jit.trace(model, ex, check_trace=False)
     ts.save(str(path))
+
+
+class UpstreamNamedYOLOv9E(nn.Module):
+    """The same graph with its parameters registered under the names of an upstream WongKinYiu/yolov9 archive
+    (``model.N.*``, detect head = ``model.42``): the fixture for the loader path the real
+    ``weights/icon_detect_v3/model.pt`` takes (ref:util/yolov9.py:50 ``torch.jit.load``)."""
+
+    def __init__(self, m: YOLOv9E):
+        super().__init__()
+        layers = [nn.Identity() for _ in range(43)]
+        for n in range(1, 42):
+            if hasattr(m, f"l{n}"):
+                layers[n] = getattr(m, f"l{n}")
+        layers[42] = m.detect
+        self.model = nn.ModuleList(layers)
+
+    def __getattr__(self, name):   # l{N} / detect resolve to model[N], so YOLOv9E.forward runs unchanged
+        if name != "model":
+            if name.startswith("l") and name[1:].isdigit():
+                return self.model[int(name[1:])]
+            if name == "detect":
+                return self.model[42]
+        return super().__getattr__(name)
+
+    forward = YOLOv9E.forward

@@ -25,7 +25,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/b200parse.h but not exported"
     assert set(_lib.PROTOTYPES) == set(names), set(_lib.PROTOTYPES) ^ set(names)
-    assert _lib.lib().b2p_abi_version() == 1
+    assert _lib.lib().b2p_abi_version() == 2
 
 
 def test_no_libcuda_link_dependency():

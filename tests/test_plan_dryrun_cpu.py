@@ -62,6 +62,30 @@ def _check(name, a):
         assert stride in (1, 2) and Cin % 32 == 0 and ld_in >= (2 if x3 else 1) * Cin and ldc >= Cout
         if stride == 2:
             assert H % 2 == 0 and W % 2 == 0
+    elif name == "b2p_gemm_planes":
+        _A, lda, _B, M, N, K, _out, ldc, _bias, _res, ldr, act, flags, lo_a, lo_out, lo_res, _st = a
+        x3, split, f32 = bool(flags & 8), bool(flags & 4), bool(flags & 2)
+        assert x3 and M > 0 and N > 0 and K % 32 == 0 and (split != f32)
+        assert lo_a % 8 == 0 and lo_a >= K and lda >= lo_a + K, ("A planes", lda, lo_a, K)
+        if split:
+            assert N % 8 == 0 and lo_out % 8 == 0 and lo_out >= N and ldc >= lo_out + N, ("out planes", ldc, lo_out, N)
+        assert lo_res % 8 == 0 and (lo_res == 0 or _res)
+    elif name == "b2p_conv3x3_planes":
+        _in, ld_in, batch, H, W, Cin, stride, _w, Cout, _out, ldc, _bias, _res, ldr, act, flags, lo_a, lo_out, lo_res, _st = a
+        x3, split, f32 = bool(flags & 8), bool(flags & 4), bool(flags & 2)
+        assert x3 and stride in (1, 2) and Cin % 32 == 0 and (split != f32)
+        assert lo_a % 8 == 0 and lo_a >= Cin and ld_in >= lo_a + Cin
+        if split:
+            assert Cout % 8 == 0 and lo_out >= Cout and ldc >= lo_out + Cout
+        if _res:
+            assert lo_res > 0 and ldr >= lo_res + Cout
+        if stride == 2:
+            assert H % 2 == 0 and W % 2 == 0
+    elif name in ("b2p_adown_pool_x3", "b2p_maxpool_s1_x3", "b2p_upsample2x_x3"):
+        n_lo = 3 if name == "b2p_adown_pool_x3" else 2
+        assert all(v > 0 and v % 8 == 0 for v in a[-1 - n_lo:-1]), (name, a[-1 - n_lo:-1])
+    elif name == "b2p_cbfuse_x3":
+        assert a[-3] > 0 and a[-2] > 0
     elif name == "b2p_layernorm":
         _x, ldx, _g, _b, eps, T, Cc, o16, ld16, o32, ld32, split, _st = a
         assert ldx >= Cc and (o16 is None or ld16 >= (2 if split else 1) * Cc) and (o32 is None or ld32 >= Cc)
@@ -149,6 +173,21 @@ def test_yolo_plan(rec):
     assert len(names) == plan.n_launches == 252
     assert names.count("b2p_gemm") + names.count("b2p_conv3x3") == 233   # the figure quoted in bench.py / DESIGN.md
     assert all(not (c[1][12] & 8) for c in rec.calls if c[0] == "b2p_gemm")      # detector: plain fp16 operands
+
+
+def test_yolo_plan_parity_mode(rec):
+    """precision="fp16x3": same launch sequence, every conv through the `_planes` entry points with hi/lo maps"""
+    from omniparser_b200.yolo_engine import YoloPlan, YoloWeights
+    from standin.yolo_weights import yolo_standin
+    w = YoloWeights(yolo_standin(0).state_dict(), torch.device("cpu"), precision="fp16x3")
+    plan = YoloPlan(w, 1, 384, 640, use_graph=False)
+    plan.run()
+    names = [c[0] for c in rec.calls]
+    assert len(names) == plan.n_launches == 252
+    assert names.count("b2p_gemm_planes") + names.count("b2p_conv3x3_planes") == 233
+    assert "b2p_gemm" not in names and "b2p_conv3x3" not in names
+    assert names.count("b2p_adown_pool_x3") == 8 and names.count("b2p_cbfuse_x3") == 5 and names.count("b2p_maxpool_s1_x3") == 3
+    assert rec.calls[0][0] == "b2p_im2col_u8" and rec.calls[0][1][-2] == 1     # stem im2col writes [hi | lo]
 
 
 class _Graph:

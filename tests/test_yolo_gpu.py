@@ -189,3 +189,88 @@ def test_fullres_detect_config1(setup):
     print(f"full-res: {len(bb)} candidates, {len(kb)} kept (gpu {len(gbx)})")
     assert len(gbx) == len(kb)
     assert (gbx - kb).abs().max().item() < 2e-3 and (gs - ks).abs().max().item() < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Parity-grade detector mode (precision="fp16x3": hi/lo feature maps, three tensor-core products per term) against
+# (a) the fp32 oracle network's head tensors and (b) the goldens written by the UNMODIFIED reference
+# (oracle/make_golden.py: util/yolov9.py::YOLOv9Detector.predict on the TorchScript stand-in, fp32 on the CPU).
+import json  # noqa: E402
+from pathlib import Path  # noqa: E402
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def setup_x3():
+    m = yolo_standin(0)
+    det = B200YOLOv9Detector(state_dict=m.state_dict(), device=DEV, precision="fp16x3")
+    return m, det
+
+
+def test_parity_mode_heads_vs_fp32_oracle(setup_x3):
+    """Every tapped feature map and all six head tensors of the fp16x3 engine against the fp32 PyTorch oracle on the
+    same letterboxed canvas.  Two fp32-grade evaluations of a ~100-layer network differ by their own rounding noise
+    amplified through the depth (measured: 1e-5 relative after the first ELAN block, 1.3e-4 at the SPP block); the
+    bounds below are 4x the measured drift, 50-100x tighter than the fp16 mode's (2e-2 / 0.25)."""
+    m, det = setup_x3
+    img = synth.screenshot(3)
+    canvas, scale, pl, pt = R.letterbox_numpy(img, 640)
+    x = torch.from_numpy(canvas.astype(np.float32).transpose(2, 0, 1) / 255.0).unsqueeze(0)
+    outs, feats, raw = _oracle_taps(m, x)
+    io = det._get_io(1, img.shape[0], img.shape[1], 640, 300)
+    plan = io["plan"]
+    assert plan.x3
+    plan.canvas.copy_(torch.from_numpy(canvas).to(DEV).unsqueeze(0))
+    plan.run()
+    torch.cuda.synchronize()
+    for k in TAP_LAYERS:
+        ref = feats[k]
+        got = plan.taps[k].torch().cpu()
+        rel = ((got - ref).abs().max() / ref.abs().max()).item()
+        print(f"x3 tap {k:4s} max-rel {rel:.2e}")
+        assert rel < 5e-4
+    for i in range(3):
+        gb = plan.box_out[i].permute(0, 3, 1, 2).cpu()
+        gc = plan.cls_out[i].permute(0, 3, 1, 2).cpu()
+        eb = (gb - raw[("box", i)]).abs().max().item()
+        ec = (gc - raw[("cls", i)]).abs().max().item()
+        print(f"x3 head {i}: box-logit max abs err {eb:.2e}, cls-logit max abs err {ec:.2e}")
+        assert eb < 4e-3 and ec < 4e-3   # logits of magnitude ~10
+
+
+@pytest.mark.parametrize("name", ["synth_seed0", "synth_seed3_odd", "synth_seed5_3240x2160"])
+def test_parity_mode_predict_reproduces_reference_golden(setup_x3, name):
+    """predict() of the parity-grade detector returns the boxes the unmodified reference returned: identical kept
+    count and ORDER (= identical kept indices after NMS, tie-break rule in DESIGN.md §2), coordinates within 0.5 px
+    (measured ~1e-3), scores within 1e-3."""
+    _, det = setup_x3
+    g = json.loads((GOLD / f"{name}.json").read_text())
+    w, h = g["case"]["size"]
+    img = synth.screenshot(g["case"]["seed"], w, h)
+    res = det.predict(img, conf=g["box_threshold"], iou=0.1)[0].boxes
+    gb, gs = res.xyxy.cpu(), res.conf.cpu()
+    rb, rs = torch.tensor(g["det_xyxy"], dtype=torch.float32).reshape(-1, 4), torch.tensor(g["det_conf"], dtype=torch.float32)
+    assert len(gb) == len(rb), (len(gb), len(rb))
+    db, ds = (gb - rb).abs().max().item(), (gs - rs).abs().max().item()
+    print(f"{name}: {len(gb)} boxes, max |dxy| {db:.2e} px, max |dconf| {ds:.2e}")
+    assert db <= 0.5 and ds <= 1e-3
+
+
+@pytest.mark.parametrize("name", ["synth_seed0", "synth_seed3_odd", "synth_seed5_3240x2160"])
+def test_fast_mode_flips_vs_reference_golden_are_counted(setup, name):
+    """The fast fp16 detector (the reference's own CUDA precision) against the same goldens: box flips caused by fp16
+    rounding of near-tied scores are COUNTED and reported (tie-class events), bounded, never hidden."""
+    from torchvision.ops import box_iou
+    _, det = setup
+    g = json.loads((GOLD / f"{name}.json").read_text())
+    w, h = g["case"]["size"]
+    img = synth.screenshot(g["case"]["seed"], w, h)
+    res = det.predict(img, conf=g["box_threshold"], iou=0.1)[0].boxes
+    gb = res.xyxy.cpu()
+    rb = torch.tensor(g["det_xyxy"], dtype=torch.float32).reshape(-1, 4)
+    iou = box_iou(rb, gb) if len(gb) else torch.zeros((len(rb), 0))
+    matched = int((iou.max(1).values > 0.9).sum()) if len(gb) else 0
+    flips = len(rb) - matched
+    print(f"{name}: fp16 detector {len(gb)} boxes vs reference {len(rb)}; matched at IoU>0.9: {matched}; tie-class flips: {flips}")
+    assert matched >= 0.5 * len(rb)
