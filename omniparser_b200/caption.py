@@ -100,6 +100,7 @@ class B200Florence2Model:
         self.use_graph = use_graph
         self._plans: Dict[tuple, FlorencePlan] = {}
         self._plan_lock = threading.Lock()
+        self._lock = threading.RLock()   # generate() uses plan instance 0: one call at a time per handle (see detector._lock)
         inv = np.zeros((3, 256), np.float32)
         for c in range(3):
             inv[c] = (np.arange(256, dtype=np.float32) * np.float32(1 / 255.0) - np.float32(IMAGENET_MEAN[c])) / np.float32(IMAGENET_STD[c])
@@ -150,7 +151,7 @@ class B200Florence2Model:
     def generate_from_device_crops(self, plan: FlorencePlan, n: int, sync_every: int = 4, from_resized: bool = False) -> torch.Tensor:
         """Crops already in ``plan.crops[:n]`` (device; ``plan.crops_in`` if from_resized).  Returns LongTensor [n, T] on
         the device, HF layout ``[decoder_start, tokens..., eos, pad...]`` truncated where every row has finished."""
-        with torch.cuda.device(self.device):
+        with plan.lock, torch.cuda.device(self.device):   # a plan instance (buffers + graphs) serves one generation at a time
             if n < plan.K:
                 (plan.crops_in if from_resized else plan.crops)[n:].zero_()
             plan.encode(from_resized)
@@ -185,6 +186,10 @@ class B200Florence2Model:
         """ref:util/utils.py:125."""
         if num_beams != 1 or do_sample:
             raise NotImplementedError("only greedy decoding (num_beams=1, do_sample=False) is on the hot path")
+        with self._lock:
+            return self._generate(input_ids, pixel_values, max_new_tokens)
+
+    def _generate(self, input_ids, pixel_values, max_new_tokens):
         u8 = self._to_u8(pixel_values)
         n = u8.shape[0]
         if n == 0:

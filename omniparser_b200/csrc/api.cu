@@ -5,6 +5,7 @@
 #include <mutex>
 #include <string>
 #include <stdlib.h>
+#include <stdio.h>
 
 namespace b2p {
 static std::mutex g_err_mu;
@@ -17,6 +18,16 @@ int set_error(const char* msg) {
   return -1;
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+static std::atomic<int> g_bound_dev{-1};
+int bind_device() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return set_error("cudaGetDevice failed (no CUDA device?)");
+  int expect = -1;
+  if (g_bound_dev.compare_exchange_strong(expect, dev) || expect == dev) return 0;
+  char buf[160];
+  snprintf(buf, sizeof buf, "libb200parse is bound to CUDA device %d (one process drives one GPU); called with device %d current", expect, dev);
+  return set_error(buf);
+}
 bool pdl_enabled() {
   // PDL on the small SIMT kernels is OFF by default: measured on the 2-stream pipelined parse it costs 20 % (their
   // early-launched CTAs sit blocked in griddepcontrol.wait and take SM slots from the other stream); the persistent

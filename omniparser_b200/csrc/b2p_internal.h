@@ -6,6 +6,9 @@
 namespace b2p {
 
 int set_error(const char* msg);   // records msg for b2p_last_error(); returns -1
+// One process drives ONE GPU (include/b200parse.h): the first launch binds the library to the current device; a later
+// call made with another device current fails loudly instead of reusing the first device's workspaces and attributes.
+int bind_device();
 void count_launch(int n = 1);     // bumps the kernel-launch counter read by b2p_launch_count()
 
 #define B2P_CHECK_LAUNCH()                                          \

@@ -8,6 +8,7 @@
 // boolean-mask indexing produces at ref:util/yolov9.py:124-127.  NMS order = descending score, ties by
 // ascending candidate index (torchvision sorts with stable=True), suppress when IoU > thr (strict).
 #include "b2p_internal.h"
+#include <atomic>
 #include <math.h>
 
 namespace b2p {
@@ -311,8 +312,9 @@ int b2p_batched_nms(const float* box, const float* score, const int* cls, const 
   a.thr = t;
   a.img_w = img_w; a.img_h = img_h; a.keep_idx = keep_idx; a.out_box = out_box; a.out_score = out_score; a.out_count = out_count;
   const size_t dyn = size_t(P) * sizeof(unsigned long long) + kNmsMaxKeep * 28 + kNmsThreads * 24 + kNmsThreads * (kNmsThreads / 32) * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (int e = bind_device()) return e;
+  static std::atomic<bool> attr_set{false};   // idempotent attribute: a race between two first callers is harmless
+  if (!attr_set.load()) {
     if (cudaFuncSetAttribute(batched_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8 + kNmsMaxKeep * 28 + kNmsThreads * 24 + kNmsThreads * (kNmsThreads / 32) * 4) != cudaSuccess)
       return set_error("batched_nms: cannot raise dynamic shared memory limit");
     attr_set = true;

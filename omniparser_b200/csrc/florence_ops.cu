@@ -4,6 +4,7 @@
 // All are HBM/latency-bound SIMT kernels in fp32; the dense contractions run in gemm_tcgen05.cu.
 // Residual streams are fp32, GEMM operands fp16.
 #include "b2p_internal.h"
+#include <atomic>
 #include <cuda_fp16.h>
 #include <math.h>
 
@@ -678,7 +679,7 @@ int b2p_dwconv_ln(const float* x, int B, int H, int W, int C, const float* w9c, 
   const long long T = (long long)B * H * W;
   const size_t tile_bytes = size_t(H) * W * C * sizeof(float);
   if ((split & 2) && tile_bytes <= 200 * 1024 && B > 0) {   // opt-in tiled variant (see dwconv_ln_tile_kernel)
-    static bool attr = false;
+    static std::atomic<bool> attr{false};
     if (!attr) {
       if (cudaFuncSetAttribute(dwconv_ln_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
         return set_error("dwconv_ln: cudaFuncSetAttribute failed");
@@ -708,7 +709,8 @@ int b2p_window_attn(const float* qkv, const float* qkv_bias, int B, int H, int W
   if (C / heads != 32) return set_error("window_attn: head_dim must be 32");
   const int nw = ((W + win - 1) / win) * ((H + win - 1) / win);
   const size_t smem = size_t(2) * win * win * 32 * sizeof(float);
-  static bool attr = false;
+  if (int e = bind_device()) return e;
+  static std::atomic<bool> attr{false};
   if (!attr) {
     cudaFuncSetAttribute(window_attn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr = true;

@@ -17,6 +17,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <mutex>
+#include <atomic>
 
 namespace b2p {
 
@@ -823,7 +824,10 @@ static int g_trace_n = 0;
 static int g_trace_meta[kTraceCap][8];
 static std::mutex g_trace_mu;
 
+static std::mutex g_setup_mu;
 static int device_setup() {
+  if (int e = bind_device()) return e;
+  std::lock_guard<std::mutex> lk(g_setup_mu);
   if (g_num_sms) return 0;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return set_error("cudaGetDevice failed (no CUDA device?)");
@@ -1071,8 +1075,8 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
       p.mt_fast = (m2_tiles > 1 && (long long)d.N > (long long)d.M) ? 1 : 0;
       const int items = m2_tiles * p.n_tiles;
       const int pairs = items < g_num_sms / 2 ? items : g_num_sms / 2;
-      static bool attr_set = false;
-      if (!attr_set) {
+      static std::atomic<bool> attr_set{false};
+      if (!attr_set.load()) {
         if (cudaFuncSetAttribute(gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem) != cudaSuccess)
           return set_error("cudaFuncSetAttribute(gemm_pair_kernel) failed");
         attr_set = true;

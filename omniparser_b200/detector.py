@@ -7,6 +7,7 @@ sync: LANCZOS letterbox -> YOLOv9-E forward (CUDA graph) -> decode/filter -> bit
 """
 from __future__ import annotations
 
+import threading
 from pathlib import Path
 from typing import Dict, List, Sequence, Union
 
@@ -76,6 +77,10 @@ class B200YOLOv9Detector:
         self.use_graph = use_graph
         self._plans: Dict[tuple, YoloPlan] = {}
         self._io: Dict[tuple, dict] = {}
+        # One parse at a time per detector handle: the reference's callers share ONE module-level model between worker
+        # threads (ref:gradio_demo.py:15-16,35-59) and its PyTorch modules are re-entrant; this object's launch plans and io
+        # buffers are not, so every public entry point serialises on this lock (SURVEY.md §8b "self-serialising per device").
+        self._lock = threading.RLock()
 
     def to(self, device):   # called at ref:eval/ss_pro_gpt4o_omniv2.py:30
         return self
@@ -109,6 +114,7 @@ class B200YOLOv9Detector:
                 host=torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory(),
                 host_count=torch.zeros((B,), dtype=torch.int32).pin_memory(),
                 host_box=torch.zeros((B, max_det, 4), dtype=torch.float32).pin_memory(),
+                host_cand=torch.zeros((B,), dtype=torch.int32).pin_memory(),
                 src=torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev),
                 tmp=torch.empty((B, H, max(rw, 1), 3), dtype=torch.uint8, device=dev),
                 pad_l=torch.full((B,), float(pl), **f32), pad_t=torch.full((B,), float(pt), **f32),
@@ -135,12 +141,21 @@ class B200YOLOv9Detector:
         ops.batched_nms(io["cand_box"], io["cand_score"], io["cand_cls"], io["cand_count"], B, io["cap"], iou, max_det,
                         io["img_w"], io["img_h"], io["keep"], io["out_box"], io["out_score"], io["out_count"])
 
+    @staticmethod
+    def check_capacity(cand_count_host: torch.Tensor, cap: int) -> None:
+        """The decode kernel keeps the first ``cap`` candidates in anchor order; more than that (only reachable with
+        full-resolution ``imgsz`` and a very low threshold) would silently drop the coarse-stride candidates."""
+        m = int(cand_count_host.max()) if cand_count_host.numel() else 0
+        if m > cap:
+            raise RuntimeError(f"{m} candidates above the confidence threshold exceed the NMS capacity ({cap}): raise the "
+                               "threshold or lower imgsz")
+
     @torch.inference_mode()
     def predict_batch(self, images: Sequence[np.ndarray], conf=0.25, imgsz=640, iou=0.7, max_det=300) -> List[Result]:
         """Same-size u8 HWC images -> one Result per image (one H2D copy, one D2H of the counts)."""
         B = len(images)
         H, W = images[0].shape[:2]
-        with torch.cuda.device(self.device):
+        with self._lock, torch.cuda.device(self.device):
             io = self._get_io(B, H, W, imgsz, max_det)
             for i, im in enumerate(images):
                 assert im.shape == (H, W, 3) and im.dtype == np.uint8
@@ -148,8 +163,7 @@ class B200YOLOv9Detector:
             io["src"].copy_(io["host"], non_blocking=True)
             self.detect_device(io, B, H, W, conf, iou, max_det)
             counts = io["out_count"].cpu().tolist()
-            if int(io["cand_count"].max().item()) > io["cap"]:
-                raise RuntimeError("more candidates above the confidence threshold than the NMS capacity (16384)")
+            self.check_capacity(io["cand_count"].cpu(), io["cap"])
             return [Result(Boxes(io["out_box"][i, :n].clone(), io["out_score"][i, :n].clone())) for i, n in enumerate(counts)]
 
     @torch.inference_mode()

@@ -178,6 +178,8 @@ class FlorencePlan:
         self.dw_tile = bool(os.environ.get("B2P_DWCONV_TILE"))   # opt-in smem-tiled dwconv+LN (unvalidated)
         self.ca_small = bool(os.environ.get("B2P_CHATTN_SMALL"))   # opt-in warp-per-group channel attention for N <= 16 (unvalidated)
         self.warmed = False
+        import threading
+        self.lock = threading.Lock()
         self.w, self.K, self.dev = w, K, w.device
         self.x3 = w.x3
         self.KX = 2 if w.x3 else 1

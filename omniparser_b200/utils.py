@@ -21,7 +21,7 @@ import numpy as np
 import torch
 from PIL import Image
 
-from . import host_glue, ops
+from . import host_glue, ops, som_overlay
 from .caption import (CAPTION_PROMPT_IDS, B200Florence2Model, B200Florence2Processor, find_tokenizer_dir, load_florence_state,
                       load_tokenizer)
 from .detector import B200YOLOv9Detector
@@ -72,6 +72,15 @@ class ParseTimings(dict):
     pass
 
 
+def _check_crop_status(status: torch.Tensor) -> None:
+    """b2p_crop_resize flags crops whose truncated box is empty.  The reference silently skips such a crop
+    (ref:util/utils.py:104-105) and then mis-assigns every later caption; int_box_area > 0 (:444-445) makes it impossible
+    on this path, so a flagged crop is a bug and raises (read after the ids' D2H sync: no extra synchronisation)."""
+    bad = int(status.count_nonzero().item())
+    if bad:
+        raise RuntimeError(f"{bad} crop boxes were empty after truncation (status flags of b2p_crop_resize)")
+
+
 @torch.inference_mode()
 def parse_screenshots(images: Sequence[np.ndarray], model: B200YOLOv9Detector, caption_model_processor: dict,
                       ocr: Sequence[tuple], BOX_TRESHOLD=0.01, iou_threshold=0.9, imgsz=640, max_new_tokens=20,
@@ -87,7 +96,7 @@ def parse_screenshots(images: Sequence[np.ndarray], model: B200YOLOv9Detector, c
     cap_model: B200Florence2Model = caption_model_processor["model"]
     processor = caption_model_processor["processor"]
     t0 = time.perf_counter()
-    with torch.cuda.device(model.device):
+    with model._lock, torch.cuda.device(model.device):   # io slot 0 / caption plan instance 0 are this handle's: one call at a time
         io_ = model._get_io(B, H, W, imgsz, 300)
         if not _skip_h2d:   # bench "value" leg: the u8 screenshots are already resident in io_["src"]
             for i, im in enumerate(images):
@@ -97,6 +106,7 @@ def parse_screenshots(images: Sequence[np.ndarray], model: B200YOLOv9Detector, c
             model.detect_device(io_, B, H, W, BOX_TRESHOLD, 0.1, 300)
             counts = io_["out_count"].cpu().tolist()                   # D2H #1 (sync)
             boxes = io_["out_box"].cpu()
+            model.check_capacity(io_["cand_count"].cpu(), io_["cap"])
         else:   # tests: inject detector output (e.g. the golden boxes) to pin the stages after it exactly
             counts = [len(b) for b in _det_override]
             boxes = [torch.as_tensor(b, dtype=torch.float32).reshape(-1, 4) for b in _det_override]
@@ -117,6 +127,7 @@ def parse_screenshots(images: Sequence[np.ndarray], model: B200YOLOv9Detector, c
         t2 = time.perf_counter()
         ids = None
         if n:
+          with cap_model._lock:   # plan instance 0 of the caption handle (also what model.generate() uses)
             dev = model.device
             if caption_size == 64:
                 plan = cap_model.plan_for(n, max_new_tokens, prompt_ids)
@@ -131,12 +142,13 @@ def parse_screenshots(images: Sequence[np.ndarray], model: B200YOLOv9Detector, c
                 meta = dict(hw=torch.tensor([[H, W]] * B, dtype=torch.int32, device=dev),
                             off=torch.tensor([i * H * W * 3 for i in range(B)], dtype=torch.int64, device=dev))
                 model._io[key] = meta
-            status = torch.empty((n,), dtype=torch.int32, device=dev)
+            status = torch.zeros((n,), dtype=torch.int32, device=dev)
             ops.crop_resize(io_["src"], meta["hw"], meta["off"], d_boxes, d_bimg, n, 64, crops_dst, status)
             if caption_size == 64:
                 ids = cap_model.generate_from_device_crops(plan, n).cpu()  # D2H #2 (sync)
             else:
                 ids = cap_model.generate_chunked(crops_dst, max_new_tokens, prompt_ids, from_resized=False).cpu()
+            _check_crop_status(status)
         t3 = time.perf_counter()
     out = []
     k = 0
@@ -218,6 +230,7 @@ class PipelinedParser:
             m.detect_device(io_, B, H, W, self.conf, 0.1, 300)
             io_["host_count"].copy_(io_["out_count"], non_blocking=True)
             io_["host_box"].copy_(io_["out_box"], non_blocking=True)
+            io_["host_cand"].copy_(io_["cand_count"], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.s_det)
         return dict(io=io_, ev=ev, B=B, H=H, W=W)
@@ -230,6 +243,7 @@ class PipelinedParser:
         t1 = time.perf_counter()
         counts = io_["host_count"].tolist()
         boxes = io_["host_box"]
+        self.model.check_capacity(io_["host_cand"], io_["cap"])
         whwh = torch.Tensor([W, H, W, H])
         all_elems, crop_boxes, crop_img = [], [], []
         for i in range(B):
@@ -274,9 +288,10 @@ class PipelinedParser:
                     meta = dict(hw=torch.tensor([[H, W]] * B, dtype=torch.int32, device=dev),
                                 off=torch.tensor([i * H * W * 3 for i in range(B)], dtype=torch.int64, device=dev))
                     model._io[key] = meta
-                status = torch.empty((n,), dtype=torch.int32, device=dev)
+                status = torch.zeros((n,), dtype=torch.int32, device=dev)
                 ops.crop_resize(io_["src"], meta["hw"], meta["off"], d_boxes, d_bimg, n, 64, plan.crops, status)
                 ids = cap_model.generate_from_device_crops(plan, n).cpu()
+                _check_crop_status(status)
         t3 = time.perf_counter()
         texts_all = [t.strip() for t in processor.batch_decode(ids, skip_special_tokens=True)] if ids is not None else []
         out, k = [], 0
@@ -317,7 +332,7 @@ class PipelinedParser:
                         meta = dict(hw=torch.tensor([[H, W]] * B, dtype=torch.int32, device=dev),
                                     off=torch.tensor([i * H * W * 3 for i in range(B)], dtype=torch.int64, device=dev))
                         model._io[key] = meta
-                    status = torch.empty((ng,), dtype=torch.int32, device=dev)
+                    status = torch.zeros((ng,), dtype=torch.int32, device=dev)
                     ops.crop_resize(io_["src"], meta["hw"], meta["off"], d_boxes, d_bimg, ng, 64, plan.crops[off:], status)
                     off += ng
                 ids = cap_model.generate_from_device_crops(plan, n).cpu()
@@ -357,7 +372,7 @@ class PipelinedParser:
         screenshots alive until its crops have been cut.  Results come out in order, ``lanes`` batches behind the glue."""
         from collections import deque
         self._job = 0   # lane assignment is a function of the position in THIS run (batch i -> lane i % lanes)
-        with self._device_ctx():
+        with self._device_ctx():   # also takes the handle lock: the pipeline owns the io slots and caption lanes while it runs
             it = iter(batches)
             rit = iter(resident) if resident is not None else None
             cur = next(it, None)
@@ -394,7 +409,13 @@ class PipelinedParser:
                 yield pending.popleft().result()
 
     def _device_ctx(self):
-        return torch.cuda.device(self.model.device)
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            with self.model._lock, torch.cuda.device(self.model.device):
+                yield
+        return ctx()
 
     @torch.inference_mode()
     def prewarm(self, crop_counts):
@@ -426,30 +447,32 @@ class PipelinedParser:
 
 
 # ------------------------------------------------------------------------------------------------ reference API
-def _annotate(image_np: np.ndarray, boxes_xyxy_ratio, text_scale=0.4, text_padding=5, text_thickness=2, thickness=3):
-    """Set-of-Marks overlay (numbered boxes).  Host post-step outside the hot path; a plain OpenCV
-    renderer, not pixel-identical with ref:util/box_annotator.py (its `supervision` dependency is absent here)."""
-    import cv2
-    h, w = image_np.shape[:2]
-    frame = image_np.copy()
-    palette = [(255, 64, 64), (64, 200, 64), (64, 64, 255), (230, 180, 30), (200, 64, 200), (64, 200, 200)]
-    for i, b in enumerate(boxes_xyxy_ratio):
-        x1, y1, x2, y2 = int(b[0] * w), int(b[1] * h), int(b[2] * w), int(b[3] * h)
-        col = palette[i % len(palette)]
-        cv2.rectangle(frame, (x1, y1), (x2, y2), col, thickness)
-        label = str(i)
-        (tw, th), _ = cv2.getTextSize(label, cv2.FONT_HERSHEY_SIMPLEX, text_scale, text_thickness)
-        cv2.rectangle(frame, (x1, y1 - th - 2 * text_padding), (x1 + tw + 2 * text_padding, y1), col, -1)
-        cv2.putText(frame, label, (x1 + text_padding, y1 - text_padding), cv2.FONT_HERSHEY_SIMPLEX, text_scale,
-                    (255, 255, 255), text_thickness, cv2.LINE_AA)
-    return frame
+def _prompt_ids(prompt, caption_model_processor) -> Sequence[int]:
+    """ref:util/utils.py:107-112: no prompt -> "<CAPTION>" for Florence-2, which the HF processor rewrites to "What does
+    the image describe?" (hf:models/florence2/processing_florence2.py:81).  Any other prompt needs the tokenizer."""
+    proc = caption_model_processor["processor"]
+    if not prompt or prompt == "<CAPTION>":
+        return list(getattr(proc, "prompt_ids", CAPTION_PROMPT_IDS))
+    tok = getattr(proc, "tokenizer", None)
+    enc = getattr(tok, "encode", None) or getattr(getattr(tok, "tk", None), "encode", None)
+    if enc is None:
+        raise NotImplementedError(f"prompt={prompt!r}: a custom prompt has to be tokenised, and this processor was built "
+                                  "without tokenizer files (see get_caption_model_processor)")
+    ids = enc(prompt)
+    ids = list(getattr(ids, "ids", ids))
+    return ids
 
 
 def get_som_labeled_img(image_source: Union[str, Image.Image], model=None, BOX_TRESHOLD=0.01, output_coord_in_ratio=False,
                         ocr_bbox=None, text_scale=0.4, text_padding=5, draw_bbox_config=None,
                         caption_model_processor=None, ocr_text=[], use_local_semantics=True, iou_threshold=0.9,
                         prompt=None, scale_img=False, imgsz=None, batch_size=128):
-    """ref:util/utils.py:417-496.  Returns ``(base64 PNG, {str(i): [x, y, w, h]}, filtered_boxes_elem)``."""
+    """ref:util/utils.py:417-496.  Returns ``(base64 PNG, {str(i): [x, y, w, h]}, filtered_boxes_elem)`` -- the element
+    list, the label coordinates and the decoded overlay image equal the reference's (tests/golden, tests/test_overlay_cpu.py).
+    ``batch_size`` only chunks the reference's generate calls (rows are independent under greedy decoding), so it has no
+    effect on the result here; it is validated and otherwise unused."""
+    if not (isinstance(batch_size, int) and batch_size > 0):
+        raise ValueError(f"batch_size must be a positive int, got {batch_size!r}")
     if isinstance(image_source, str):
         image_source = Image.open(image_source)
     image_source = image_source.convert("RGB")
@@ -462,7 +485,7 @@ def get_som_labeled_img(image_source: Union[str, Image.Image], model=None, BOX_T
         print("no ocr bbox!!!")                      # side effect kept (ref:util/utils.py:441)
     if use_local_semantics:
         res = parse_screenshots([img], model, caption_model_processor, [(list(ocr_text), ocr_bbox or None)], BOX_TRESHOLD,
-                                iou_threshold, use_imgsz)
+                                iou_threshold, use_imgsz, prompt_ids=_prompt_ids(prompt, caption_model_processor))
         elems = res[0][0]
     else:
         r = model.predict(img, conf=BOX_TRESHOLD, imgsz=use_imgsz, iou=0.1)[0].boxes
@@ -472,14 +495,6 @@ def get_som_labeled_img(image_source: Union[str, Image.Image], model=None, BOX_T
         elems, _ = host_glue.build_elements(xyxy, oratio, list(ocr_text), w, h, iou_threshold)
     print("len(filtered_boxes):", len(elems), next((i for i, e in enumerate(elems) if e["content"] is None), -1))
     boxes = [e["bbox"] for e in elems]
-    cfg = draw_bbox_config or dict(text_scale=text_scale, text_padding=text_padding)
-    frame = _annotate(img, boxes, **cfg)
-    buf = io.BytesIO()
-    Image.fromarray(frame).save(buf, format="PNG")
-    encoded = base64.b64encode(buf.getvalue()).decode("ascii")
-    # ref:util/utils.py:478-494: xyxy -> xywh label coordinates, in pixels unless output_coord_in_ratio
-    coords = {}
-    for i, b in enumerate(boxes):
-        x, y, bw, bh = b[0], b[1], b[2] - b[0], b[3] - b[1]
-        coords[str(i)] = [x, y, bw, bh] if output_coord_in_ratio else [x * w, y * h, bw * w, bh * h]
+    cfg = draw_bbox_config if draw_bbox_config else dict(text_scale=text_scale, text_padding=text_padding)
+    encoded, coords, _ = som_overlay.som_outputs(img, boxes, output_coord_in_ratio, **cfg)
     return encoded, coords, elems

@@ -59,6 +59,46 @@ class _Model:
         return out
 
 
+def _overlay_sha(png_b64: str, size) -> str:
+    """sha256 of the decoded RGB pixels of the reference's annotated PNG (the PNG byte stream itself is encoder-specific)."""
+    import base64, hashlib, io
+    im = Image.open(io.BytesIO(base64.b64decode(png_b64))).convert("RGB")
+    assert im.size == tuple(size)
+    return hashlib.sha256(np.asarray(im).tobytes()).hexdigest()
+
+
+FACADE = dict(name="facade_seed7", seed=7, size=(1920, 1080))
+
+
+def facade_golden(path, fl):
+    """The reference's own facade, ``util/omniparser.py::Omniparser`` (ref:util/omniparser.py:7-32), run UNMODIFIED: the
+    easyocr stand-in returns fixed quads (OCR is outside the hot path), ``get_yolo_model`` loads the TorchScript archive,
+    and only ``get_caption_model_processor`` -- which needs the network for microsoft/Florence-2-base, ref:util/utils.py:64 --
+    is replaced in the facade's namespace by the seeded stand-in pair."""
+    import base64, io, sys
+    import easyocr
+    ro = __import__("util.omniparser", fromlist=["Omniparser"])
+    w, h = FACADE["size"]
+    img = synth.screenshot(FACADE["seed"], w, h)
+    texts, boxes = synth.ocr_boxes(FACADE["seed"], w, h)
+    quads = [([[b[0], b[1]], [b[2], b[1]], [b[2], b[3]], [b[0], b[3]]], t, 0.99) for b, t in zip(boxes, texts)]
+    import util.utils as ru
+    ru.reader.readtext = lambda image_np, **kw: quads                       # the instance created at ref:util/utils.py:22
+    cm = _Model(fl)
+    ro.get_caption_model_processor = lambda **kw: {"model": cm, "processor": _Processor()}
+    op = ro.Omniparser({"som_model_path": str(path), "caption_model_name": "florence2", "caption_model_path": "seeded/florence2-standin",
+                        "BOX_TRESHOLD": BOX_TRESHOLD})
+    buf = io.BytesIO()
+    Image.fromarray(img).save(buf, format="PNG")
+    png, parsed = op.parse(base64.b64encode(buf.getvalue()).decode("ascii"))
+    ids = torch.cat(cm.ids, 0) if cm.ids else torch.zeros((0, 1), dtype=torch.long)
+    gold = dict(case=FACADE, config=dict(BOX_TRESHOLD=BOX_TRESHOLD), ocr_text=texts, ocr_bbox=boxes, parsed_content_list=parsed,
+                caption_ids=ids.tolist(), overlay_sha256=_overlay_sha(png, (w, h)))
+    out = GOLDEN / f"{FACADE['name']}.json"
+    out.write_text(json.dumps(gold, default=lambda o: float(o) if isinstance(o, (np.floating,)) else o.tolist()))
+    print("wrote", out, len(parsed), "elements,", ids.shape[0], "captions")
+
+
 def main():
     ru, ry = import_reference()
     m = yolo_standin(0)
@@ -73,7 +113,7 @@ def main():
         texts, boxes = synth.ocr_boxes(case["seed"], w, h)
         raw = det.predict(Image.fromarray(img), conf=BOX_TRESHOLD, iou=0.1)[0].boxes
         cm = _Model(fl)
-        _, coords, parsed = ru.get_som_labeled_img(Image.fromarray(img), det, BOX_TRESHOLD=BOX_TRESHOLD, output_coord_in_ratio=True,
+        png, coords, parsed = ru.get_som_labeled_img(Image.fromarray(img), det, BOX_TRESHOLD=BOX_TRESHOLD, output_coord_in_ratio=True,
                                                    ocr_bbox=boxes, draw_bbox_config=None,
                                                    caption_model_processor={"model": cm, "processor": _Processor()},
                                                    ocr_text=texts, use_local_semantics=True, iou_threshold=IOU, scale_img=False,
@@ -81,10 +121,12 @@ def main():
         ids = torch.cat(cm.ids, 0) if cm.ids else torch.zeros((0, 1), dtype=torch.long)
         gold = dict(case=case, box_threshold=BOX_TRESHOLD, iou_threshold=IOU, max_new_tokens=20,
                     det_xyxy=[[float(np.float32(v)) for v in b] for b in raw.xyxy.tolist()], det_conf=[float(c) for c in raw.conf.tolist()],
-                    parsed_content_list=parsed, caption_ids=ids.tolist(), label_coordinates=coords)
+                    parsed_content_list=parsed, caption_ids=ids.tolist(), label_coordinates=coords,
+                    overlay_sha256=_overlay_sha(png, (w, h)))
         out = GOLDEN / f"{case['name']}.json"
         out.write_text(json.dumps(gold, default=lambda o: float(o) if isinstance(o, (np.floating,)) else o.tolist()))
         print("wrote", out, len(raw.xyxy), "boxes,", ids.shape[0], "captions")
+    facade_golden(path, fl)
 
 
 if __name__ == "__main__":

@@ -111,7 +111,10 @@ def install_shims() -> None:
 
     Color.BLACK = Color(0, 0, 0)
     Color.WHITE = Color(255, 255, 255)
-    ColorPalette.DEFAULT = ColorPalette([Color(255, 64, 64), Color(64, 200, 64), Color(64, 64, 255), Color(230, 180, 30)])
+    # supervision 0.18.0 (pinned at ref:requirements.txt) ColorPalette.DEFAULT, recalled (DEFAULT_COLOR_PALETTE hex list)
+    _hex = ["A351FB", "FF4040", "FFA1A0", "FF7633", "FFB633", "D1D435", "4CFB12", "94CF1A", "40DE8A", "1B9640", "00D6C1",
+            "2E9CAA", "00C4FF", "364797", "6675FF", "0019EF", "863AFF", "530087", "CD3AFF", "FF97CA", "FF39C9"]
+    ColorPalette.DEFAULT = ColorPalette([Color(int(h[0:2], 16), int(h[2:4], 16), int(h[4:6], 16)) for h in _hex])
     sv.Detections = Detections
     core2.Detections = Detections
     sv.detection = core

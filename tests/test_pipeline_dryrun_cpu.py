@@ -33,14 +33,20 @@ class _FakeDetector:
         self.device = torch.device("cpu")
         self._io = {}
         self.lock = threading.Lock()
+        self._lock = threading.RLock()          # the handle-level lock of the real detector
         self.n = 0
+
+    @staticmethod
+    def check_capacity(cand_count_host, cap):
+        assert int(cand_count_host.max()) <= cap
 
     def _get_io(self, B_, H_, W_, imgsz, max_det, slot=0):
         key = (B_, H_, W_, slot)
         if key not in self._io:
             self._io[key] = dict(src=torch.zeros((B_, H_, W_, 3), dtype=torch.uint8), host=torch.zeros((B_, H_, W_, 3), dtype=torch.uint8),
                                  host_count=torch.zeros((B_,), dtype=torch.int32), host_box=torch.zeros((B_, max_det, 4)),
-                                 out_count=torch.zeros((B_,), dtype=torch.int32), out_box=torch.zeros((B_, max_det, 4)))
+                                 out_count=torch.zeros((B_,), dtype=torch.int32), out_box=torch.zeros((B_, max_det, 4)),
+                                 cand_count=torch.zeros((B_,), dtype=torch.int32), host_cand=torch.zeros((B_,), dtype=torch.int32), cap=8400)
         return self._io[key]
 
     def detect_device(self, io, B_, H_, W_, conf, iou, max_det):
@@ -63,6 +69,7 @@ def _cap_model(florence):
     m.use_graph = False
     m._plans = {}
     m._plan_lock = threading.Lock()
+    m._lock = threading.RLock()
     return m
 
 

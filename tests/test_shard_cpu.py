@@ -62,6 +62,60 @@ def test_two_rank_gather_roundtrip():
             assert np.array_equal(ids, ref[k][1].numpy())
 
 
+def _pipe_worker(rank, world, port, T, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    steps, B = 5, 3
+    pipe = shard.GatherPipe(rank, world, "cpu", B, T)
+    for s in range(steps):
+        pipe.submit(_fake_results(10 * rank + s, B, T))       # returns at once; the worker thread runs the collective
+    pipe.drain()
+    if rank == 0:
+        q.put([[shard.unpack_records(g, T) for g in step] for step in pipe.received])
+    pipe.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_async_gather_pipe_two_ranks():
+    """the bench's gather path: submit() never blocks on the peer, drain() completes every step's gather, in order"""
+    T, world = 8, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30100 + (os.getpid() % 500)
+    procs = [ctx.Process(target=_pipe_worker, args=(r, world, port, T, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert len(got) == 5
+    for s, step in enumerate(got):
+        for r in range(world):
+            ref = _fake_results(10 * r + s, 3, T)
+            for (boxes, ids), (elems, rids) in zip(step[r], ref):
+                assert np.array_equal(boxes, np.asarray([e["bbox"] for e in elems], np.float32))
+                assert np.array_equal(ids, rids.numpy())
+
+
+def test_dense_screenshot_fits_the_record_and_overflow_raises():
+    """300 icons (= max_det, all captioned, the reference captions every box in chunks of 128) + 200 OCR boxes round-trip;
+    anything beyond the capacity raises instead of being clamped."""
+    import pytest
+    T = 8
+    rng = np.random.default_rng(1)
+    elems = [{"bbox": [float(np.float32(v)) for v in rng.uniform(0, 1, 4)]} for _ in range(500)]
+    ids = torch.from_numpy(rng.integers(0, 51289, size=(300, T + 1)))
+    rec = shard.pack_records([(elems, ids)], T)
+    (boxes, rids), = shard.unpack_records(rec, T)
+    assert boxes.shape == (500, 4) and np.array_equal(rids, ids.numpy())
+    with pytest.raises(ValueError, match="capacity"):
+        shard.pack_records([(elems, torch.zeros((301, T + 1), dtype=torch.long))], T)
+    with pytest.raises(ValueError, match="capacity"):
+        shard.pack_records([(elems * 3, ids)], T)
+
+
 def test_shard_indices_cover():
     for n in (0, 1, 7, 64):
         for w in (1, 2, 8):
