@@ -43,7 +43,9 @@ def log(msg):
 def host_threads() -> int:
     """Usable host cores: torch's default, capped by the affinity mask and the cgroup CPU quota (oversubscribing
     OpenMP threads on a quota-limited container stalls for minutes)."""
-    n = torch.get_num_threads()
+    # NOT torch.get_num_threads(): torchrun exports OMP_NUM_THREADS=1, which would make a multi-rank launch report a
+    # one-thread reference (round-1 finding); the machine's cores, the affinity mask and the cgroup quota are what count
+    n = os.cpu_count() or 1
     try:
         n = min(n, len(os.sched_getaffinity(0)))
     except Exception:
@@ -149,8 +151,14 @@ def _inputs(rank: int, B: int):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
+REF_SAMPLE = 4        # screenshots of the step's batch the reference arm parses per step (bounded sample)
+
+
 def run_reference(args):
-    """The reference algorithm (oracle port, see oracle/pipeline_cpu.py) on the host cores; rank 0 only."""
+    """The reference algorithm (oracle port, see oracle/pipeline_cpu.py) on ALL the host cores; rank 0 only.  Same
+    workload, config, seeds and thresholds as the B200 arm: step j parses the first REF_SAMPLE screenshots of the batch
+    rank 0 of the B200 arm parses at step j (a bounded sample of the step: the whole --steps/--warmup run must end within
+    minutes at ~1 s per screenshot)."""
     rank, world, _ = _dist()
     if rank != 0:
         return
@@ -158,27 +166,34 @@ def run_reference(args):
     from oracle.pipeline_cpu import OraclePipeline
     torch.set_num_threads(host_threads())
     pipe = OraclePipeline()
-    times, nb = [], []
-    for i in range(args.warmup + args.steps):
-        img = synth.screenshot(i)
-        texts, boxes = synth.ocr_boxes(i)
-        tm = {}
+    B = args.batch
+    k = min(REF_SAMPLE, B)
+    times, nb, nbox = [], [], []
+    for j in range(args.warmup + args.steps):
+        seeds = [(j % N_SETS) * B + i for i in range(k)]      # = _inputs(rank 0)[j % N_SETS][:k]
+        data = [(synth.screenshot(sd), synth.ocr_boxes(sd)) for sd in seeds]
         t0 = time.perf_counter()
-        pipe.parse(img, texts, boxes, BOX_TRESHOLD=args.box_threshold, iou_threshold=0.7, max_new_tokens=args.max_new_tokens,
-                   caption_768=args.caption_768, timings=tm)
+        for img, (texts, boxes) in data:
+            tm = {}
+            pipe.parse(img, texts, boxes, BOX_TRESHOLD=args.box_threshold, iou_threshold=0.7, max_new_tokens=args.max_new_tokens,
+                       caption_768=args.caption_768, timings=tm)
+            if j >= args.warmup:
+                nb.append(tm["n_crops"])
         dt = time.perf_counter() - t0
-        if i >= args.warmup:
+        if j >= args.warmup:
             times.append(dt)
-            nb.append(tm["n_crops"])
     total = sum(times)
-    val = len(times) / total
-    sample = f"{len(times)} screenshots, 1 per step, {np.mean(nb):.0f} crops each, caption mode {'768 (reference CPU branch)' if args.caption_768 else '64 (mode-matched with the GPU path)'}"
+    val = k * len(times) / total
+    sample = (f"{k} of the {B * args.gpus} screenshots of each step (same seeds as the B200 arm's rank 0), {len(times)} steps, "
+              f"{np.mean(nb):.1f} crops per screenshot, caption mode "
+              f"{'768 (reference CPU branch)' if args.caption_768 else '64 (mode-matched with the GPU path)'}, fp32, {torch.get_num_threads()} threads")
     line = {"impl": "reference", "metric": "screenshots/sec", "value": val, "unit": "screenshots/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": _config(args, 1),
+            "config": _config(args, B),
             "cpu_baseline": {"value": val, "unit": "screenshots/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
-            "e2e": {"value": val, "unit": "screenshots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": val, "unit": "screenshots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "crops_per_screenshot": float(np.mean(nb))}
     print(json.dumps(line), flush=True)
 
 
@@ -190,7 +205,7 @@ def _config(args, per_gpu_batch):
             "decode_tokens": args.max_new_tokens, "box_threshold": args.box_threshold, "weights": "seeded stand-ins (no checkpoints offline)",
             "caption_precision": args.precision, "detector_precision": "fp16 operands, fp32 accumulate",
             "l2": f"inputs rotate over {N_SETS} distinct batches ({N_SETS * per_gpu_batch * W * H * 3 / 1e6:.0f} MB/GPU) > 126 MB L2",
-            "parallelism": f"dp{args.gpus} (screenshots sharded, one NCCL gather of results per step)",
+            "parallelism": f"dp{args.gpus} (screenshots sharded, one NCCL gather of results per step, issued off the parse loop)",
             "schedule": "one batch at a time" if getattr(args, "no_pipeline", False) else
                         f"pipeline across steps: detect(i+1) on stream A | host list logic(i) | {args.caption_lanes} caption lanes (batches i-1.. on own streams/plans), caption group {args.caption_group}; fill and drain are inside the timed region"}
 
@@ -213,8 +228,7 @@ def run_b200(args):
     log("models ready; generating inputs")
     B = args.batch
     sets = _inputs(rank, B)
-    rec = torch.zeros((B, shard.record_width(args.max_new_tokens)), dtype=torch.float32, device=dev)
-    gathered = [torch.zeros_like(rec) for _ in range(world)] if (world > 1 and rank == 0) else None
+    pipe = shard.GatherPipe(rank, world, dev, B, args.max_new_tokens, keep=False)   # one NCCL gather per step, on its own thread + stream
     stats = {"boxes": 0, "crops": 0, "n": 0}
 
     def step(i, resident):
@@ -226,9 +240,7 @@ def run_b200(args):
         out = parse_screenshots(imgs, model, cmp_, ocr, BOX_TRESHOLD=args.box_threshold, iou_threshold=0.7,
                                 max_new_tokens=args.max_new_tokens, timings=tm, _skip_h2d=resident)
         stats["boxes"] += tm["n_boxes"]; stats["crops"] += tm["n_crops"]; stats["n"] += B
-        if world > 1:   # one gather of fixed-size padded records per step
-            rec.copy_(shard.pack_records(out, args.max_new_tokens), non_blocking=True)
-            shard.gather_records(rec, rank, world, gathered)
+        pipe.submit(out)   # one gather of fixed-size padded records per step; no-op at world 1
         return tm
 
     dsets = [torch.from_numpy(np.stack(s[0])).to(dev) for s in sets]
@@ -253,16 +265,24 @@ def run_b200(args):
         tm0 = dict(pp.timings)
         for out in pp.run(batches, res):
             stats["n"] += B
-            if world > 1:
-                rec.copy_(shard.pack_records(out, args.max_new_tokens), non_blocking=True)
-                shard.gather_records(rec, rank, world, gathered)
+            pipe.submit(out)
         stats["boxes"] += pp.timings["n_boxes"] - tm0["n_boxes"]
         stats["crops"] += pp.timings["n_crops"] - tm0["n_crops"]
         d = {k: (pp.timings[k] - tm0[k]) / max(n_steps, 1) for k in ("detect_wait_s", "glue_s", "caption_s")}
         return [dict(detect_s=d["detect_wait_s"], glue_s=d["glue_s"], caption_s=d["caption_s"])]
 
-    def timed(resident):
+    def run_steps_pageable(n_steps):
+        """the path an unprepared caller hits: plain (pageable) numpy screenshots; the pipeline stages them through its
+        own page-locked slot buffer"""
+        for out in pp.run(((sets[i % N_SETS][0], sets[i % N_SETS][1]) for i in range(n_steps)), None):
+            stats["n"] += B
+            pipe.submit(out)
+        return []
+
+    def timed(mode):
+        resident = mode == "resident"
         sampler = ClockSampler(local)
+        pipe.drain()     # gathers of the warm-up steps are done before the barrier (collectives stay in one order on every rank)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -272,7 +292,8 @@ def run_b200(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
-        tms = run_steps(args.steps, resident)
+        tms = run_steps(args.steps, resident) if mode != "pageable" else run_steps_pageable(args.steps)
+        pipe.drain()            # every step's gather has completed (inside the timed region)
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -297,10 +318,14 @@ def run_b200(args):
         run_steps(2, False)
         torch.cuda.synchronize()
         log("pipelined warm-up done")
-    ms_res, _, launches, clocks, tms, st = timed(True)
+    ms_res, _, launches, clocks, tms, st = timed("resident")
     log(f"resident leg: {ms_res / args.steps:.1f} ms/step")
-    ms_e2e, _, _, _, tms2, _ = timed(False)
+    ms_e2e, _, _, _, tms2, _ = timed("pinned")
     log(f"e2e leg: {ms_e2e / args.steps:.1f} ms/step")
+    ms_pg = None
+    if not args.no_pipeline:
+        ms_pg, _, _, _, _, _ = timed("pageable")
+        log(f"e2e leg, pageable inputs: {ms_pg / args.steps:.1f} ms/step")
     value = world * B * args.steps / (ms_res / 1e3)
     e2e = world * B * args.steps / (ms_e2e / 1e3)
 
@@ -386,6 +411,41 @@ def run_b200(args):
     except Exception as exc:   # noqa: BLE001
         caption_stages = {"error": repr(exc)[:200]}
 
+    # per-stage roofline list (detect / caption encode / decode step): achieved = algorithmic FLOPs (logical: what the
+    # reference's fp32 graph computes; the fp16x3 stages execute 3x that on the tensor pipe) / CUDA-event time in THIS run;
+    # traffic = DRAM bytes of the stage from the committed ncu launch list of the same kernels (profiles/, per stage).
+    stage_traffic = {}
+    tpf = ROOT / "profiles" / "r2_stage_traffic.json"
+    if tpf.is_file() and B == 8:
+        stage_traffic = json.loads(tpf.read_text())
+    roofline_stages = [{"stage": "detect: YOLOv9-E forward (gemm_tcgen05_kernel x233 + 19 HBM kernels)", "bound": "tensor", "ms": fwd_ms,
+                        "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                        "traffic": (stage_traffic.get("detect") or {}).get("dram_bytes", traffic)}]
+    if caption_stages and "encode" in caption_stages:
+        for key, label in (("encode", "caption encode: DaViT + projector + BART encoder + cross-KV"), ("decode_step", "caption decode step (6 layers + LM head + pick)")):
+            cs = caption_stages[key]
+            roofline_stages.append({"stage": label, "bound": "tensor", "ms": cs["ms"], "achieved": cs["logical_tflops"], "executed": cs["executed_tflops"],
+                                    "peak": peak_tf, "unit": "TFLOP/s", "frac": cs["logical_tflops"] / peak_tf, "frac_executed": cs["executed_frac_of_peak"],
+                                    "traffic": (stage_traffic.get(key) or {}).get("dram_bytes")})
+
+    # the reference's CPU-branch caption semantics (768x768 crops, ref:util/utils.py:123) on the GPU: extra figure, 2 screenshots
+    cap768 = None
+    if args.with_768:
+        try:
+            imgs, ocr = sets[0]
+            parse_screenshots(imgs[:2], model, cmp_, ocr[:2], BOX_TRESHOLD=args.box_threshold, iou_threshold=0.7,
+                              max_new_tokens=args.max_new_tokens, caption_size=768)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out768 = parse_screenshots(imgs[:2], model, cmp_, ocr[:2], BOX_TRESHOLD=args.box_threshold, iou_threshold=0.7,
+                                       max_new_tokens=args.max_new_tokens, caption_size=768)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            cap768 = {"screenshots_per_s": 2 / dt, "crops": int(sum(o[1].shape[0] for o in out768)), "note": "768x768 caption mode (the reference's CPU branch), batch of 2 screenshots, one batch at a time, host buffers"}
+            log(f"768-mode: {2 / dt:.2f} screenshots/s")
+        except Exception as exc:   # noqa: BLE001
+            cap768 = {"error": repr(exc)[:200]}
+
     if rank == 0:
         line = {"metric": "screenshots/sec", "value": value, "unit": "screenshots/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -399,12 +459,17 @@ def run_b200(args):
                              "traffic_note": "DRAM bytes per forward from the committed ncu launch list (caches flushed per kernel), not from this run",
                              "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})", "forward_ms": fwd_ms,
                              "algorithmic_gflop_per_forward": plan.flops / 1e9},
+                "roofline_stages": roofline_stages,
+                "e2e_pageable": None if ms_pg is None else {"value": world * B * args.steps / (ms_pg / 1e3), "unit": "screenshots/s", "ms_per_step": ms_pg / args.steps,
+                                                            "note": "same as e2e but the screenshots are plain pageable numpy arrays (staged through the pipeline's pinned slot)"},
+                "caption_768": cap768,
                 "verify": verify, "caption_stages": caption_stages, "p50_latency_ms_batch1": lat[len(lat) // 2],
                 "stage_ms_per_step": {k: 1e3 * float(np.mean([t[k] for t in tms2])) for k in ("detect_s", "glue_s", "caption_s")},
                 "boxes_per_screenshot": st["boxes"] / max(st["n"], 1), "crops_per_screenshot": st["crops"] / max(st["n"], 1)}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)
+    pipe.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -446,6 +511,7 @@ def main():
     ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp16"])
     ap.add_argument("--caption-768", action="store_true", help="reference arm only: the reference's CPU branch (768x768 crops)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--with-768", action="store_true", help="B200 arm: also time the 768x768 caption mode (extra key caption_768)")
     ap.add_argument("--no-pipeline", action="store_true", help="one batch at a time (no detect/caption overlap across steps)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -588,179 +588,6 @@ gemm_tcgen05_kernel_trace(const __grid_constant__ CUtensorMap tmA, const __grid_
   gemm_body<true>(tmA, tmB, g);
 }
 
-// ------------------------------------------------------------------------------------------- CTA-pair GEMM (opt-in)
-// B2P_CTA2=1: plain row GEMMs (mode 0, no split-K) with >= one wave of 256-row pair tiles run on clusters of two CTAs with
-// tcgen05 cta_group::2 -- ONE M = 256 MMA per k-step over [A_cta0; A_cta1] x [B_cta0; B_cta1]^T, every CTA holding its own
-// 128 rows of A and HALF of the B tile (bn/2 rows).  Fill per CTA and k-block: 16 KB + bn/2 x 128 B instead of 16 KB +
-// bn x 128 B, i.e. two thirds of the L2->SM traffic that bounds the single-CTA kernel (profiles/r1_gemm_notes.md).
-// Barrier ownership: "full" (TMA bytes of BOTH CTAs) and "TMEM empty" live in the leader (cluster rank 0), which issues
-// every MMA; "empty" and "TMEM full" exist in both CTAs and are signalled by the leader's multicast tcgen05.commit.
-// STATUS: written at the end of round 1 without hardware access -- compiled, never run; off unless B2P_CTA2 is set.
-__global__ void __launch_bounds__(kThreads, 1)
-gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t rank = cluster_ctarank();
-  const bool leader = rank == 0;
-  const uint32_t a_part = g.x3 ? 2u * kASlot : uint32_t(kASlot);
-  const uint32_t stage_bytes = a_part + (g.x3 ? 2u : 1u) * g.b_slot;          // g.b_slot: one HALF B tile (bn/2 rows)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(g.stages) * stage_bytes);
-  const uint32_t bar_full = smem_u32(bars);
-  const uint32_t bar_empty = bar_full + 8 * g.stages;
-  const uint32_t bar_tfull = bar_empty + 8 * g.stages;
-  const uint32_t bar_tempty = bar_tfull + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * g.stages + 4);
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < g.stages; ++s) {
-      mbar_init(bar_full + 8 * s, 1);     // leader's copy is the live one: one arrive.expect_tx per phase (leader producer)
-      mbar_init(bar_empty + 8 * s, 1);    // one multicast commit per phase
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 2 * kEpiWarps);   // the epilogue warps of BOTH CTAs release the leader's accumulator slot
-    }
-    mbar_fence_init();
-  }
-  if (warp == 2) {
-    tmem_alloc_pair(smem_u32(tmem_slot), kTmemCols);   // collective over the same warp of both CTAs
-    tmem_relinquish_pair();
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync();          // both CTAs' barriers exist before any remote arrive / TMA credit can reach them
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-
-  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int m2_tiles = (g.m_tiles + 1) >> 1;                    // 256-row pair tiles
-  const int total_items = m2_tiles * g.n_tiles;
-  const uint32_t smem_base = smem_u32(smem);
-  const int bn_half = g.bn >> 1;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ TMA producer (both CTAs)
-      const uint32_t lead_full = mapa_u32(bar_full, 0);         // shared::cluster address of the LEADER's full barriers
-      const uint32_t stage_tx = 2u * (g.x3 ? 2u : 1u) * (g.a_bytes + g.b_bytes);   // bytes of both CTAs per stage
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int item = pair; item < total_items; item += npairs) {
-        const int nt = g.mt_fast ? item / m2_tiles : item % g.n_tiles;
-        const int mt2 = g.mt_fast ? item % m2_tiles : item / g.n_tiles;
-        const int m0 = mt2 * 256 + int(rank) * kTileM;
-        const int nb0 = nt * g.bn + int(rank) * bn_half;
-        for (int kb = 0; kb < g.num_kb; ++kb) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-          if (leader) mbar_expect_tx(bar_full + 8 * stage, stage_tx);
-          const uint32_t fb = lead_full + 8 * stage;
-          const uint32_t sa = smem_base + stage * stage_bytes;
-          const uint32_t sb = sa + a_part;
-          tma_load_2d_pair(sa, &tmA, fb, kb * g.bk, m0);
-          tma_load_2d_pair(sb, &tmB, fb, kb * g.bk, nb0);
-          if (g.x3) {
-            tma_load_2d_pair(sa + kASlot, &tmA, fb, g.lo_a + kb * g.bk, m0);
-            tma_load_2d_pair(sb + g.b_slot, &tmB, fb, g.lo_b + kb * g.bk, nb0);
-          }
-          if (++stage == g.stages) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      // ------------------------------------------------------------ MMA issuer (leader CTA only)
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      const int ksteps = g.bk / 16;
-      for (int item = pair; item < total_items; item += npairs) {
-        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + uint32_t(acc * 256);
-        for (int kb = 0; kb < g.num_kb; ++kb) {
-          mbar_wait(bar_full + 8 * stage, phase);
-          tc_fence_after();
-          const uint32_t sa = smem_base + stage * stage_bytes;
-          const uint32_t sb = sa + a_part;
-          const uint64_t da = g.desc_hi | uint64_t((sa & 0x3FFFF) >> 4);
-          const uint64_t db = g.desc_hi | uint64_t((sb & 0x3FFFF) >> 4);
-          if (g.x3) {
-            const uint64_t da_lo = g.desc_hi | uint64_t(((sa + kASlot) & 0x3FFFF) >> 4);
-            const uint64_t db_lo = g.desc_hi | uint64_t(((sb + g.b_slot) & 0x3FFFF) >> 4);
-            for (int k = 0; k < ksteps; ++k) {
-              umma_f16_pair(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), g.idesc, (kb | k) != 0);
-              umma_f16_pair(d_tmem, da + uint64_t(2 * k), db_lo + uint64_t(2 * k), g.idesc, 1u);
-              umma_f16_pair(d_tmem, da_lo + uint64_t(2 * k), db + uint64_t(2 * k), g.idesc, 1u);
-            }
-          } else {
-            for (int k = 0; k < ksteps; ++k)
-              umma_f16_pair(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), g.idesc, (kb | k) != 0);
-          }
-          umma_commit_pair(bar_empty + 8 * stage, 3);      // frees this stage in BOTH CTAs
-          if (++stage == g.stages) { stage = 0; phase ^= 1; }
-        }
-        umma_commit_pair(bar_tfull + 8 * acc, 3);          // accumulator halves ready in both CTAs
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-      }
-    }
-  } else {
-    // -------------------------------------------------------------- epilogue (both CTAs, own 128 rows)
-    const int grp = warp & 3;
-    const int cq = (warp - 2) >> 2;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    const uint32_t lead_tempty = mapa_u32(bar_tempty, 0);
-    EpiCtx e;
-    e.outh = reinterpret_cast<__half*>(g.out);
-    e.outf = reinterpret_cast<float*>(g.out);
-    e.resh = reinterpret_cast<const __half*>(g.res);
-    e.resf = reinterpret_cast<const float*>(g.res);
-    for (int item = pair; item < total_items; item += npairs) {
-      const int nt = g.mt_fast ? item / m2_tiles : item % g.n_tiles;
-      const int mt2 = g.mt_fast ? item % m2_tiles : item / g.n_tiles;
-      const int n0 = nt * g.bn;
-      const long long pix = (long long)mt2 * 256 + (long long)rank * kTileM + grp * 32 + lane;
-      const bool valid = pix < g.M;
-      mbar_wait(bar_tfull + 8 * acc, acc_phase);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + (uint32_t(grp * 32) << 16) + uint32_t(acc * 256);
-      for (int c = cq * 16; c < g.bn; c += 64) {
-        uint32_t v[16];
-        tmem_ld16(t_row + c, v);
-        tmem_ld_wait();
-        if (n0 + c >= g.N) continue;   // warp-uniform
-        float x[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]);
-        epi_store16(g, e, x, n0 + c, pix, valid);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(lead_tempty + 8 * acc);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync();          // nobody leaves while its pair may still read its smem or signal its barriers
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc_pair(tmem_base, kTmemCols);
-  }
-}
-
 // ------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1050,59 +877,6 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
              (!d.bias || ((reinterpret_cast<uintptr_t>(d.bias) & 15) == 0));
   static const bool dbg = getenv("B2P_DEBUG") != nullptr;
   static const bool no_pdl = getenv("B2P_NO_PDL") != nullptr;
-  {
-    // opt-in CTA-pair path (see gemm_pair_kernel): plain row GEMMs with at least one wave of 256-row pair tiles
-    static const bool cta2 = getenv("B2P_CTA2") != nullptr;
-    const int m2_tiles = (g.m_tiles + 1) / 2;
-    if (cta2 && d.mode == 0 && ksplit == 1 && bn >= 64 && bn % 32 == 0 && g.m_tiles >= 2 &&
-        m2_tiles * g.n_tiles >= g_num_sms / 2) {
-      GemmArgs p = g;
-      CUtensorMap tmBh;
-      p.b_bytes = uint32_t(bn / 2) * bk * 2;
-      p.b_slot = (p.b_bytes + 1023) & ~1023u;
-      p.idesc = make_idesc(bn, d.bf16, 256);
-      cuuint64_t dims[2] = {cuuint64_t(xk) * cuuint64_t(Ktot), cuuint64_t(d.N)};
-      cuuint64_t str[1] = {cuuint64_t(xk) * cuuint64_t(Ktot) * 2};
-      cuuint32_t box[2] = {cuuint32_t(bk), cuuint32_t(bn / 2)};
-      if (int e = encode(&tmBh, d.bf16, 2, d.B, dims, str, box, bk)) return e;
-      const int sb = xk * (kASlot + int(p.b_slot));
-      int st2 = (g_max_smem - 1024 - 512) / sb;
-      if (st2 > kMaxStages) st2 = kMaxStages;
-      if (st2 > p.num_kb && p.num_kb >= 2) st2 = p.num_kb;
-      if (st2 < 2) st2 = 2;
-      p.stages = st2;
-      p.kb_per = p.num_kb;
-      p.mt_fast = (m2_tiles > 1 && (long long)d.N > (long long)d.M) ? 1 : 0;
-      const int items = m2_tiles * p.n_tiles;
-      const int pairs = items < g_num_sms / 2 ? items : g_num_sms / 2;
-      static std::atomic<bool> attr_set{false};
-      if (!attr_set.load()) {
-        if (cudaFuncSetAttribute(gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem) != cudaSuccess)
-          return set_error("cudaFuncSetAttribute(gemm_pair_kernel) failed");
-        attr_set = true;
-      }
-      if (dbg)
-        fprintf(stderr, "b2p_gemm PAIR M=%d N=%d Ktot=%d bk=%d bn=%d m2_tiles=%d n_tiles=%d stages=%d pairs=%d x3=%d\n", d.M, d.N, Ktot, bk,
-                bn, m2_tiles, p.n_tiles, st2, pairs, p.x3);
-      cudaLaunchConfig_t cfg2{};
-      cfg2.gridDim = dim3(2 * pairs);
-      cfg2.blockDim = dim3(kThreads);
-      cfg2.dynamicSmemBytes = size_t(st2) * sb + 1024 + 512;
-      cfg2.stream = st;
-      cudaLaunchAttribute at2[2];
-      at2[0].id = cudaLaunchAttributeClusterDimension;
-      at2[0].val.clusterDim.x = 2; at2[0].val.clusterDim.y = 1; at2[0].val.clusterDim.z = 1;
-      at2[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      at2[1].val.programmaticStreamSerializationAllowed = 1;
-      cfg2.attrs = at2;
-      cfg2.numAttrs = no_pdl ? 1 : 2;
-      cudaError_t ce2 = cudaLaunchKernelEx(&cfg2, gemm_pair_kernel, tmA, tmBh, p);
-      if (ce2 == cudaSuccess) ce2 = cudaGetLastError();
-      if (ce2 != cudaSuccess) return set_error(cudaGetErrorString(ce2));
-      count_launch();
-      return 0;
-    }
-  }
   const int total = g.m_tiles * g.n_tiles * g.ksplit;
   const int grid = total < g_num_sms ? total : g_num_sms;
   if (grid <= 0) return 0;

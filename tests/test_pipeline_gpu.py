@@ -29,11 +29,7 @@ def _same_elements(got, ref, ids_got, ids_ref):
     assert ids_got.tolist() == (ids_ref.tolist() if torch.is_tensor(ids_ref) else ids_ref)
 
 
-_UNVALIDATED = pytest.mark.skipif(not os.environ.get("B2P_TEST_UNVALIDATED"),
-                                  reason="added after the round-1 GPU budget was spent; B2P_TEST_UNVALIDATED=1 runs it")
-
-
-@pytest.mark.parametrize("name", ["synth_seed0", "synth_seed3_odd", pytest.param("synth_seed5_3240x2160", marks=_UNVALIDATED)])
+@pytest.mark.parametrize("name", ["synth_seed0", "synth_seed3_odd", "synth_seed5_3240x2160"])
 def test_after_detection_equals_reference_golden(name):
     det, cmp_ = ge.standin_models(DEV)
     g = json.loads((GOLD / f"{name}.json").read_text())
@@ -131,7 +127,6 @@ def test_pipelined_parser_equals_sequential(lanes):
                 assert ge_ == re_
 
 
-@_UNVALIDATED
 @pytest.mark.parametrize("lanes,group", [(1, 2), (2, 2), (2, 3)])
 def test_grouped_captioning_equals_sequential(lanes, group):
     """caption_group > 1: the crops of several batches go through Florence-2 in one pass; per-batch results unchanged."""
