@@ -125,7 +125,7 @@ __global__ void dwconv_ln_kernel(const float* __restrict__ x, int B, int H, int 
   }
 }
 
-// Tiled variant (opt-in, split bit 1 / B2P_DWCONV_TILE=1; written at the end of round 1, not yet run on hardware): one CTA
+// Tiled variant (split bit 1; the default since it was validated on the B200 in round 2, B2P_NO_DWCONV_TILE=1 disables it): one CTA
 // per image stages the whole H x W x C map in shared memory once, so the nine taps read smem instead of re-reading L2 nine
 // times (the per-token kernel above moves ~36 B per element through L2: 24 us per launch where HBM needs 5).  Same
 // arithmetic in the same order as dwconv_ln_kernel => bit-identical outputs (tests/test_ops_gpu.py, gated).
@@ -222,7 +222,7 @@ __global__ void dwconv3x3_res_kernel(const float* __restrict__ x, int B, int H, 
 // v = bias_v) with multiplicity n_pad = 144 - n_real.  One CTA per (batch, window, head); one thread per query.
 template <int D>
 __global__ void window_attn_kernel(const float* __restrict__ qkv, const float* __restrict__ qkv_bias, int B, int H,
-                                   int W, int C, int heads, int win, __half* __restrict__ out, int split) {
+                                   int W, int C, int heads, int win, __half* __restrict__ out, int split, int kv_cap) {
   pdl_wait();   // PDL: inputs come from the previous kernel in the stream
   extern __shared__ float4 sm4[];
   constexpr int D4 = D / 4;
@@ -236,7 +236,7 @@ __global__ void window_attn_kernel(const float* __restrict__ qkv, const float* _
   const int ny = min(win, H - y0), nx = min(win, W - x0);
   const int nreal = ny * nx, npad = win * win - nreal;
   float4* Ks = sm4;                       // [nreal][D4]
-  float4* Vs = sm4 + win * win * D4;      // [nreal][D4]
+  float4* Vs = sm4 + kv_cap * D4;         // [nreal][D4]; kv_cap = most real tokens any window of this map holds
   for (int i = threadIdx.x; i < nreal * D4; i += blockDim.x) {
     const int t = i / D4, d = i - t * D4;
     const long long tok = ((long long)b * H + y0 + t / nx) * W + x0 + t % nx;
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(256) channel_attn_kernel(const float* __restri
   }
 }
 
-// Small-N variant (opt-in, split bit 1 / B2P_CHATTN_SMALL=1; written at the end of round 1, not yet run on hardware): for
+// Small-N variant (split bit 1; the default since it was validated on the B200 in round 2, B2P_NO_CHATTN_SMALL=1 disables it): for
 // the 4x4 / 2x2 maps of the 64x64-crop mode (N <= 16 tokens) the 256-thread CTA above is almost all synchronisation; here
 // ONE WARP owns a (batch, group) pair, 4 pairs per CTA.  Same sums in the same order => bit-identical outputs.
 __global__ void __launch_bounds__(128) channel_attn_small_kernel(const float* __restrict__ qkv, int B, int N, int C, int groups,
@@ -708,7 +708,10 @@ int b2p_window_attn(const float* qkv, const float* qkv_bias, int B, int H, int W
                     int split, cudaStream_t st) {
   if (C / heads != 32) return set_error("window_attn: head_dim must be 32");
   const int nw = ((W + win - 1) / win) * ((H + win - 1) / win);
-  const size_t smem = size_t(2) * win * win * 32 * sizeof(float);
+  // K/V staging sized by the REAL tokens of a window: the 4x4 / 2x2 maps of the 64x64-crop mode need 4 KB / 1 KB, not the
+  // 36.9 KB of a full 12x12 window (which capped those launches at 6 one-warp CTAs per SM: ~100 us each, r1 step table)
+  const int kv_cap = (W < win ? W : win) * (H < win ? H : win);
+  const size_t smem = size_t(2) * kv_cap * 32 * sizeof(float);
   if (int e = bind_device()) return e;
   static std::atomic<bool> attr{false};
   if (!attr) {
@@ -717,9 +720,9 @@ int b2p_window_attn(const float* qkv, const float* qkv_bias, int B, int H, int W
   }
   if (smem > 64 * 1024) return set_error("window_attn: window too large");
   // one thread per query of the window: small maps (4x4, 8x8 in the 64x64-crop mode) get small CTAs so more of them fit per SM
-  const int nq = (W < win ? W : win) * (H < win ? H : win);
+  const int nq = kv_cap;
   const int threads = nq >= 160 ? 160 : ((nq + 31) / 32) * 32;
-  launch_pdl(window_attn_kernel<32>, dim3(B * nw * heads), dim3(threads), smem, st, qkv, qkv_bias, B, H, W, C, heads, win, (__half*)out, split ? C : 0);
+  launch_pdl(window_attn_kernel<32>, dim3(B * nw * heads), dim3(threads), smem, st, qkv, qkv_bias, B, H, W, C, heads, win, (__half*)out, split ? C : 0, kv_cap);
   B2P_CHECK_LAUNCH();
   return 0;
 }

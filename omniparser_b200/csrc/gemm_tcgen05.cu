@@ -35,8 +35,14 @@ struct GemmArgs {
   int m_tiles, n_tiles, stages, ldpar;
   int nb;                // images per tile (small maps: a TMA box spans nb consecutive images)
   int tw_valid;          // valid output columns per tile row (== tw except in halo mode, where tw is the halo pitch)
-  int stagesA, cin;      // halo mode: A ring depth, Cin
-  uint32_t a_slot;       // halo mode: bytes per A slot
+  int stagesA, cin;      // separate-pipeline modes: A ring depth; Cin
+  uint32_t a_slot;       // separate-pipeline modes: bytes per A slot
+  // sep: A and B move through SEPARATE pipelines (always in halo mode 3, where one A tile feeds nine weight taps).
+  // bres (implies sep): the WHOLE weight matrix of this launch (n_tiles == 1) stays resident in shared memory -- every B
+  // k-block is loaded once per CTA, on its first work item, and the persistent loop afterwards streams only A tiles.  For
+  // the small-channel layers (N, Cin <= 64..256 on the 160x160 / 80x80 maps: 10+ tiles per CTA) the weight re-loads and
+  // their barrier round trips were the per-tile critical path (3.5 us per 128-pixel tile, profiles/r2_notes.md).
+  int sep, bres, taps;
   int ksplit, kb_per;    // split-K: work item = (m tile, n tile, k slice); the last CTA of a tile reduces + stores
   uint32_t a_bytes, b_bytes, b_slot;
   uint32_t idesc;
@@ -228,8 +234,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t a_part = g.x3 ? 2u * kASlot : uint32_t(kASlot);                     // [A_hi][A_lo] | [A]
-  const uint32_t stage_bytes = (g.mode == 3) ? g.b_slot : a_part + (g.x3 ? 2u : 1u) * g.b_slot;
-  const uint32_t a_region = (g.mode == 3) ? uint32_t(g.stagesA) * g.a_slot : 0u;   // halo mode: [A slots][B slots]
+  const uint32_t stage_bytes = g.sep ? g.b_slot : a_part + (g.x3 ? 2u : 1u) * g.b_slot;
+  const uint32_t a_region = g.sep ? uint32_t(g.stagesA) * g.a_slot : 0u;   // separate pipelines: [A slots][B slots]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + a_region + size_t(g.stages) * stage_bytes);
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = bar_full + 8 * g.stages;
@@ -304,21 +310,54 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
           img *= g.nb;   // nb > 1 only when one tile covers whole images (per_img == 1)
         }
         const int kb0 = ks * g.kb_per, kb1 = min(g.num_kb, kb0 + g.kb_per);
-        if (g.mode == 3) {
-          // halo mode: ONE (th+2) x (tw+2) input tile per 64-channel block feeds all nine taps (the MMA side shifts
-          // the smem descriptor start address by (ky*pitch + kx) rows); only the weights stream per tap.
-          for (int cb = kb0; cb < kb1; ++cb) {
+        if (g.sep) {
+          // separate pipelines.  Halo mode (3): ONE (th+2) x (tw+2) input tile per channel block feeds all nine taps (the MMA
+          // side shifts the smem descriptor start address by (ky*pitch + kx) rows); only the weights stream per tap.
+          // Other modes: one A tile per k-block.  Resident weights (bres): B slot (unit*taps + tap) is filled on this CTA's
+          // first item only and never released.
+          const bool first_item = (item == int(blockIdx.x));
+          for (int u = kb0; u < kb1; ++u) {
             mbar_wait(bar_aempty + 8 * stageA, phaseA ^ 1);
             const uint32_t fa = bar_afull + 8 * stageA;
+            const uint32_t dstA = smem_base + stageA * g.a_slot;
             mbar_expect_tx(fa, g.a_bytes);
-            tma_load_4d(smem_base + stageA * g.a_slot, &tmA, fa, cb * g.bk, x0 - 1, y0 - 1, img);
-            if constexpr (kTrace) { if (item == blockIdx.x && cb == kb0) trace_stamp<kTrace>(g, kTrFirstTma); }
+            int bcol0;
+            if (g.mode == 3) {
+              tma_load_4d(dstA, &tmA, fa, u * g.bk, x0 - 1, y0 - 1, img);
+              bcol0 = u * g.bk;                                   // + tap * cin below
+            } else if (g.mode == 0) {
+              tma_load_2d(dstA, &tmA, fa, u * g.bk, mt * kTileM);
+              bcol0 = u * g.bk;
+            } else {
+              const int tap = u / g.cin_blocks;
+              const int c0 = (u - tap * g.cin_blocks) * g.bk;
+              const int ky = tap / 3, kx = tap - ky * 3;
+              bcol0 = tap * g.b_tap + c0;
+              if (g.mode == 1) {
+                tma_load_4d(dstA, &tmA, fa, c0, x0 + kx - 1, y0 + ky - 1, img);
+              } else {
+                const int py = (ky != 1), px = (kx != 1);
+                const int yo = y0 - (ky == 0), xo = x0 - (kx == 0);
+                tma_load_5d(dstA, &tmA, fa, c0 + px * g.ldpar, xo, py, yo, img);
+              }
+            }
+            if constexpr (kTrace) { if (item == blockIdx.x && u == kb0) trace_stamp<kTrace>(g, kTrFirstTma); }
             if (++stageA == g.stagesA) { stageA = 0; phaseA ^= 1; }
-            for (int tap = 0; tap < 9; ++tap) {
+            for (int tap = 0; tap < g.taps; ++tap) {
+              const int bcol = (g.mode == 3) ? tap * g.cin + bcol0 : bcol0;
+              if (g.bres) {
+                if (first_item) {
+                  const int slot = (u - kb0) * g.taps + tap;
+                  const uint32_t fb = bar_full + 8 * slot;
+                  mbar_expect_tx(fb, g.b_bytes);
+                  tma_load_2d(smem_base + a_region + slot * stage_bytes, &tmB, fb, bcol, n0);
+                }
+                continue;
+              }
               mbar_wait(bar_empty + 8 * stage, phase ^ 1);
               const uint32_t fb = bar_full + 8 * stage;
               mbar_expect_tx(fb, g.b_bytes);
-              tma_load_2d(smem_base + a_region + stage * stage_bytes, &tmB, fb, tap * g.cin + cb * g.bk, n0);
+              tma_load_2d(smem_base + a_region + stage * stage_bytes, &tmB, fb, bcol, n0);
               if (++stage == g.stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -372,26 +411,33 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(acc * 256);
-        if (g.mode == 3) {
-          for (int cb = kb0; cb < kb1; ++cb) {
+        if (g.sep) {
+          for (int u = kb0; u < kb1; ++u) {
             mbar_wait(bar_afull + 8 * stageA, phaseA);
             const uint32_t sa0 = smem_base + stageA * g.a_slot;
-            for (int tap = 0; tap < 9; ++tap) {
-              mbar_wait(bar_full + 8 * stage, phase);
+            for (int tap = 0; tap < g.taps; ++tap) {
+              // resident weights: slot (unit, tap) completed its one and only phase (parity 0) on the first item
+              const int slot = g.bres ? (u - kb0) * g.taps + tap : stage;
+              mbar_wait(bar_full + 8 * slot, g.bres ? 0u : phase);
               tc_fence_after();
-              if constexpr (kTrace) { if (item == blockIdx.x && cb == kb0 && tap == 0) trace_stamp<kTrace>(g, kTrFirstFull); }
-              const int ky = tap / 3, kx = tap - ky * 3;
-              const uint32_t sa = sa0 + uint32_t(ky * g.tw + kx) * uint32_t(2 * g.bk);   // shifted view of the halo tile
-              const uint32_t sb = smem_base + a_region + stage * stage_bytes;
+              if constexpr (kTrace) { if (item == blockIdx.x && u == kb0 && tap == 0) trace_stamp<kTrace>(g, kTrFirstFull); }
+              uint32_t sa = sa0;
+              if (g.mode == 3) {
+                const int ky = tap / 3, kx = tap - ky * 3;
+                sa = sa0 + uint32_t(ky * g.tw + kx) * uint32_t(2 * g.bk);   // shifted view of the halo tile
+              }
+              const uint32_t sb = smem_base + a_region + slot * stage_bytes;
               // The 128B-swizzle pattern is anchored at the 1024-B aligned slot base (that is how TMA wrote it), so the
               // "matrix base offset" field stays 0 even though the start address points into the middle of an atom:
               // the XOR phase is taken from the address bits, exactly as for the +32 B K-advance.
               const uint64_t da = g.desc_hi | uint64_t((sa & 0x3FFFF) >> 4);
               const uint64_t db = g.desc_hi | uint64_t((sb & 0x3FFFF) >> 4);
               for (int k = 0; k < ksteps; ++k)
-                umma_f16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), g.idesc, ((cb - kb0) | tap | k) != 0);
-              umma_commit(bar_empty + 8 * stage);
-              if (++stage == g.stages) { stage = 0; phase ^= 1; }
+                umma_f16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), g.idesc, ((u - kb0) | tap | k) != 0);
+              if (!g.bres) {
+                umma_commit(bar_empty + 8 * stage);
+                if (++stage == g.stages) { stage = 0; phase ^= 1; }
+              }
             }
             umma_commit(bar_aempty + 8 * stageA);
             if (++stageA == g.stagesA) { stageA = 0; phaseA ^= 1; }
@@ -844,6 +890,31 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
   static const bool no_split = getenv("B2P_NO_SPLITK") != nullptr;
   const int slot = no_split ? -1 : ws_slot_for(st);
   pick_tiling(d.N, g.m_tiles, g.num_kb, halo ? 9 * bk : bk, g.a_bytes, d.bn_max > 0 ? d.bn_max : 256, slot >= 0, d.x3 != 0, &bn, &ksplit);
+  // Resident weights: one N tile, no split-K, at least one full wave of M tiles, and the whole weight matrix + a >= 2-deep
+  // A ring must fit in shared memory (see GemmArgs::bres).
+  static const bool no_res = getenv("B2P_NO_BRES") != nullptr;
+  bool bres = false;
+  int res_slots = 0, res_stagesA = 0;
+  const uint32_t a_slot_sep = halo ? g.a_slot : uint32_t(kASlot);
+  if (!no_res && !d.x3 && d.N <= 256 && g.m_tiles >= g_num_sms && (d.bn_max <= 0 || d.bn_max >= d.N)) {
+    static const int cand[] = {16, 32, 48, 64, 96, 128, 192, 256};
+    int bnr = 256;
+    for (int c : cand) if (c >= d.N) { bnr = c; break; }
+    const uint32_t bslot = (uint32_t(bnr) * bk * 2 + 1023) & ~1023u;
+    res_slots = halo ? g.cin_blocks * 9 : g.num_kb;
+    const long long bar_bytes = 8LL * (2 * res_slots + 4 + 2 * 8) + 64;
+    const long long avail = (long long)g_max_smem - 1024 - ((bar_bytes + 1023) & ~1023LL) - (long long)res_slots * bslot;
+    if (avail >= 2LL * a_slot_sep) {
+      bres = true;
+      bn = bnr;
+      ksplit = 1;
+      res_stagesA = int(avail / a_slot_sep);
+      if (res_stagesA > 8) res_stagesA = 8;
+    }
+  }
+  g.bres = bres ? 1 : 0;
+  g.sep = (halo || bres) ? 1 : 0;
+  g.taps = halo ? 9 : 1;
   g.bn = bn;
   g.ksplit = ksplit;
   g.kb_per = (g.num_kb + ksplit - 1) / ksplit;
@@ -861,15 +932,31 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
     cuuint32_t box[2] = {cuuint32_t(bk), cuuint32_t(bn)};
     if (int e = encode(&tmB, d.bf16, 2, d.B, dims, str, box, bk)) return e;
   }
-  const int stage_bytes = halo ? int(g.b_slot) : xk * (kASlot + int(g.b_slot));
-  g.stagesA = halo ? 2 : 0;
-  const int a_region = halo ? g.stagesA * int(g.a_slot) : 0;
-  int stages = (g_max_smem - 1024 - 512 - a_region) / stage_bytes;
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (!halo && stages > g.kb_per && g.kb_per >= 2 && g.ksplit == 1) stages = g.kb_per;
-  if (stages < 2) stages = 2;
+  const int stage_bytes = g.sep ? int(g.b_slot) : xk * (kASlot + int(g.b_slot));
+  int stages, bar_space = 512;
+  if (bres) {
+    g.a_slot = a_slot_sep;
+    g.stagesA = res_stagesA;
+    stages = res_slots;                                   // every B k-block (x tap) owns a slot for the whole launch
+    bar_space = int((8LL * (2 * stages + 4 + 2 * g.stagesA) + 64 + 1023) & ~1023LL);
+  } else if (halo) {
+    // B ring first (up to 8 taps in flight), then as deep an A ring as fits (2..4 halo tiles)
+    stages = (g_max_smem - 1024 - 512 - 2 * int(g.a_slot)) / stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) stages = 2;
+    int sa = (g_max_smem - 1024 - 512 - stages * stage_bytes) / int(g.a_slot);
+    g.stagesA = sa > 4 ? 4 : (sa < 2 ? 2 : sa);
+  } else {
+    g.stagesA = 0;
+    stages = (g_max_smem - 1024 - 512) / stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages > g.kb_per && g.kb_per >= 2 && g.ksplit == 1) stages = g.kb_per;
+    if (stages < 2) stages = 2;
+  }
+  const int a_region = g.sep ? g.stagesA * int(g.a_slot) : 0;
   g.stages = stages;
-  const size_t smem = size_t(a_region) + size_t(stages) * stage_bytes + 1024 + 512;
+  const size_t smem = size_t(a_region) + size_t(stages) * stage_bytes + 1024 + bar_space;
+  if (smem > size_t(g_max_smem)) return set_error("gemm: internal error, shared-memory plan exceeds the device limit");
   // vector epilogue needs 16-byte aligned rows in out / residual and bias
   const int esz = d.out_f32 ? 4 : 2;
   g.vec_ok = ((reinterpret_cast<uintptr_t>(d.out) & 15) == 0) && ((d.ldc * esz) % 16 == 0) &&
@@ -881,9 +968,9 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
   const int grid = total < g_num_sms ? total : g_num_sms;
   if (grid <= 0) return 0;
   if (dbg)
-    fprintf(stderr, "b2p_gemm mode=%d M=%d N=%d Ktot=%d bk=%d bn=%d tw=%d th=%d m_tiles=%d n_tiles=%d stages=%d grid=%d act=%d f32=%d res=%d ksplit=%d x3=%d\n",
+    fprintf(stderr, "b2p_gemm mode=%d M=%d N=%d Ktot=%d bk=%d bn=%d tw=%d th=%d m_tiles=%d n_tiles=%d stages=%d grid=%d act=%d f32=%d res=%d ksplit=%d x3=%d bres=%d stagesA=%d\n",
             g.mode, d.mode == 0 ? d.M : g.m_tiles * 128, d.N, Ktot, bk, bn, g.tw, g.th, g.m_tiles, g.n_tiles, stages, grid,
-            d.act, d.out_f32, d.res != nullptr, ksplit, g.x3);
+            d.act, d.out_f32, d.res != nullptr, ksplit, g.x3, g.bres, g.stagesA);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);

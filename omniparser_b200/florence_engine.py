@@ -175,8 +175,10 @@ class FlorencePlan:
         assert size in (64, 768)
         self.S = size
         self.tag = f"florence{instance}"
-        self.dw_tile = bool(os.environ.get("B2P_DWCONV_TILE"))   # opt-in smem-tiled dwconv+LN (unvalidated)
-        self.ca_small = bool(os.environ.get("B2P_CHATTN_SMALL"))   # opt-in warp-per-group channel attention for N <= 16 (unvalidated)
+        # smem-tiled dwconv+LN and warp-per-group channel attention (N <= 16): bit-identical with the per-token / per-CTA kernels
+        # (tests/test_ops_gpu.py, validated on the B200 in round 2); B2P_NO_DWCONV_TILE / B2P_NO_CHATTN_SMALL select the old ones
+        self.dw_tile = not os.environ.get("B2P_NO_DWCONV_TILE")
+        self.ca_small = not os.environ.get("B2P_NO_CHATTN_SMALL")
         self.warmed = False
         import threading
         self.lock = threading.Lock()

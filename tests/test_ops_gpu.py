@@ -27,7 +27,9 @@ def _act(x, act):
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 64, 128), (256, 256, 256), (300, 200, 192), (37, 24, 32),
                                    (1000, 320, 160), (129, 1, 256), (4096, 768, 768), (60, 3072, 768),
                                    (480, 1000, 3072), (25600, 128, 32), (13, 51289, 768),
-                                   (416, 768, 9216), (416, 2304, 2304), (100, 64, 4608)])
+                                   (416, 768, 9216), (416, 2304, 2304), (100, 64, 4608),
+                                   # >= one wave of M tiles with N <= 256: the weight-resident path (GemmArgs::bres)
+                                   (30000, 64, 64), (40000, 256, 256), (20001, 192, 256), (19000, 16, 32), (25600, 128, 128)])
 @pytest.mark.parametrize("cfg", [dict(), dict(bias=True, act=ops.ACT_SILU), dict(bias=True, act=ops.ACT_GELU, res=True),
                                  dict(bias=True, res=True, out_f32=True)])
 def test_gemm(M, N, K, cfg):
@@ -70,7 +72,10 @@ def test_gemm_strided_views():
                                                     (3, 34, 60, 64, 64, 1), (1, 160, 160, 64, 64, 1),
                                                     (1, 40, 40, 256, 64, 2), (2, 80, 80, 128, 128, 2),
                                                     (1, 320, 320, 64, 128, 2), (1, 22, 38, 32, 48, 2),
-                                                    (37, 16, 16, 128, 64, 2), (10, 8, 8, 256, 96, 2), (5, 4, 4, 64, 48, 2)])
+                                                    (37, 16, 16, 128, 64, 2), (10, 8, 8, 256, 96, 2), (5, 4, 4, 64, 48, 2),
+                                                    # weight-resident path: halo (s1) and parity-view (s2) convs with >= 148 tiles
+                                                    (4, 160, 160, 32, 32, 1), (2, 160, 160, 64, 64, 1), (8, 80, 80, 64, 64, 1),
+                                                    (2, 320, 320, 64, 128, 2), (3, 160, 160, 32, 64, 2), (2, 161, 159, 32, 48, 1)])
 def test_conv3x3(B, H, W, Cin, Cout, stride):
     g = torch.Generator(device="cpu").manual_seed(B + H + Cin + Cout + stride)
     ld = Cin + 64

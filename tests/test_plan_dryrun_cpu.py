@@ -146,21 +146,21 @@ def test_florence_plan_768(rec, florence):
     assert len(rec.calls) == n_all - 1 and rec.calls[0][0] == "b2p_im2col_u8"
 
 
-def test_opt_in_kernel_flags_are_forwarded(rec, florence, monkeypatch):
+def test_kernel_variant_flags_are_forwarded(rec, florence, monkeypatch):
     from omniparser_b200.florence_engine import FlorencePlan, FlorenceWeights
-    monkeypatch.setenv("B2P_DWCONV_TILE", "1")
-    monkeypatch.setenv("B2P_CHATTN_SMALL", "1")
+    monkeypatch.delenv("B2P_NO_DWCONV_TILE", raising=False)
+    monkeypatch.delenv("B2P_NO_CHATTN_SMALL", raising=False)
     w = FlorenceWeights(florence.state_dict(), torch.device("cpu"), FS.GEN, "fp16x3")
     p = FlorencePlan(w, 2, 2, FS.PROMPT_IDS, use_graph=False, size=64)
     p.encode()
-    assert {c[1][-2] for c in rec.calls if c[0] == "b2p_dwconv_ln"} == {3}
+    assert {c[1][-2] for c in rec.calls if c[0] == "b2p_dwconv_ln"} == {3}        # default: smem-tiled / warp-per-group variants
     assert {c[1][-2] for c in rec.calls if c[0] == "b2p_channel_attn"} == {3}
     rec.calls.clear()
-    monkeypatch.delenv("B2P_DWCONV_TILE")
-    monkeypatch.delenv("B2P_CHATTN_SMALL")
+    monkeypatch.setenv("B2P_NO_DWCONV_TILE", "1")
+    monkeypatch.setenv("B2P_NO_CHATTN_SMALL", "1")
     p = FlorencePlan(w, 2, 2, FS.PROMPT_IDS, use_graph=False, size=64)
     p.encode()
-    assert {c[1][-2] for c in rec.calls if c[0] in ("b2p_dwconv_ln", "b2p_channel_attn")} == {1}   # the validated default
+    assert {c[1][-2] for c in rec.calls if c[0] in ("b2p_dwconv_ln", "b2p_channel_attn")} == {1}   # the round-1 kernels
 
 
 def test_yolo_plan(rec):
