@@ -99,7 +99,50 @@ def facade_golden(path, fl):
     print("wrote", out, len(parsed), "elements,", ids.shape[0], "captions")
 
 
+# Real screenshots shipped with the reference (ref:imgs/*), parsed with the ScreenSpot-Pro eval's call-site parameters
+# (ref:eval/ss_pro_gpt4o_omniv2.py:37-51: draw_bbox_config scaled by max(size)/3200, BOX_TRESHOLD 0.05, iou_threshold 0.7,
+# output_coord_in_ratio, image passed as a PATH).  BASELINE configs[0] = imgs/demo_image.jpg; configs[4]'s dataset is not
+# on disk, so the same call site is replayed on the reference's own images.  The images travel as fixtures
+# (tests/golden/imgs/, byte copies: /root/reference does not exist on the GPU box); OCR boxes are seeded (OCR is outside the path).
+REAL_CASES = [dict(name="real_demo_image", file="demo_image.jpg", seed=11), dict(name="real_omni3", file="omni3.jpg", seed=12),
+              dict(name="real_excel_rgba", file="excel.png", seed=13), dict(name="real_header_bar_thin", file="header_bar_thin.png", seed=14)]
+
+
+def eval_draw_config(size):
+    r = max(size) / 3200
+    return {"text_scale": 0.8 * r, "text_thickness": max(int(2 * r), 1), "text_padding": max(int(3 * r), 1), "thickness": max(int(3 * r), 1)}
+
+
+def real_goldens(ru, det, fl):
+    import shutil
+    (GOLDEN / "imgs").mkdir(exist_ok=True)
+    for case in REAL_CASES:
+        src = Path("/root/reference/imgs") / case["file"]
+        dst = GOLDEN / "imgs" / case["file"]
+        if not dst.exists():
+            shutil.copyfile(src, dst)
+        image = Image.open(dst)
+        w, h = image.size
+        texts, boxes = synth.ocr_boxes(case["seed"], w, h)
+        raw = det.predict(image.convert("RGB"), conf=BOX_TRESHOLD, iou=0.1)[0].boxes
+        cm = _Model(fl)
+        cfg = eval_draw_config(image.size)
+        png, coords, parsed = ru.get_som_labeled_img(str(dst), det, BOX_TRESHOLD=BOX_TRESHOLD, output_coord_in_ratio=True, ocr_bbox=boxes,
+                                                   draw_bbox_config=cfg, caption_model_processor={"model": cm, "processor": _Processor()},
+                                                   ocr_text=texts, use_local_semantics=True, iou_threshold=IOU, scale_img=False, batch_size=128)
+        ids = torch.cat(cm.ids, 0) if cm.ids else torch.zeros((0, 1), dtype=torch.long)
+        gold = dict(case=dict(case, size=[w, h], mode=image.mode), box_threshold=BOX_TRESHOLD, iou_threshold=IOU, max_new_tokens=20,
+                    draw_bbox_config=cfg, ocr_text=texts, ocr_bbox=boxes,
+                    det_xyxy=[[float(np.float32(v)) for v in b] for b in raw.xyxy.tolist()], det_conf=[float(c) for c in raw.conf.tolist()],
+                    parsed_content_list=parsed, caption_ids=ids.tolist(), label_coordinates=coords,
+                    overlay_sha256=_overlay_sha(png, (w, h)))
+        out = GOLDEN / f"{case['name']}.json"
+        out.write_text(json.dumps(gold, default=lambda o: float(o) if isinstance(o, (np.floating,)) else o.tolist()))
+        print("wrote", out, len(raw.xyxy), "boxes,", ids.shape[0], "captions", flush=True)
+
+
 def main():
+    import sys
     ru, ry = import_reference()
     m = yolo_standin(0)
     path = Path("/tmp/b2p_golden/icon_detect_v3/model.pt")
@@ -107,6 +150,9 @@ def main():
     det = ru.get_yolo_model(str(path), device="cpu")
     assert type(det).__name__ == "YOLOv9Detector"
     fl = FS.florence_standin(0)
+    if "real" in sys.argv[1:]:          # python -m oracle.make_golden real  -> only the real-image goldens
+        real_goldens(ru, det, fl)
+        return
     for case in CASES:
         w, h = case["size"]
         img = synth.screenshot(case["seed"], w, h)
@@ -127,6 +173,7 @@ def main():
         out.write_text(json.dumps(gold, default=lambda o: float(o) if isinstance(o, (np.floating,)) else o.tolist()))
         print("wrote", out, len(raw.xyxy), "boxes,", ids.shape[0], "captions")
     facade_golden(path, fl)
+    real_goldens(ru, det, fl)
 
 
 if __name__ == "__main__":

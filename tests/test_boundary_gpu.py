@@ -174,6 +174,29 @@ def test_get_som_labeled_img_reproduces_reference_golden_end_to_end(loaded, name
     print(f"{name}: {len(elems)} elements, {ev} integer-boundary events, label coords within {dc:.1e} px, {100 * frac:.4f} % overlay pixels differ")
 
 
+@pytest.mark.parametrize("name", ["real_demo_image", "real_omni3", "real_excel_rgba", "real_header_bar_thin"])
+def test_real_images_with_eval_call_site_parameters(loaded, name):
+    """BASELINE configs[0] / configs[4]: the reference repo's own screenshots (byte copies under tests/golden/imgs), passed as a
+    PATH with the ScreenSpot-Pro eval's parameters (ref:eval/ss_pro_gpt4o_omniv2.py:37-51) -- goldens written by the
+    unmodified reference (oracle/make_golden.py real_goldens).  RGBA / odd sizes / a 1280x90 strip included."""
+    det, cmp_ = loaded
+    g = json.loads((GOLD / f"{name}.json").read_text())
+    path = GOLD / "imgs" / g["case"]["file"]
+    w, h = g["case"]["size"]
+    cfg = g["draw_bbox_config"]
+    png, coords, elems = get_som_labeled_img(str(path), det, BOX_TRESHOLD=g["box_threshold"], output_coord_in_ratio=True,
+                                             ocr_bbox=g["ocr_bbox"], draw_bbox_config=cfg, caption_model_processor=cmp_,
+                                             ocr_text=g["ocr_text"], use_local_semantics=True, iou_threshold=g["iou_threshold"],
+                                             scale_img=False, batch_size=128)
+    ev = _same_elements(elems, g["parsed_content_list"], (w, h))
+    assert set(coords) == set(g["label_coordinates"])
+    dc = max(abs(float(x) - y) * s for k, v in coords.items() for x, y, s in zip(v, g["label_coordinates"][k], (w, h, w, h)))
+    assert dc <= 0.05, dc
+    img = np.asarray(Image.open(path).convert("RGB"))
+    frac = _overlay_close(png, img, g["parsed_content_list"], g["overlay_sha256"], cfg, (w, h))
+    print(f"{name}: {len(elems)} elements, {ev} integer-boundary events, label coords within {dc:.1e} px, {100 * frac:.4f} % overlay pixels differ")
+
+
 def test_handles_serialise_concurrent_callers(loaded):
     det, cmp_ = loaded
     model, proc = cmp_["model"], cmp_["processor"]

@@ -35,6 +35,20 @@ def test_label_coordinates_and_overlay_equal_reference_golden(name):
     assert back.shape == frame.shape and np.array_equal(back, frame)  # the fast PNG decodes to the reference's pixels
 
 
+@pytest.mark.parametrize("name", ["real_demo_image", "real_omni3", "real_excel_rgba", "real_header_bar_thin"])
+def test_real_image_overlay_with_eval_draw_config_equals_reference_golden(name):
+    """ref:imgs/* with the eval call site's draw_bbox_config (ref:eval/ss_pro_gpt4o_omniv2.py:38-44): label coordinates and
+    every pixel of the annotated image equal what the unmodified reference produced (oracle/make_golden.py real_goldens)."""
+    g = json.loads((GOLD / f"{name}.json").read_text())
+    img = np.asarray(Image.open(GOLD / "imgs" / g["case"]["file"]).convert("RGB"))
+    boxes = [e["bbox"] for e in g["parsed_content_list"]]
+    _, coords, frame = SO.som_outputs(img, boxes, True, **g["draw_bbox_config"])
+    assert set(coords) == set(g["label_coordinates"])
+    for k, v in g["label_coordinates"].items():
+        assert [float(x) for x in coords[k]] == v, (k, coords[k], v)
+    assert hashlib.sha256(frame.tobytes()).hexdigest() == g["overlay_sha256"]
+
+
 def test_float32_box_arithmetic_equals_torchvision():
     from torchvision.ops import box_convert
     rng = np.random.default_rng(5)
