@@ -109,6 +109,18 @@ int b2p_batched_nms(const float* box, const float* score, const int* cls, const 
                     double iou_thr, int max_det, const float* img_w, const float* img_h, int* keep_idx, float* out_box,
                     float* out_score, int* out_count, b2p_stream_t stream);
 
+/* ---- overlap filter on the device, ref:util/utils.py:241-319 (remove_overlap_new), :411-415 (int_box_area), :432, :444-451 ----
+ * Per screenshot b: the detector's kept boxes box_px[b][0..count[b]) (pixels, fp32, b2p_batched_nms output) and ocr_count[b]
+ * OCR boxes as fp32 RATIO boxes (int_box_area-filtered on the host, where their strings stay).  Same float64 arithmetic,
+ * comparisons and list order as the reference.  Outputs: icon_state[b][i] = 0 dropped | 1 kept, needs a caption | 2 kept,
+ * labelled by OCR text; label_mask[b][i][max_ocr/32] bit k = OCR box k labels icon i; ocr_removed[b][k]; icon_ratio = the
+ * fp32 ratio boxes (:432); crop_box / crop_img = the state-1 boxes of the whole batch in order (the crop list of
+ * b2p_crop_resize); crop_counts[0..B) per screenshot, crop_counts[B] the total.  `arrive` is a zeroed int the kernel resets. */
+int b2p_overlap_filter(const float* box_px, const int* count, int B, int max_det, const float* img_w, const float* img_h,
+                       const float* ocr_ratio, const int* ocr_count, int max_ocr, double iou_thr, int* icon_state,
+                       unsigned* label_mask, int* ocr_removed, float* icon_ratio, float* crop_box, int* crop_img,
+                       int* crop_counts, int* arrive, b2p_stream_t stream);
+
 /* ---- crop + resize, ref:util/utils.py:97-103 (numpy slice + cv2.resize(.., (64,64)), bit-exact) ---- */
 int b2p_crop_resize(const unsigned char* imgs, const int* img_hw, const long long* img_off, const float* boxes_ratio,
                     const int* box_img, int n_box, int out_hw, unsigned char* out, int* status, b2p_stream_t stream);

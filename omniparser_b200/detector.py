@@ -47,6 +47,7 @@ def _geometry(w: int, h: int, imgsz):
 class B200YOLOv9Detector:
     strides = (8, 16, 32)
     CAND_CAP = 16384
+    OCR_CAP = 256      # OCR boxes per screenshot the device overlap filter takes (host_glue.OCR_DEVICE_CAP); more -> host path
 
     def __init__(self, model_path: Union[str, Path, None] = None, device: Union[str, torch.device, None] = None,
                  state_dict: Dict[str, torch.Tensor] | None = None, use_graph: bool = True, precision: str | None = None):
@@ -127,6 +128,24 @@ class B200YOLOv9Detector:
                 out_box=torch.empty((B, max_det, 4), **f32), out_score=torch.empty((B, max_det), **f32),
                 out_count=torch.zeros((B,), dtype=torch.int32, device=dev),
             )
+            # device overlap filter (b2p_overlap_filter, ref:util/utils.py:241-319): OCR ratio boxes in, flags + crop list out
+            mo = self.OCR_CAP
+            i32 = dict(dtype=torch.int32, device=dev)
+            io.update(
+                max_ocr=mo,
+                ocr_ratio=torch.zeros((B, mo, 4), **f32), ocr_count=torch.zeros((B,), **i32),
+                host_ocr_ratio=torch.zeros((B, mo, 4), dtype=torch.float32).pin_memory(),
+                host_ocr_count=torch.zeros((B,), dtype=torch.int32).pin_memory(),
+                icon_state=torch.zeros((B, max_det), **i32), label_mask=torch.zeros((B, max_det, mo // 32), **i32),
+                ocr_removed=torch.zeros((B, mo), **i32), icon_ratio=torch.zeros((B, max_det, 4), **f32),
+                crop_box=torch.zeros((B * max_det, 4), **f32), crop_img=torch.zeros((B * max_det,), **i32),
+                crop_counts=torch.zeros((B + 1,), **i32), arrive=torch.zeros((1,), **i32),
+                host_state=torch.zeros((B, max_det), dtype=torch.int32).pin_memory(),
+                host_mask=torch.zeros((B, max_det, mo // 32), dtype=torch.int32).pin_memory(),
+                host_removed=torch.zeros((B, mo), dtype=torch.int32).pin_memory(),
+                host_ratio=torch.zeros((B, max_det, 4), dtype=torch.float32).pin_memory(),
+                host_crop_counts=torch.zeros((B + 1,), dtype=torch.int32).pin_memory(),
+            )
             self._io[key] = io
         return io
 
@@ -140,6 +159,38 @@ class B200YOLOv9Detector:
                         io["scale"], io["cap"], io["cand_box"], io["cand_score"], io["cand_cls"], io["cand_count"])
         ops.batched_nms(io["cand_box"], io["cand_score"], io["cand_cls"], io["cand_count"], B, io["cap"], iou, max_det,
                         io["img_w"], io["img_h"], io["keep"], io["out_box"], io["out_score"], io["out_count"])
+
+    def filter_device(self, io, B, H, W, ocr_elems, iou_threshold, max_det=300) -> bool:
+        """After :meth:`detect_device`, on the same stream: the reference's overlap filter (ref:util/utils.py:241-319,
+        :411-415, :444-451) on the device -> per-icon state, OCR label masks / removed flags and the batch's crop list, plus
+        the async D2H of the flags into this io slot's pinned mirrors.  ``ocr_elems[i]`` = host_glue.ocr_elements(...) of
+        screenshot i (the strings stay on the host).  Returns False -- nothing launched -- when a screenshot has more OCR boxes
+        than the kernel takes; the caller then runs the host list logic (host_glue.build_elements) instead."""
+        mo = io["max_ocr"]
+        if any(len(e) > mo for e in ocr_elems):
+            return False
+        hr, hc = io["host_ocr_ratio"], io["host_ocr_count"]
+        for i, e in enumerate(ocr_elems):
+            hc[i] = len(e)
+            if e:
+                hr[i, :len(e)] = torch.tensor([x["bbox"] for x in e], dtype=torch.float32)
+        io["ocr_ratio"].copy_(hr, non_blocking=True)
+        io["ocr_count"].copy_(hc, non_blocking=True)
+        ops.overlap_filter(io["out_box"], io["out_count"], B, max_det, io["img_w"], io["img_h"], io["ocr_ratio"], io["ocr_count"],
+                           mo, float(iou_threshold), io["icon_state"], io["label_mask"], io["ocr_removed"], io["icon_ratio"],
+                           io["crop_box"], io["crop_img"], io["crop_counts"], io["arrive"])
+        for h_, d_ in (("host_state", "icon_state"), ("host_mask", "label_mask"), ("host_removed", "ocr_removed"),
+                       ("host_ratio", "icon_ratio"), ("host_crop_counts", "crop_counts")):
+            io[h_].copy_(io[d_], non_blocking=True)
+        return True
+
+    @staticmethod
+    def elements_from_io(io, i, n_det, ocr_elem):
+        """Screenshot i of a filtered batch (after the D2H above has completed) -> the reference's sorted element list."""
+        from . import host_glue
+        return host_glue.elements_from_flags(io["host_ratio"][i, :n_det].tolist(), io["host_state"][i, :n_det].tolist(),
+                                             (io["host_mask"][i, :n_det].numpy().view("uint32")), ocr_elem,
+                                             io["host_removed"][i, :len(ocr_elem)].tolist())
 
     @staticmethod
     def check_capacity(cand_count_host: torch.Tensor, cap: int) -> None:

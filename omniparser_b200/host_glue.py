@@ -173,6 +173,48 @@ def build_elements(xyxy_ratio: List[List[float]], ocr_ratio: Optional[List[List[
     return elems, starting_idx
 
 
+# ------------------------------------------------------------------------------------------ device overlap filter, host half
+# b2p_overlap_filter (csrc/overlap_filter.cu) evaluates the geometry of remove_overlap_new on the GPU and returns flags; the
+# strings live here.  ocr_elements() is what the reference builds at ref:util/utils.py:444; elements_from_flags() turns the
+# flags back into the reference's sorted element list (:446-451) with the same list semantics as the loops above.
+OCR_DEVICE_CAP = 256   # OCR boxes per screenshot the device filter takes (b2p_overlap_filter max_ocr); more -> host path
+
+
+def ocr_elements(ocr_ratio: Optional[List[List[float]]], ocr_text: Sequence[str], w: int, h: int) -> List[dict]:
+    return [{"type": "text", "bbox": box, "interactivity": False, "content": txt, "source": "box_ocr_content_ocr"}
+            for box, txt in zip(ocr_ratio or [], ocr_text) if int_box_area(box, w, h) > 0]
+
+
+def elements_from_flags(icon_ratio: Sequence[Sequence[float]], state: Sequence[int], label_mask, ocr_elem: List[dict],
+                        ocr_removed: Sequence[int]) -> List[dict]:
+    """icon_ratio [n][4] (fp32 values), state [n] (0 dropped / 1 needs a caption / 2 labelled by OCR), label_mask [n][words]
+    (bit k: OCR element k labels the icon), ocr_removed [m]  ->  filtered_boxes_elem, "content is None" last (stable)."""
+    m = len(ocr_elem)
+    kept_ocr: List[dict] = list(ocr_elem)
+    if m and any(ocr_removed[k] for k in range(m)):
+        # list.remove() drops the FIRST equal element (ref:util/utils.py:296); equal OCR dicts are handled like the loops do
+        pending = [ocr_elem[k] for k in range(m) if ocr_removed[k]]
+        out = []
+        for e in kept_ocr:
+            hit = next((j for j, p_ in enumerate(pending) if p_ == e), None) if pending else None
+            if hit is not None:
+                pending.pop(hit)
+                continue
+            out.append(e)
+        kept_ocr = out
+    labelled, plain = [], []
+    for i, st in enumerate(state):
+        if st == 2:
+            words = label_mask[i]
+            labels = "".join(ocr_elem[k]["content"] + " " for k in range(m) if (int(words[k >> 5]) >> (k & 31)) & 1)
+            labelled.append({"type": "icon", "bbox": [float(v) for v in icon_ratio[i]], "interactivity": True, "content": labels,
+                             "source": "box_yolo_content_ocr"})
+        elif st == 1:
+            plain.append({"type": "icon", "bbox": [float(v) for v in icon_ratio[i]], "interactivity": True, "content": None,
+                          "source": "box_yolo_content_yolo"})
+    return kept_ocr + labelled + plain
+
+
 def fill_captions(elems: List[dict], captions: List[str]) -> None:
     """ref:util/utils.py:467-469: captions are consumed in order by the content-None elements."""
     it = iter(captions)

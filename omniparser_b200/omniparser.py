@@ -23,12 +23,10 @@ from .utils import get_caption_model_processor, get_som_labeled_img, get_yolo_mo
 
 
 def _reference_check_ocr_box():
-    try:
-        from util.utils import check_ocr_box   # the reference's own OCR pre-step, unchanged
-        return check_ocr_box
-    except Exception as exc:   # noqa: BLE001
-        raise RuntimeError("OCR pre-step unavailable: install the reference's util.utils (easyocr/paddleocr) or pass "
-                           "config['ocr_fn']") from exc
+    """The OCR pre-step (ref:util/utils.py:514-549): :func:`omniparser_b200.ocr.check_ocr_box`, the reference's function
+    with lazily bound engines (it raises a clear error if neither EasyOCR nor an injected reader is available)."""
+    from .ocr import check_ocr_box
+    return check_ocr_box
 
 
 class Omniparser(object):

@@ -219,6 +219,13 @@ def im2col_u8(img, B, H, W, k, s, p, Kpad, lut, out, split=False):
     _lib.check(_lib.lib().b2p_im2col_u8(_p(img), B, H, W, k, s, p, Kpad, _p(lut), _p(out), int(split), _stream()))
 
 
+def overlap_filter(box_px, count, B, max_det, img_w, img_h, ocr_ratio, ocr_count, max_ocr, iou_thr, icon_state, label_mask,
+                   ocr_removed, icon_ratio, crop_box, crop_img, crop_counts, arrive):
+    _lib.check(_lib.lib().b2p_overlap_filter(_p(box_px), _p(count), B, max_det, _p(img_w), _p(img_h), _p(ocr_ratio), _p(ocr_count),
+                                             max_ocr, float(iou_thr), _p(icon_state), _p(label_mask), _p(ocr_removed),
+                                             _p(icon_ratio), _p(crop_box), _p(crop_img), _p(crop_counts), _p(arrive), _stream()))
+
+
 def crop_resize(imgs, img_hw, img_off, boxes, box_img, n_box, out_hw, out, status):
     _lib.check(_lib.lib().b2p_crop_resize(_p(imgs), _p(img_hw), _p(img_off), _p(boxes), _p(box_img), n_box, out_hw,
                                           _p(out), _p(status), _stream()))

@@ -72,6 +72,12 @@ class ParseTimings(dict):
     pass
 
 
+# B2P_HOST_GLUE=1: run the reference's list logic (overlap filter, ref:util/utils.py:241-319) on the host (host_glue.py) instead
+# of the device kernel b2p_overlap_filter -- identical results (tests/test_pipeline_gpu.py), kept for A/B timing and as the path
+# for screenshots with more OCR boxes than the kernel takes
+_HOST_GLUE = bool(os.environ.get("B2P_HOST_GLUE"))
+
+
 def _check_crop_status(status: torch.Tensor) -> None:
     """b2p_crop_resize flags crops whose truncated box is empty.  The reference silently skips such a crop
     (ref:util/utils.py:104-105) and then mis-assigns every later caption; int_box_area > 0 (:444-445) makes it impossible
@@ -102,28 +108,37 @@ def parse_screenshots(images: Sequence[np.ndarray], model: B200YOLOv9Detector, c
             for i, im in enumerate(images):
                 io_["host"][i].copy_(torch.from_numpy(np.ascontiguousarray(im)))
             io_["src"].copy_(io_["host"], non_blocking=True)
+        whwh = torch.Tensor([W, H, W, H])
+        ocr_elems = [host_glue.ocr_elements((torch.tensor(ob) / whwh).tolist() if ob else None, tx, W, H) for tx, ob in ocr]   # :437-444
+        on_device = False
         if _det_override is None:
             model.detect_device(io_, B, H, W, BOX_TRESHOLD, 0.1, 300)
-            counts = io_["out_count"].cpu().tolist()                   # D2H #1 (sync)
-            boxes = io_["out_box"].cpu()
+            on_device = not _HOST_GLUE and model.filter_device(io_, B, H, W, ocr_elems, iou_threshold, 300)
+            counts = io_["out_count"].cpu().tolist()                   # D2H #1 (sync; the filter's flags ride along)
+            boxes = None if on_device else io_["out_box"].cpu()
             model.check_capacity(io_["cand_count"].cpu(), io_["cap"])
         else:   # tests: inject detector output (e.g. the golden boxes) to pin the stages after it exactly
             counts = [len(b) for b in _det_override]
             boxes = [torch.as_tensor(b, dtype=torch.float32).reshape(-1, 4) for b in _det_override]
         t1 = time.perf_counter()
-        whwh = torch.Tensor([W, H, W, H])
         all_elems, crop_boxes, crop_img = [], [], []
-        for i in range(B):
-            xyxy = (boxes[i][:counts[i]] / whwh).tolist()              # ref:util/utils.py:432
-            texts, obox = ocr[i]
-            oratio = (torch.tensor(obox) / whwh).tolist() if obox else None   # :437-442
-            elems, start = host_glue.build_elements(xyxy, oratio, texts, W, H, iou_threshold)
-            all_elems.append(elems)
-            for e in elems:
-                if e["content"] is None:
-                    crop_boxes.append(e["bbox"])
-                    crop_img.append(i)
-        n = len(crop_boxes)
+        if on_device:
+            # overlap filter ran on the GPU (b2p_overlap_filter): element lists from its flags, crop list already on the device
+            for i in range(B):
+                all_elems.append(model.elements_from_io(io_, i, counts[i], ocr_elems[i]))
+            n = int(io_["host_crop_counts"][B])
+        else:
+            for i in range(B):
+                xyxy = (boxes[i][:counts[i]] / whwh).tolist()              # ref:util/utils.py:432
+                texts, obox = ocr[i]
+                oratio = (torch.tensor(obox) / whwh).tolist() if obox else None   # :437-442
+                elems, start = host_glue.build_elements(xyxy, oratio, texts, W, H, iou_threshold)
+                all_elems.append(elems)
+                for e in elems:
+                    if e["content"] is None:
+                        crop_boxes.append(e["bbox"])
+                        crop_img.append(i)
+            n = len(crop_boxes)
         t2 = time.perf_counter()
         ids = None
         if n:
@@ -134,8 +149,11 @@ def parse_screenshots(images: Sequence[np.ndarray], model: B200YOLOv9Detector, c
                 crops_dst = plan.crops
             else:
                 crops_dst = torch.empty((n, 64, 64, 3), dtype=torch.uint8, device=dev)
-            d_boxes = torch.tensor(crop_boxes, dtype=torch.float32).to(dev, non_blocking=True)
-            d_bimg = torch.tensor(crop_img, dtype=torch.int32).to(dev, non_blocking=True)
+            if on_device:
+                d_boxes, d_bimg = io_["crop_box"], io_["crop_img"]
+            else:
+                d_boxes = torch.tensor(crop_boxes, dtype=torch.float32).to(dev, non_blocking=True)
+                d_bimg = torch.tensor(crop_img, dtype=torch.int32).to(dev, non_blocking=True)
             key = ("crop_meta", B, H, W)
             meta = model._io.get(key)
             if meta is None:
@@ -210,7 +228,7 @@ class PipelinedParser:
         self.group = max(1, int(caption_group))
 
     @torch.inference_mode()
-    def _submit(self, slot: int, images, resident_src=None):
+    def _submit(self, slot: int, images, resident_src=None, ocr=None):
         torch.cuda.set_device(self.model.device)   # runs on the worker thread: device and inference mode are thread-local
         B = len(images)
         H, W = images[0].shape[:2]
@@ -228,12 +246,19 @@ class PipelinedParser:
                     io_["host"][i].copy_(torch.from_numpy(np.ascontiguousarray(im)))
                 io_["src"].copy_(io_["host"], non_blocking=True)
             m.detect_device(io_, B, H, W, self.conf, 0.1, 300)
+            ocr_elems, on_device = None, False
+            if ocr is not None and not _HOST_GLUE:
+                # overlap filter on the device, right behind NMS on the detector's stream (no host round trip in between)
+                whwh = torch.Tensor([W, H, W, H])
+                ocr_elems = [host_glue.ocr_elements((torch.tensor(ob) / whwh).tolist() if ob else None, tx, W, H) for tx, ob in ocr]
+                on_device = m.filter_device(io_, B, H, W, ocr_elems, self.iou_thr, 300)
             io_["host_count"].copy_(io_["out_count"], non_blocking=True)
-            io_["host_box"].copy_(io_["out_box"], non_blocking=True)
+            if not on_device:
+                io_["host_box"].copy_(io_["out_box"], non_blocking=True)
             io_["host_cand"].copy_(io_["cand_count"], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.s_det)
-        return dict(io=io_, ev=ev, B=B, H=H, W=W)
+        return dict(io=io_, ev=ev, B=B, H=H, W=W, ocr_elems=ocr_elems, on_device=on_device)
 
     def _glue(self, h, ocr):
         """Stage 2 (caller's thread): wait for the detector's boxes, run the reference's host list logic."""
@@ -242,27 +267,34 @@ class PipelinedParser:
         h["ev"].synchronize()
         t1 = time.perf_counter()
         counts = io_["host_count"].tolist()
-        boxes = io_["host_box"]
         self.model.check_capacity(io_["host_cand"], io_["cap"])
-        whwh = torch.Tensor([W, H, W, H])
         all_elems, crop_boxes, crop_img = [], [], []
-        for i in range(B):
-            xyxy = (boxes[i][:counts[i]] / whwh).tolist()
-            texts, obox = ocr[i]
-            oratio = (torch.tensor(obox) / whwh).tolist() if obox else None
-            elems, _ = host_glue.build_elements(xyxy, oratio, texts, W, H, self.iou_thr)
-            all_elems.append(elems)
-            for e in elems:
-                if e["content"] is None:
-                    crop_boxes.append(e["bbox"])
-                    crop_img.append(i)
+        if h.get("on_device"):
+            # the device filter's flags arrived with the counts: element lists are built later, on the caption thread (they are
+            # only needed for the result); the crop list stays on the device
+            n_crops = int(io_["host_crop_counts"][B])
+            all_elems = None
+        else:
+            boxes = io_["host_box"]
+            whwh = torch.Tensor([W, H, W, H])
+            for i in range(B):
+                xyxy = (boxes[i][:counts[i]] / whwh).tolist()
+                texts, obox = ocr[i]
+                oratio = (torch.tensor(obox) / whwh).tolist() if obox else None
+                elems, _ = host_glue.build_elements(xyxy, oratio, texts, W, H, self.iou_thr)
+                all_elems.append(elems)
+                for e in elems:
+                    if e["content"] is None:
+                        crop_boxes.append(e["bbox"])
+                        crop_img.append(i)
+            n_crops = len(crop_boxes)
         t2 = time.perf_counter()
         tm = self.timings
         tm["detect_wait_s"] += t1 - t0; tm["glue_s"] += t2 - t1
-        tm["n_boxes"] += sum(counts); tm["n_crops"] += len(crop_boxes); tm["batches"] += 1
+        tm["n_boxes"] += sum(counts); tm["n_crops"] += n_crops; tm["batches"] += 1
         lane = (self._job // self.group) % self.lanes   # the batches of one caption group share a lane
         self._job += 1
-        return dict(h=h, all_elems=all_elems, crop_boxes=crop_boxes, crop_img=crop_img, lane=lane)
+        return dict(h=h, all_elems=all_elems, crop_boxes=crop_boxes, crop_img=crop_img, lane=lane, n_crops=n_crops, counts=counts)
 
     @torch.inference_mode()
     def _caption(self, g):
@@ -272,7 +304,7 @@ class PipelinedParser:
         h, all_elems, crop_boxes, crop_img = g["h"], g["all_elems"], g["crop_boxes"], g["crop_img"]
         io_, B, H, W = h["io"], h["B"], h["H"], h["W"]
         model, cap_model, processor = self.model, self.cmp["model"], self.cmp["processor"]
-        n = len(crop_boxes)
+        n = g["n_crops"]
         t2 = time.perf_counter()
         ids = None
         if n:
@@ -280,8 +312,11 @@ class PipelinedParser:
             lane = g.get("lane", 0)
             with torch.cuda.stream(self.s_caps[lane]):
                 plan = cap_model.plan_for(n, self.T, self.prompt, instance=lane)
-                d_boxes = torch.tensor(crop_boxes, dtype=torch.float32).to(dev, non_blocking=True)
-                d_bimg = torch.tensor(crop_img, dtype=torch.int32).to(dev, non_blocking=True)
+                if h.get("on_device"):
+                    d_boxes, d_bimg = io_["crop_box"], io_["crop_img"]
+                else:
+                    d_boxes = torch.tensor(crop_boxes, dtype=torch.float32).to(dev, non_blocking=True)
+                    d_bimg = torch.tensor(crop_img, dtype=torch.int32).to(dev, non_blocking=True)
                 key = ("crop_meta", B, H, W, lane)
                 meta = model._io.get(key)
                 if meta is None:
@@ -290,8 +325,13 @@ class PipelinedParser:
                     model._io[key] = meta
                 status = torch.zeros((n,), dtype=torch.int32, device=dev)
                 ops.crop_resize(io_["src"], meta["hw"], meta["off"], d_boxes, d_bimg, n, 64, plan.crops, status)
-                ids = cap_model.generate_from_device_crops(plan, n).cpu()
+                ids = cap_model.generate_from_device_crops(plan, n)
+                if all_elems is None:   # device overlap filter: element lists from its flags, while the GPU captions
+                    all_elems = [model.elements_from_io(io_, i, g["counts"][i], h["ocr_elems"][i]) for i in range(B)]
+                ids = ids.cpu()
                 _check_crop_status(status)
+        if all_elems is None:
+            all_elems = [model.elements_from_io(io_, i, g["counts"][i], h["ocr_elems"][i]) for i in range(B)]
         t3 = time.perf_counter()
         texts_all = [t.strip() for t in processor.batch_decode(ids, skip_special_tokens=True)] if ids is not None else []
         out, k = [], 0
@@ -311,8 +351,12 @@ class PipelinedParser:
         torch.cuda.set_device(self.model.device)
         model, cap_model, processor = self.model, self.cmp["model"], self.cmp["processor"]
         lane = gs[0]["lane"]
-        counts = [len(g["crop_boxes"]) for g in gs]
+        counts = [g["n_crops"] for g in gs]
         n = sum(counts)
+        for g in gs:
+            if g["all_elems"] is None:
+                hh = g["h"]
+                g["all_elems"] = [model.elements_from_io(hh["io"], i, g["counts"][i], hh["ocr_elems"][i]) for i in range(hh["B"])]
         t2 = time.perf_counter()
         ids = None
         if n:
@@ -324,8 +368,11 @@ class PipelinedParser:
                     if not ng:
                         continue
                     io_, B, H, W = g["h"]["io"], g["h"]["B"], g["h"]["H"], g["h"]["W"]
-                    d_boxes = torch.tensor(g["crop_boxes"], dtype=torch.float32).to(dev, non_blocking=True)
-                    d_bimg = torch.tensor(g["crop_img"], dtype=torch.int32).to(dev, non_blocking=True)
+                    if g["h"].get("on_device"):
+                        d_boxes, d_bimg = io_["crop_box"], io_["crop_img"]
+                    else:
+                        d_boxes = torch.tensor(g["crop_boxes"], dtype=torch.float32).to(dev, non_blocking=True)
+                        d_bimg = torch.tensor(g["crop_img"], dtype=torch.int32).to(dev, non_blocking=True)
                     key = ("crop_meta", B, H, W, lane)
                     meta = model._io.get(key)
                     if meta is None:
@@ -379,7 +426,7 @@ class PipelinedParser:
             if cur is None:
                 return
             slot = 0
-            h = self._submit(slot, cur[0], next(rit) if rit is not None else None)
+            h = self._submit(slot, cur[0], next(rit) if rit is not None else None, cur[1])
             pending = deque()
             grp = []
             while cur is not None:
@@ -389,7 +436,7 @@ class PipelinedParser:
                     # slots alive at once: lanes*group in caption + up to group-1 glued batches waiting for their group
                     # + the batch in the host list logic + the batch in detection  (= lanes + 2 when group == 1)
                     slot = (slot + 1) % (self.lanes * self.group + self.group + 1)
-                    fut = self._pool.submit(self._submit, slot, nxt[0], next(rit) if rit is not None else None)
+                    fut = self._pool.submit(self._submit, slot, nxt[0], next(rit) if rit is not None else None, nxt[1])
                 g = self._glue(h, cur[1])
                 if self.group == 1:
                     self._ensure_plan(g, pending, fut)
@@ -397,7 +444,7 @@ class PipelinedParser:
                 else:
                     grp.append(g)
                     if len(grp) == self.group or nxt is None:
-                        self._ensure_plan(dict(crop_boxes=[b for x in grp for b in x["crop_boxes"]], lane=grp[0]["lane"]), pending, fut)
+                        self._ensure_plan(dict(n_crops=sum(x["n_crops"] for x in grp), lane=grp[0]["lane"]), pending, fut)
                         fc = self._cap_pools[grp[0]["lane"]].submit(self._caption_group, grp)
                         pending.extend(_Member(fc, j) for j in range(len(grp)))
                         grp = []
@@ -433,7 +480,7 @@ class PipelinedParser:
     def _ensure_plan(self, g, pending, fut):
         """First batch of a crop-count bucket on a lane: drain the pipeline and build + capture the caption plan with
         the GPU idle (buffers and graphs are created once; steady state never comes here)."""
-        n = len(g["crop_boxes"])
+        n = g["n_crops"]
         cap_model = self.cmp["model"]
         if not n or cap_model.plan_ready(n, self.T, self.prompt, instance=g["lane"]):
             return

@@ -227,3 +227,46 @@ def resize_bilinear_cv2_numpy(crop: np.ndarray, out: int = 64) -> np.ndarray:
     y1 = np.clip(sy + 1, 0, sh - 1)
     v = (((b0[:, None, None] * (rows[y0] >> 4)) >> 16) + ((b1[:, None, None] * (rows[y1] >> 4)) >> 16) + 2) >> 2
     return np.clip(v, 0, 255).astype(np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------- overlap filter flags
+def overlap_flags_loops(icon_ratio, ocr_boxes, w, h, iou_threshold):
+    """The reference loops of ``remove_overlap_new`` (ref:util/utils.py:241-319) + the ``int_box_area`` filter (:411-415,
+    :445), emitting FLAGS instead of element lists -- the contract of the device kernel ``b2p_overlap_filter``
+    (omniparser_b200/csrc/overlap_filter.cu): state per icon (0 dropped / 1 needs a caption / 2 labelled by OCR text),
+    label bit masks, removed flags of the OCR boxes.  icon_ratio / ocr_boxes: lists of Python-float xyxy ratio boxes
+    (OCR boxes already int_box_area-filtered)."""
+    def area(b):
+        return (b[2] - b[0]) * (b[3] - b[1])
+
+    def inter(b1, b2):
+        return max(0, min(b1[2], b2[2]) - max(b1[0], b2[0])) * max(0, min(b1[3], b2[3]) - max(b1[1], b2[1]))
+
+    def iou(b1, b2):
+        it = inter(b1, b2)
+        union = area(b1) + area(b2) - it + 1e-6
+        r1, r2 = (it / area(b1), it / area(b2)) if area(b1) > 0 and area(b2) > 0 else (0, 0)
+        return max(it / union, r1, r2)
+
+    n, m = len(icon_ratio), len(ocr_boxes)
+    words = max(1, (m + 31) // 32)
+    state = [0] * n
+    mask = [[0] * words for _ in range(n)]
+    removed = [0] * m
+    live = [i for i, b in enumerate(icon_ratio)
+            if (int(b[2] * w) - int(b[0] * w)) * (int(b[3] * h) - int(b[1] * h)) > 0]
+    for i in live:
+        b1 = icon_ratio[i]
+        if any(j != i and iou(b1, icon_ratio[j]) > iou_threshold and area(b1) > area(icon_ratio[j]) for j in live):
+            continue
+        dropped, labelled = False, False
+        for k, b3 in enumerate(ocr_boxes):
+            if inter(b3, b1) / area(b3) > 0.80:
+                mask[i][k >> 5] |= 1 << (k & 31)
+                removed[k] = 1
+                labelled = True
+            elif inter(b1, b3) / area(b1) > 0.80:
+                dropped = True
+                break
+        state[i] = 0 if dropped else (2 if labelled else 1)
+    return state, mask, removed

@@ -114,3 +114,25 @@ def test_dense_overlaps_fast_equals_loops_and_reference(seed):
                          if ru.int_box_area(box, W, H) > 0]
             ref = ru.remove_overlap_new(boxes=xyxy_elem, iou_threshold=thr, ocr_bbox=copy.deepcopy(ocr_elem))
             assert fast == sorted(ref, key=lambda x: x['content'] is None)
+
+
+# ---------------------------------------------------------------------------------------------- device-filter contract
+@pytest.mark.parametrize("seed", range(8))
+def test_elements_from_flags_equals_build_elements(seed):
+    """Host half of the device overlap filter: the flag contract of b2p_overlap_filter (restated as loops in
+    oracle/ref_restate.py::overlap_flags_loops) + host_glue.elements_from_flags rebuild exactly the element list of the
+    reference-pinned build_elements, including duplicated OCR elements (list.remove drops the first equal one)."""
+    from oracle.ref_restate import overlap_flags_loops
+    icons, ob, texts = _dense_case(seed) if seed % 2 else _case(seed)
+    if seed == 3:
+        ob = ob + [ob[0], ob[0]]                       # equal OCR dicts
+        texts = texts + [texts[0], texts[0]]
+    whwh = torch.Tensor([W, H, W, H])
+    oratio = (torch.tensor(ob) / whwh).tolist()
+    ratio = icons.tolist()
+    for thr in (0.7, 0.9):
+        ref, _ = host_glue.build_elements(ratio, oratio, texts, W, H, thr)
+        ocr_elem = host_glue.ocr_elements(oratio, texts, W, H)
+        state, mask, removed = overlap_flags_loops(ratio, [e["bbox"] for e in ocr_elem], W, H, thr)
+        got = host_glue.elements_from_flags(ratio, state, mask, ocr_elem, removed)
+        assert got == ref

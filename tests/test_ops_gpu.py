@@ -363,3 +363,79 @@ def test_channel_attn_small_variant_bit_identical(B, N, C, split):
         torch.cuda.synchronize()
         outs.append(o.cpu())
     assert torch.equal(outs[0], outs[1])
+
+
+# ---------------------------------------------------------------------------------------------- overlap filter (8f-2)
+def _overlap_device(px_list, ocr_px_list, W, H, thr, max_det=300, max_ocr=256):
+    """b2p_overlap_filter on a batch: px_list[b] fp32 [n_b,4] pixel boxes (NMS output format), ocr_px_list[b] (texts, int boxes)
+    -> per screenshot (elements via host_glue.elements_from_flags, crop boxes, crop image ids)."""
+    from omniparser_b200 import host_glue
+    B = len(px_list)
+    f32, i32 = dict(dtype=torch.float32, device=DEV), dict(dtype=torch.int32, device=DEV)
+    box = torch.zeros((B, max_det, 4), **f32)
+    cnt = torch.zeros((B,), **i32)
+    whwh = torch.Tensor([W, H, W, H])
+    ocr_elems = []
+    oc = torch.zeros((B, max_ocr, 4), **f32)
+    ocnt = torch.zeros((B,), **i32)
+    for b, (px, (texts, ob)) in enumerate(zip(px_list, ocr_px_list)):
+        box[b, :len(px)] = px.to(DEV)
+        cnt[b] = len(px)
+        el = host_glue.ocr_elements((torch.tensor(ob) / whwh).tolist() if ob else None, texts, W, H)
+        ocr_elems.append(el)
+        if el:
+            oc[b, :len(el)] = torch.tensor([e["bbox"] for e in el], dtype=torch.float32).to(DEV)
+        ocnt[b] = len(el)
+    state = torch.full((B, max_det), -7, **i32); mask = torch.full((B, max_det, max_ocr // 32), -1, **i32)
+    removed = torch.full((B, max_ocr), -7, **i32); ratio = torch.zeros((B, max_det, 4), **f32)
+    cbox = torch.zeros((B * max_det, 4), **f32); cimg = torch.zeros((B * max_det,), **i32)
+    ccnt = torch.zeros((B + 1,), **i32); arrive = torch.zeros((1,), **i32)
+    iw = torch.full((B,), float(W), **f32); ih = torch.full((B,), float(H), **f32)
+    for _ in range(2):   # twice: the arrival counter must reset itself
+        ops.overlap_filter(box, cnt, B, max_det, iw, ih, oc, ocnt, max_ocr, thr, state, mask, removed, ratio, cbox, cimg, ccnt, arrive)
+    torch.cuda.synchronize()
+    assert int(arrive.item()) == 0
+    out = []
+    ccnt = ccnt.cpu().tolist()
+    for b in range(B):
+        n = len(px_list[b])
+        el = host_glue.elements_from_flags(ratio[b, :n].cpu().tolist(), state[b, :n].cpu().tolist(),
+                                           mask[b, :n].cpu().numpy().view("uint32"), ocr_elems[b], removed[b, :len(ocr_elems[b])].cpu().tolist())
+        out.append(el)
+    tot = ccnt[B]
+    assert tot == sum(ccnt[:B])
+    return out, cbox[:tot].cpu().tolist(), cimg[:tot].cpu().tolist(), ccnt
+
+
+@pytest.mark.parametrize("thr", [0.7, 0.9, 0.1])
+def test_overlap_filter_equals_reference_list_logic(thr):
+    """Device overlap filter == the reference-pinned host list logic (host_glue.build_elements, itself equal to the unmodified
+    ref:util/utils.py remove_overlap_new in tests/test_host_glue_cpu.py): identical element lists (order, sources, float box
+    values, OCR label strings) and identical crop lists, on the adversarial cases of the CPU tests + empty / no-OCR screenshots."""
+    from omniparser_b200 import host_glue
+    from test_host_glue_cpu import _case, _dense_case, W, H
+    whwh = torch.Tensor([W, H, W, H])
+    px_list, ocr_list = [], []
+    for seed in range(10):
+        icons, ob, texts = _dense_case(seed) if seed % 2 else _case(seed)
+        px_list.append((icons * whwh).to(torch.float32))
+        ocr_list.append((texts, ob))
+    px_list.append(torch.zeros((0, 4)));            ocr_list.append((["a"], [[10, 10, 60, 30]]))     # no detections
+    px_list.append(px_list[0].clone());             ocr_list.append(([], []))                          # no OCR
+    px_list.append(px_list[1][:1].clone());         ocr_list.append(ocr_list[1])
+    dup_t, dup_b = ocr_list[3]
+    px_list.append(px_list[3].clone());             ocr_list.append((dup_t + [dup_t[0]] * 2, dup_b + [dup_b[0]] * 2))   # equal OCR dicts
+    got, cbox, cimg, ccnt = _overlap_device(px_list, ocr_list, W, H, thr)
+    exp_box, exp_img = [], []
+    labelled = 0
+    for b, (px, (texts, ob)) in enumerate(zip(px_list, ocr_list)):
+        xyxy = (px / whwh).tolist()
+        oratio = (torch.tensor(ob) / whwh).tolist() if ob else None
+        ref, _ = host_glue.build_elements(xyxy, oratio, texts, W, H, thr)
+        assert got[b] == ref, f"screenshot {b}: element lists differ"
+        labelled += sum(e["source"] == "box_yolo_content_ocr" for e in ref)
+        for e in ref:
+            if e["content"] is None:
+                exp_box.append([float(np.float32(v)) for v in e["bbox"]]); exp_img.append(b)
+    assert labelled > 0
+    assert cbox == exp_box and cimg == exp_img

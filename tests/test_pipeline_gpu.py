@@ -162,3 +162,37 @@ def test_edge_cases_no_boxes_and_no_ocr():
     out = parse_screenshots([img, np.full_like(img, 200)], det, cmp_, [([], None), ([], None)], BOX_TRESHOLD=0.3, iou_threshold=0.7,
                             max_new_tokens=8)
     assert len(out) == 2 and out[0][1].shape[0] == len(out[0][0]) and out[1][1].shape[0] == len(out[1][0])
+
+
+def test_device_overlap_filter_path_equals_host_list_logic(monkeypatch):
+    """parse_screenshots / PipelinedParser with the overlap filter on the device (default) return exactly what
+    they return with the reference's list logic on the host (B2P_HOST_GLUE), on screenshots whose OCR boxes sit inside icons,
+    contain icons, and are plain clutter."""
+    from omniparser_b200 import utils as U
+    det, cmp_ = ge.standin_models(DEV)
+    seeds = [60, 61, 62, 63]
+    imgs = [synth.screenshot(s) for s in seeds]
+    ocr = []
+    probe = det.predict_batch(imgs, conf=0.05, iou=0.1)
+    for s, r in zip(seeds, probe):
+        texts, boxes = synth.ocr_boxes(s)
+        for j, b in enumerate(r.boxes.xyxy.cpu().tolist()[:12]):
+            x1, y1, x2, y2 = b
+            if j % 3 == 0 and x2 - x1 > 12 and y2 - y1 > 12:      # OCR box inside an icon -> label
+                boxes.append([int(x1) + 3, int(y1) + 3, int(x2) - 3, int(y2) - 3]); texts.append(f"in{j}")
+            elif j % 3 == 1:                                       # OCR box containing an icon -> icon dropped
+                boxes.append([max(0, int(x1) - 20), max(0, int(y1) - 20), int(x2) + 20, int(y2) + 20]); texts.append(f"around{j}")
+        ocr.append((texts, boxes))
+    monkeypatch.setattr(U, "_HOST_GLUE", True)
+    ref = U.parse_screenshots(imgs, det, cmp_, ocr, BOX_TRESHOLD=0.05, iou_threshold=0.7, max_new_tokens=8)
+    monkeypatch.setattr(U, "_HOST_GLUE", False)
+    got = U.parse_screenshots(imgs, det, cmp_, ocr, BOX_TRESHOLD=0.05, iou_threshold=0.7, max_new_tokens=8)
+    assert any(e["source"] == "box_yolo_content_ocr" for el, _ in ref for e in el)
+    for (ge_, gi), (re_, ri) in zip(got, ref):
+        assert ge_ == re_ and torch.equal(gi, ri)
+    pp = U.PipelinedParser(det, cmp_, BOX_TRESHOLD=0.05, iou_threshold=0.7, max_new_tokens=8, caption_lanes=2)
+    batches = [(imgs[:2], ocr[:2]), (imgs[2:], ocr[2:]), (imgs[:2], ocr[:2])]
+    out = list(pp.run(iter(batches)))
+    flat = [x for b in out for x in b]
+    for (ge_, gi), (re_, ri) in zip(flat, ref + ref[:2]):
+        assert ge_ == re_ and torch.equal(gi, ri)

@@ -34,7 +34,7 @@ class _Sched(PipelinedParser):
     def _ensure_plan(self, g, pending, fut):
         pass
 
-    def _submit(self, slot, images, resident_src=None):
+    def _submit(self, slot, images, resident_src=None, ocr=None):
         with self.lock:
             if slot in self.busy_slots:
                 self.errors.append(f"slot {slot} reused while batch {self.busy_slots[slot]} still owns it")
@@ -46,7 +46,7 @@ class _Sched(PipelinedParser):
         time.sleep(self.rng.uniform(0.0, 0.003))
         lane = (self._job // self.group) % self.lanes
         self._job += 1
-        return dict(h=h, lane=lane, crop_boxes=[0])
+        return dict(h=h, lane=lane, crop_boxes=[0], n_crops=1)
 
     def _caption_group(self, gs):
         lane, batches = gs[0]["lane"], [g["h"]["batch"] for g in gs]
