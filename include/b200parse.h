@@ -37,7 +37,7 @@ int b2p_trace_read(unsigned long long* stamps, int* meta, int max_launches);
  * flags: bit0 operands bf16 (else fp16) | bit1 output fp32 (else fp16) | bit2 fp16 output in the "fp16x3" operand
  * layout [hi(N) | lo(N)] (ldc >= 2N) | bit3 fp16x3 OPERANDS: A rows [hi(K) | lo(K)] (lda >= 2K; conv: pixels
  * [hi(Cin) | lo(Cin)]), weight rows [hi | lo] likewise (conv: per tap), K / Cin the logical sizes; the kernel loads each
- * half once per k-block and accumulates hi*hi + hi*lo + lo*hi in fp32 | bits 8.. maximum N tile (0 = auto).
+ * half once per k-block and accumulates hi*hi + hi*lo + lo*hi in fp32 | bit4 never split K (tuning) | bits 8.. maximum N tile (0 = auto).
  * act: 0 none, 1 SiLU, 2 exact GELU.
  * out = act(A[M,K] * B[N,K]^T + bias[N]) + residual (residual has the dtype of out). */
 int b2p_gemm(const void* A, long long lda, const void* B, int M, int N, int K, void* out, long long ldc,

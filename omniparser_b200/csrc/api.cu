@@ -66,7 +66,7 @@ int b2p_gemm_planes(const void* A, long long lda, const void* B, int M, int N, i
   ConvGemm d{};
   d.mode = 0; d.bf16 = flags & 1; d.A = A; d.lda = lda; d.B = B; d.M = M; d.N = N; d.K = K;
   d.out = out; d.ldc = ldc; d.out_f32 = (flags >> 1) & 1; d.bias = bias; d.res = residual; d.ldr = ldr; d.act = act;
-  d.bn_max = (flags >> 8) & 0x1ff; d.split_out = (flags >> 2) & 1; d.x3 = (flags >> 3) & 1;
+  d.bn_max = (flags >> 8) & 0x1ff; d.no_split = (flags >> 4) & 1; d.split_out = (flags >> 2) & 1; d.x3 = (flags >> 3) & 1;
   d.lo_a = lo_a; d.lo_out = lo_out; d.lo_res = lo_res;
   return gemm_launch(d, st);
 }
@@ -85,7 +85,7 @@ int b2p_conv3x3_planes(const void* in, long long ld_in, int batch, int H, int W,
   d.mode = stride; d.bf16 = flags & 1; d.A = in; d.lda = ld_in; d.B = weight; d.N = Cout;
   d.batch = batch; d.H = H; d.W = W; d.Cin = Cin;
   d.out = out; d.ldc = ldc; d.out_f32 = (flags >> 1) & 1; d.bias = bias; d.res = residual; d.ldr = ldr; d.act = act;
-  d.bn_max = (flags >> 8) & 0x1ff; d.split_out = (flags >> 2) & 1; d.x3 = (flags >> 3) & 1;
+  d.bn_max = (flags >> 8) & 0x1ff; d.no_split = (flags >> 4) & 1; d.split_out = (flags >> 2) & 1; d.x3 = (flags >> 3) & 1;
   d.lo_a = lo_a; d.lo_out = lo_out; d.lo_res = lo_res;
   return gemm_launch(d, st);
 }

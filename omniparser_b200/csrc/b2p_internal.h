@@ -35,6 +35,7 @@ struct ConvGemm {
   long long ldr;
   int act;             // 0 none, 1 SiLU, 2 GELU(erf)
   int bn_max;          // 0 = auto
+  int no_split;        // 1 = never split K for this launch (tuning knob, flags bit 4)
   int split_out;       // fp16 output written as [hi(N) | lo(N)] (row stride ldc >= 2N): operand of a fp16x3 GEMM
   int x3;              // fp16x3 operands: A rows [hi(K) | lo(K)] (conv: per pixel [hi(Cin) | lo(Cin)]), B rows likewise;
                        // K / Cin are the LOGICAL sizes.  out = A_hi*B_hi + A_hi*B_lo + A_lo*B_hi, fp32 accumulate

@@ -398,86 +398,92 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ MMA issuer
-      int stage = 0, stageA = 0;
-      uint32_t phase = 0, phaseA = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      const int ksteps = g.bk / 16;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int ks = item % g.ksplit;
-        const int kb0 = ks * g.kb_per, kb1 = min(g.num_kb, kb0 + g.kb_per);
-        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + uint32_t(acc * 256);
-        if (g.sep) {
-          for (int u = kb0; u < kb1; ++u) {
-            mbar_wait(bar_afull + 8 * stageA, phaseA);
-            const uint32_t sa0 = smem_base + stageA * g.a_slot;
-            for (int tap = 0; tap < g.taps; ++tap) {
-              // resident weights: slot (unit, tap) completed its one and only phase (parity 0) on the first item
-              const int slot = g.bres ? (u - kb0) * g.taps + tap : stage;
-              mbar_wait(bar_full + 8 * slot, g.bres ? 0u : phase);
-              tc_fence_after();
-              if constexpr (kTrace) { if (item == blockIdx.x && u == kb0 && tap == 0) trace_stamp<kTrace>(g, kTrFirstFull); }
-              uint32_t sa = sa0;
-              if (g.mode == 3) {
-                const int ky = tap / 3, kx = tap - ky * 3;
-                sa = sa0 + uint32_t(ky * g.tw + kx) * uint32_t(2 * g.bk);   // shifted view of the halo tile
+    // ------------------------------------------------------------ MMA issuer
+    // The whole warp runs this (warp-uniform) loop and waits on the barriers; one elected lane issues the tensor-core
+    // instructions from inside the asm blocks (ptx.cuh umma_*_stage).  Everything the loops need is copied out of the
+    // kernel-parameter struct first: with the volatile asm statements in between, the compiler re-read every g.* field
+    // from the constant bank on every tap otherwise (92 SASS instructions per tap, ~3.6 us per 128-pixel tile of the
+    // 32-channel layers against 0.3 us of tensor work: profiles/r2_notes.md).
+    const int n_stages = g.stages, n_stagesA = g.stagesA, ksplit = g.ksplit, kb_per = g.kb_per, num_kb = g.num_kb;
+    const bool sep = g.sep != 0, bres = g.bres != 0, halo = (g.mode == 3), x3 = g.x3 != 0, k64 = (g.bk == 64);
+    const uint32_t idesc = g.idesc, a_slot = g.a_slot, b_slot = g.b_slot;
+    const uint32_t dhi = uint32_t(g.desc_hi >> 32), dlo = uint32_t(g.desc_hi);       // descriptor halves (dlo = the LBO field)
+    const uint32_t row_shift = (uint32_t(g.tw) * uint32_t(2 * g.bk)) >> 4, col_shift = uint32_t(2 * g.bk) >> 4;   // halo taps
+    const uint32_t b_base = smem_base + a_region;
+    int stage = 0, stageA = 0;
+    uint32_t phase = 0, phaseA = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    bool b_ready = false;   // resident weights: every slot has landed once the first item has been issued
+    auto lo_of = [dlo](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | dlo; };
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int ks = (ksplit == 1) ? 0 : item % ksplit;
+      const int kb0 = ks * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+      mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + uint32_t(acc * 256);
+      uint32_t accum = 0;   // the first MMA of an item overwrites the accumulator
+      if (sep) {
+        for (int u = kb0; u < kb1; ++u) {
+          mbar_wait(bar_afull + 8 * stageA, phaseA);
+          tc_fence_after();
+          const uint32_t a0 = lo_of(smem_base + uint32_t(stageA) * a_slot);
+          if constexpr (kTrace) { if (item == blockIdx.x && u == kb0 && lane == 0) trace_stamp<kTrace>(g, kTrFirstFull); }
+          const int taps_y = halo ? 3 : 1;
+          int slot = bres ? (u - kb0) * (halo ? 9 : 1) : stage;
+          for (int ky = 0; ky < taps_y; ++ky) {
+            for (int kx = 0; kx < taps_y; ++kx) {
+              if (!b_ready) {
+                // resident weights: slot (unit, tap) completes its one and only phase (parity 0) during the first item
+                mbar_wait(bar_full + 8 * slot, bres ? 0u : phase);
+                tc_fence_after();
               }
-              const uint32_t sb = smem_base + a_region + slot * stage_bytes;
-              // The 128B-swizzle pattern is anchored at the 1024-B aligned slot base (that is how TMA wrote it), so the
-              // "matrix base offset" field stays 0 even though the start address points into the middle of an atom:
-              // the XOR phase is taken from the address bits, exactly as for the +32 B K-advance.
-              const uint64_t da = g.desc_hi | uint64_t((sa & 0x3FFFF) >> 4);
-              const uint64_t db = g.desc_hi | uint64_t((sb & 0x3FFFF) >> 4);
-              for (int k = 0; k < ksteps; ++k)
-                umma_f16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), g.idesc, ((u - kb0) | tap | k) != 0);
-              if (!g.bres) {
-                umma_commit(bar_empty + 8 * stage);
-                if (++stage == g.stages) { stage = 0; phase ^= 1; }
+              // halo mode: shifted view of the halo tile.  The 128B/64B swizzle pattern is anchored at the 1024-B aligned slot
+              // base (that is how TMA wrote it), so the "matrix base offset" field stays 0 even though the start address
+              // points into the middle of an atom: the XOR phase is taken from the address bits, as for the K-advance.
+              const uint32_t a_lo = a0 + uint32_t(ky) * row_shift + uint32_t(kx) * col_shift;
+              const uint32_t b_lo = lo_of(b_base + uint32_t(slot) * b_slot);
+              if (k64) umma_f16_stage<4>(d_tmem, a_lo, b_lo, dhi, idesc, accum);
+              else umma_f16_stage<2>(d_tmem, a_lo, b_lo, dhi, idesc, accum);
+              accum = 1;
+              if (bres) {
+                ++slot;
+              } else {
+                umma_commit_elect(bar_empty + 8 * stage);
+                if (++stage == n_stages) { stage = 0; phase ^= 1; }
+                slot = stage;
               }
             }
-            umma_commit(bar_aempty + 8 * stageA);
-            if (++stageA == g.stagesA) { stageA = 0; phaseA ^= 1; }
           }
-          umma_commit(bar_tfull + 8 * acc);
-          if constexpr (kTrace) { if (item == blockIdx.x) trace_stamp<kTrace>(g, kTrFirstAccDone); }
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1;
-          continue;
+          umma_commit_elect(bar_aempty + 8 * stageA);
+          if (++stageA == n_stagesA) { stageA = 0; phaseA ^= 1; }
         }
+        if (bres) b_ready = true;
+      } else {
+        const uint32_t stage_bytes_ = stage_bytes;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
-          if constexpr (kTrace) { if (item == blockIdx.x && kb == kb0) trace_stamp<kTrace>(g, kTrFirstFull); }
-          const uint32_t sa = smem_base + stage * stage_bytes;
+          if constexpr (kTrace) { if (item == blockIdx.x && kb == kb0 && lane == 0) trace_stamp<kTrace>(g, kTrFirstFull); }
+          const uint32_t sa = smem_base + uint32_t(stage) * stage_bytes_;
           const uint32_t sb = sa + a_part;
-          const uint64_t da = g.desc_hi | uint64_t((sa & 0x3FFFF) >> 4);
-          const uint64_t db = g.desc_hi | uint64_t((sb & 0x3FFFF) >> 4);
-          if (g.x3) {
-            const uint64_t da_lo = g.desc_hi | uint64_t(((sa + kASlot) & 0x3FFFF) >> 4);
-            const uint64_t db_lo = g.desc_hi | uint64_t(((sb + g.b_slot) & 0x3FFFF) >> 4);
-            for (int k = 0; k < ksteps; ++k) {
-              umma_f16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), g.idesc, ((kb - kb0) | k) != 0);   // hi * hi
-              umma_f16(d_tmem, da + uint64_t(2 * k), db_lo + uint64_t(2 * k), g.idesc, 1u);                   // hi * lo
-              umma_f16(d_tmem, da_lo + uint64_t(2 * k), db + uint64_t(2 * k), g.idesc, 1u);                   // lo * hi
-            }
+          if (x3) {
+            // advancing K inside the swizzle span = +32 B on the start address (encoded >> 4)
+            if (k64) umma_f16x3_stage<4>(d_tmem, lo_of(sa), lo_of(sa + kASlot), lo_of(sb), lo_of(sb + b_slot), dhi, idesc, accum);
+            else umma_f16x3_stage<2>(d_tmem, lo_of(sa), lo_of(sa + kASlot), lo_of(sb), lo_of(sb + b_slot), dhi, idesc, accum);
           } else {
-            for (int k = 0; k < ksteps; ++k) {
-              // advancing K inside the swizzle span = +32 B on the start address (encoded >> 4)
-              umma_f16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), g.idesc, ((kb - kb0) | k) != 0);
-            }
+            if (k64) umma_f16_stage<4>(d_tmem, lo_of(sa), lo_of(sb), dhi, idesc, accum);
+            else umma_f16_stage<2>(d_tmem, lo_of(sa), lo_of(sb), dhi, idesc, accum);
           }
-          umma_commit(bar_empty + 8 * stage);
-          if (++stage == g.stages) { stage = 0; phase ^= 1; }
+          accum = 1;
+          umma_commit_elect(bar_empty + 8 * stage);
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(bar_tfull + 8 * acc);
-        if constexpr (kTrace) { if (item == blockIdx.x) trace_stamp<kTrace>(g, kTrFirstAccDone); }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
       }
+      umma_commit_elect(bar_tfull + 8 * acc);
+      if constexpr (kTrace) { if (item == blockIdx.x && lane == 0) trace_stamp<kTrace>(g, kTrFirstAccDone); }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     // -------------------------------------------------------------- epilogue (16 warps: 128 TMEM lanes x 4 column phases)
@@ -888,7 +894,7 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
   }
   int bn = 16, ksplit = 1;
   static const bool no_split = getenv("B2P_NO_SPLITK") != nullptr;
-  const int slot = no_split ? -1 : ws_slot_for(st);
+  const int slot = (no_split || d.no_split) ? -1 : ws_slot_for(st);
   pick_tiling(d.N, g.m_tiles, g.num_kb, halo ? 9 * bk : bk, g.a_bytes, d.bn_max > 0 ? d.bn_max : 256, slot >= 0, d.x3 != 0, &bn, &ksplit);
   // Resident weights: one N tile, no split-K, at least one full wave of M tiles, and the whole weight matrix + a >= 2-deep
   // A ring must fit in shared memory (see GemmArgs::bres).

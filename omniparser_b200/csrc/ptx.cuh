@@ -104,6 +104,75 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- warp-converged issue: the WHOLE warp executes these (operands warp-uniform); elect.sync picks the same lane every
+// time (deterministic for a full member mask), which issues the tensor-core instructions.  No C++ divergence around the
+// tcgen05.mma, so the compiler keeps the descriptors in uniform registers instead of wrapping every UTCHMMA in a
+// per-active-thread serialisation loop (profiles/r2_notes.md: the single MMA-issuing thread was instruction-bound).
+// Descriptors are passed as 32-bit halves: lo = (smem address >> 4) | LBO field, hi = constant per launch; advancing K by
+// 16 elements inside the swizzle span is +2 on lo.  KSTEPS k-steps of one (A, B) stage per call.
+template <int KSTEPS>
+__device__ __forceinline__ void umma_f16_stage(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+  static_assert(KSTEPS == 2 || KSTEPS == 4, "k-block of 32 or 64 elements");
+  if constexpr (KSTEPS == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t.reg .b32 a1, b1;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+        "add.u32 a1, %1, 2;\n\tadd.u32 b1, %2, 2;\n\t"
+        "mov.b64 da, {a1, %3};\n\tmov.b64 db, {b1, %3};\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, 1;\n\t}\n"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t.reg .b32 a1, b1;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+        "add.u32 a1, %1, 2;\n\tadd.u32 b1, %2, 2;\n\t"
+        "mov.b64 da, {a1, %3};\n\tmov.b64 db, {b1, %3};\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, 1;\n\t"
+        "add.u32 a1, %1, 4;\n\tadd.u32 b1, %2, 4;\n\t"
+        "mov.b64 da, {a1, %3};\n\tmov.b64 db, {b1, %3};\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, 1;\n\t"
+        "add.u32 a1, %1, 6;\n\tadd.u32 b1, %2, 6;\n\t"
+        "mov.b64 da, {a1, %3};\n\tmov.b64 db, {b1, %3};\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, 1;\n\t}\n"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// fp16x3 operands: per k-step hi*hi (+)= , hi*lo +=, lo*hi += into the same accumulator
+template <int KSTEPS>
+__device__ __forceinline__ void umma_f16x3_stage(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                                 uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+#pragma unroll
+  for (int k = 0; k < KSTEPS; ++k) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 dah, dal, dbh, dbl;\n\t"
+        "setp.ne.b32 p, %7, 0;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "mov.b64 dah, {%1, %5};\n\tmov.b64 dal, {%2, %5};\n\tmov.b64 dbh, {%3, %5};\n\tmov.b64 dbl, {%4, %5};\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], dah, dbh, %6, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], dah, dbl, %6, 1;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], dal, dbh, %6, 1;\n\t}\n"
+        ::"r"(tmem_d), "r"(a_hi + 2u * k), "r"(a_lo + 2u * k), "r"(b_hi + 2u * k), "r"(b_lo + 2u * k), "r"(desc_hi), "r"(idesc),
+          "r"(k == 0 ? accumulate : 1u)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
+      ::"r"(bar)
+      : "memory");
+}
+
 // Arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

@@ -35,7 +35,7 @@ def count_graph_launches(n: int):
     """the detect and caption threads of the pipelined parser replay graphs concurrently"""
     with _GRAPH_LAUNCHES_LOCK:
         GRAPH_LAUNCHES[0] += n
-FLAG_BF16, FLAG_OUT_F32, FLAG_SPLIT, FLAG_X3 = 1, 2, 4, 8
+FLAG_BF16, FLAG_OUT_F32, FLAG_SPLIT, FLAG_X3, FLAG_NO_SPLITK = 1, 2, 4, 8, 16
 
 
 def _stream():
@@ -93,10 +93,10 @@ def new_map(B, H, W, Ctot, device, dtype=torch.float16, x3=False):
 
 
 def gemm(a_ptr, lda, w, M, N, K, out_ptr, ldc, bias=None, res_ptr=None, ldr=0, act=ACT_NONE, out_f32=False,
-         bf16=False, bn_max=0, split=False, x3=False):
+         bf16=False, bn_max=0, split=False, x3=False, no_splitk=False):
     """x3: fp16x3 operands -- A rows [hi(K) | lo(K)], w rows [hi(K) | lo(K)], K logical; split: fp16 output as [hi | lo]."""
     flags = ((FLAG_BF16 if bf16 else 0) | (FLAG_OUT_F32 if out_f32 else 0) | (FLAG_SPLIT if split else 0) |
-             (FLAG_X3 if x3 else 0) | (bn_max << 8))
+             (FLAG_X3 if x3 else 0) | (FLAG_NO_SPLITK if no_splitk else 0) | (bn_max << 8))
     _lib.check(_lib.lib().b2p_gemm(_p(a_ptr), lda, _p(w), M, N, K, _p(out_ptr), ldc, _p(bias), _p(res_ptr), ldr, act,
                                    flags, _stream()))
 

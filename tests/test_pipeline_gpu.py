@@ -190,9 +190,15 @@ def test_device_overlap_filter_path_equals_host_list_logic(monkeypatch):
     assert any(e["source"] == "box_yolo_content_ocr" for el, _ in ref for e in el)
     for (ge_, gi), (re_, ri) in zip(got, ref):
         assert ge_ == re_ and torch.equal(gi, ri)
-    pp = U.PipelinedParser(det, cmp_, BOX_TRESHOLD=0.05, iou_threshold=0.7, max_new_tokens=8, caption_lanes=2)
+    # the pipelined parser, batches of 2 (detector numerics depend on the batch size through the GEMM tiling, so the host-logic
+    # reference is taken at the same batch size)
     batches = [(imgs[:2], ocr[:2]), (imgs[2:], ocr[2:]), (imgs[:2], ocr[:2])]
+    monkeypatch.setattr(U, "_HOST_GLUE", True)
+    ref2 = [x for im, oc in batches for x in U.parse_screenshots(im, det, cmp_, oc, BOX_TRESHOLD=0.05, iou_threshold=0.7, max_new_tokens=8)]
+    monkeypatch.setattr(U, "_HOST_GLUE", False)
+    pp = U.PipelinedParser(det, cmp_, BOX_TRESHOLD=0.05, iou_threshold=0.7, max_new_tokens=8, caption_lanes=2)
     out = list(pp.run(iter(batches)))
     flat = [x for b in out for x in b]
-    for (ge_, gi), (re_, ri) in zip(flat, ref + ref[:2]):
+    assert len(flat) == len(ref2)
+    for (ge_, gi), (re_, ri) in zip(flat, ref2):
         assert ge_ == re_ and torch.equal(gi, ri)
