@@ -29,8 +29,29 @@ static constexpr int kASlot = 16384;    // 128 rows x 128 B
 static constexpr int kMaxStages = 8;
 static constexpr int kTmemCols = 512;
 
+// q = n / d for 0 <= n < 2^31 by multiply-high + shift (d >= 1), precomputed on the host
+struct FastDiv {
+  uint32_t mul, shr;
+  __host__ static FastDiv make(int d) {
+    FastDiv f;
+    if (d <= 1) { f.mul = 0; f.shr = 0; return f; }          // shr == 0 marks d == 1
+    uint32_t l = 0;
+    while ((1u << l) < uint32_t(d)) ++l;                     // ceil(log2 d)
+    const unsigned long long m = ((1ull << (32 + l)) + uint32_t(d) - 1) / uint32_t(d);   // ceil(2^(32+l) / d)  (33 bits)
+    f.mul = uint32_t(m - (1ull << 32));
+    f.shr = l;
+    return f;
+  }
+  __device__ __forceinline__ int div(int n) const {
+    if (shr == 0) return n;
+    const uint32_t t = __umulhi(uint32_t(n), mul);
+    return int((((uint32_t(n) - t) >> 1) + t) >> (shr - 1));   // Granlund-Montgomery round-up method, d in [2, 2^31)
+  }
+};
+
 struct GemmArgs {
   int mode, M, N, num_kb, bk, bn;
+  FastDiv d_ksplit, d_ntiles, d_mtiles, d_perimg, d_tilesx, d_cinb;   // divisors of the item -> tile decode
   int cin_blocks, tw, th, tiles_x, tiles_y, Ho, Wo, batch;
   int m_tiles, n_tiles, stages, ldpar;
   int nb;                // images per tile (small maps: a TMA box spans nb consecutive images)
@@ -43,7 +64,7 @@ struct GemmArgs {
   // the small-channel layers (N, Cin <= 64..256 on the 160x160 / 80x80 maps: 10+ tiles per CTA) the weight re-loads and
   // their barrier round trips were the per-tile critical path (3.5 us per 128-pixel tile, profiles/r2_notes.md).
   int sep, bres, taps;
-  int ksplit, kb_per;    // split-K: work item = (m tile, n tile, k slice); the last CTA of a tile reduces + stores
+  int ksplit, kb_per;    // split-K: work item = (m tile, n tile, k slice); the last CTA to arrive for a tile reduces + stores
   uint32_t a_bytes, b_bytes, b_slot;
   uint32_t idesc;
   uint64_t desc_hi;   // high 32 bits of the smem matrix descriptor (SBO, version, layout), shifted in place
@@ -63,6 +84,7 @@ struct GemmArgs {
   int x3, lo_a, lo_b, b_tap;   // lo_a / lo_b: column offset of the lo half in A / B; b_tap: B columns per conv tap
   float* ws;   // split-K partial tiles [tile][slice][128][bn] fp32
   int* counters;   // split-K {arrived, finished} counters per output tile (self-resetting)
+  int sk_last;     // split-K variant: 1 = last arriver reduces (wait-free, B2P_SPLITK_LAST=1), 0 = distributed reduction
   unsigned long long* trace;   // B2P_TRACE build of the kernel only: [CTA][16] globaltimer stamps (see trace_stamp)
 };
 
@@ -290,111 +312,122 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
   const uint32_t smem_base = smem_u32(smem);
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ TMA producer
-      int stage = 0, stageA = 0;
-      uint32_t phase = 0, phaseA = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int ks = item % g.ksplit;
-        const int tile = item / g.ksplit;
-        const int nt = g.mt_fast ? tile / g.m_tiles : tile % g.n_tiles;
-        const int mt = g.mt_fast ? tile % g.m_tiles : tile / g.n_tiles;
-        const int n0 = nt * g.bn;
-        int img = 0, y0 = 0, x0 = 0;
-        if (g.mode != 0) {
-          const int per_img = g.tiles_x * g.tiles_y;
-          img = mt / per_img;
-          const int r = mt - img * per_img;
-          y0 = (r / g.tiles_x) * g.th;
-          x0 = (r % g.tiles_x) * g.tw_valid;
-          img *= g.nb;   // nb > 1 only when one tile covers whole images (per_img == 1)
-        }
-        const int kb0 = ks * g.kb_per, kb1 = min(g.num_kb, kb0 + g.kb_per);
-        if (g.sep) {
-          // separate pipelines.  Halo mode (3): ONE (th+2) x (tw+2) input tile per channel block feeds all nine taps (the MMA
-          // side shifts the smem descriptor start address by (ky*pitch + kx) rows); only the weights stream per tap.
-          // Other modes: one A tile per k-block.  Resident weights (bres): B slot (unit*taps + tap) is filled on this CTA's
-          // first item only and never released.
-          const bool first_item = (item == int(blockIdx.x));
-          for (int u = kb0; u < kb1; ++u) {
-            mbar_wait(bar_aempty + 8 * stageA, phaseA ^ 1);
-            const uint32_t fa = bar_afull + 8 * stageA;
-            const uint32_t dstA = smem_base + stageA * g.a_slot;
-            mbar_expect_tx(fa, g.a_bytes);
-            int bcol0;
-            if (g.mode == 3) {
-              tma_load_4d(dstA, &tmA, fa, u * g.bk, x0 - 1, y0 - 1, img);
-              bcol0 = u * g.bk;                                   // + tap * cin below
-            } else if (g.mode == 0) {
-              tma_load_2d(dstA, &tmA, fa, u * g.bk, mt * kTileM);
-              bcol0 = u * g.bk;
+    // ------------------------------------------------------------ TMA producer
+    // Warp-converged like the MMA issuer below: all lanes run the loop and wait on the "empty" barriers, one elected lane
+    // issues the TMA instructions; loop state lives in registers, item -> tile coordinates by multiply-shift division.
+    const int n_stages = g.stages, n_stagesA = g.stagesA, ksplit = g.ksplit, kb_per = g.kb_per, num_kb = g.num_kb;
+    const int mode = g.mode, bk = g.bk, bn = g.bn, cin = g.cin, cin_blocks = g.cin_blocks, b_tap = g.b_tap, ldpar = g.ldpar;
+    const int th = g.th, tw_valid = g.tw_valid, nb = g.nb, lo_a = g.lo_a, lo_b = g.lo_b, taps = g.taps;
+    const bool sep = g.sep != 0, bres = g.bres != 0, x3 = g.x3 != 0, mt_fast = g.mt_fast != 0;
+    const uint32_t a_bytes = g.a_bytes, b_bytes = g.b_bytes, a_slot = g.a_slot, b_slot = g.b_slot;
+    const FastDiv d_ksplit = g.d_ksplit, d_ntiles = g.d_ntiles, d_mtiles = g.d_mtiles, d_perimg = g.d_perimg, d_tilesx = g.d_tilesx,
+                  d_cinb = g.d_cinb;
+    const uint32_t b_base = smem_base + a_region;
+    int stage = 0, stageA = 0;
+    uint32_t phase = 0, phaseA = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int tile = d_ksplit.div(item);
+      const int ks = item - tile * ksplit;
+      int nt, mt;
+      if (mt_fast) { nt = d_mtiles.div(tile); mt = tile - nt * g.m_tiles; }
+      else { mt = d_ntiles.div(tile); nt = tile - mt * g.n_tiles; }
+      const int n0 = nt * bn;
+      int img = 0, y0 = 0, x0 = 0;
+      if (mode != 0) {
+        img = d_perimg.div(mt);
+        const int r = mt - img * g.tiles_x * g.tiles_y;
+        const int ty = d_tilesx.div(r);
+        y0 = ty * th;
+        x0 = (r - ty * g.tiles_x) * tw_valid;
+        img *= nb;   // nb > 1 only when one tile covers whole images (per_img == 1)
+      }
+      const int kb0 = ks * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+      if (sep) {
+        // separate pipelines.  Halo mode (3): ONE (th+2) x (tw+2) input tile per channel block feeds all nine taps (the MMA
+        // side shifts the smem descriptor start address by (ky*pitch + kx) rows); only the weights stream per tap.
+        // Other modes: one A tile per k-block.  Resident weights (bres): B slot (unit*taps + tap) is filled on this CTA's
+        // first item only and never released.
+        const bool first_item = (item == int(blockIdx.x));
+        for (int u = kb0; u < kb1; ++u) {
+          mbar_wait(bar_aempty + 8 * stageA, phaseA ^ 1);
+          const uint32_t fa = bar_afull + 8 * stageA;
+          const uint32_t dstA = smem_base + uint32_t(stageA) * a_slot;
+          mbar_expect_tx_elect(fa, a_bytes);
+          int bcol0;
+          if (mode == 3) {
+            tma_load_4d_elect(dstA, &tmA, fa, u * bk, x0 - 1, y0 - 1, img);
+            bcol0 = u * bk;                                   // + tap * cin below
+          } else if (mode == 0) {
+            tma_load_2d_elect(dstA, &tmA, fa, u * bk, mt * kTileM);
+            bcol0 = u * bk;
+          } else {
+            const int tap = d_cinb.div(u);
+            const int c0 = (u - tap * cin_blocks) * bk;
+            const int ky = (tap * 11) >> 5, kx = tap - ky * 3;     // tap / 3 for tap in 0..8
+            bcol0 = tap * b_tap + c0;
+            if (mode == 1) {
+              tma_load_4d_elect(dstA, &tmA, fa, c0, x0 + kx - 1, y0 + ky - 1, img);
             } else {
-              const int tap = u / g.cin_blocks;
-              const int c0 = (u - tap * g.cin_blocks) * g.bk;
-              const int ky = tap / 3, kx = tap - ky * 3;
-              bcol0 = tap * g.b_tap + c0;
-              if (g.mode == 1) {
-                tma_load_4d(dstA, &tmA, fa, c0, x0 + kx - 1, y0 + ky - 1, img);
-              } else {
-                const int py = (ky != 1), px = (kx != 1);
-                const int yo = y0 - (ky == 0), xo = x0 - (kx == 0);
-                tma_load_5d(dstA, &tmA, fa, c0 + px * g.ldpar, xo, py, yo, img);
-              }
-            }
-            if constexpr (kTrace) { if (item == blockIdx.x && u == kb0) trace_stamp<kTrace>(g, kTrFirstTma); }
-            if (++stageA == g.stagesA) { stageA = 0; phaseA ^= 1; }
-            for (int tap = 0; tap < g.taps; ++tap) {
-              const int bcol = (g.mode == 3) ? tap * g.cin + bcol0 : bcol0;
-              if (g.bres) {
-                if (first_item) {
-                  const int slot = (u - kb0) * g.taps + tap;
-                  const uint32_t fb = bar_full + 8 * slot;
-                  mbar_expect_tx(fb, g.b_bytes);
-                  tma_load_2d(smem_base + a_region + slot * stage_bytes, &tmB, fb, bcol, n0);
-                }
-                continue;
-              }
-              mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-              const uint32_t fb = bar_full + 8 * stage;
-              mbar_expect_tx(fb, g.b_bytes);
-              tma_load_2d(smem_base + a_region + stage * stage_bytes, &tmB, fb, bcol, n0);
-              if (++stage == g.stages) { stage = 0; phase ^= 1; }
+              const int py = (ky != 1), px = (kx != 1);
+              const int yo = y0 - (ky == 0), xo = x0 - (kx == 0);
+              tma_load_5d_elect(dstA, &tmA, fa, c0 + px * ldpar, xo, py, yo, img);
             }
           }
-          continue;
-        }
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-          const uint32_t fb = bar_full + 8 * stage;
-          const uint32_t sa = smem_base + stage * stage_bytes;
-          const uint32_t sb = sa + a_part;
-          mbar_expect_tx(fb, g.x3 ? 2u * (g.a_bytes + g.b_bytes) : g.a_bytes + g.b_bytes);
-          int bcol = kb * g.bk;
-          for (int half = 0; half <= g.x3; ++half) {     // half 1 = the lo parts (fp16x3 operands only)
-            const uint32_t dst = sa + half * kASlot;
-            const int ca = half * g.lo_a;
-            if (g.mode == 0) {
-              tma_load_2d(dst, &tmA, fb, ca + kb * g.bk, mt * kTileM);
-            } else {
-              const int tap = kb / g.cin_blocks;
-              const int c0 = (kb - tap * g.cin_blocks) * g.bk;
-              const int ky = tap / 3, kx = tap - ky * 3;
-              bcol = tap * g.b_tap + c0;
-              if (g.mode == 1) {
-                tma_load_4d(dst, &tmA, fb, ca + c0, x0 + kx - 1, y0 + ky - 1, img);
-              } else {
-                // input row 2*oy + (ky-1): ky=0 -> (oy-1, odd), ky=1 -> (oy, even), ky=2 -> (oy, odd); same in x.
-                const int py = (ky != 1), px = (kx != 1);
-                const int yo = y0 - (ky == 0), xo = x0 - (kx == 0);
-                tma_load_5d(dst, &tmA, fb, ca + c0 + px * g.ldpar, xo, py, yo, img);
+          if constexpr (kTrace) { if (item == blockIdx.x && u == kb0 && lane == 0) trace_stamp<kTrace>(g, kTrFirstTma); }
+          if (++stageA == n_stagesA) { stageA = 0; phaseA ^= 1; }
+          if (bres) {
+            if (first_item) {
+              for (int tap = 0; tap < taps; ++tap) {
+                const int slot = (u - kb0) * taps + tap;
+                const uint32_t fb = bar_full + 8 * slot;
+                mbar_expect_tx_elect(fb, b_bytes);
+                tma_load_2d_elect(b_base + uint32_t(slot) * b_slot, &tmB, fb, (mode == 3) ? tap * cin + bcol0 : bcol0, n0);
               }
             }
+            continue;
           }
-          tma_load_2d(sb, &tmB, fb, bcol, n0);
-          if (g.x3) tma_load_2d(sb + g.b_slot, &tmB, fb, bcol + g.lo_b, n0);
-          if constexpr (kTrace) { if (item == blockIdx.x && kb == kb0) trace_stamp<kTrace>(g, kTrFirstTma); }
-          if (++stage == g.stages) { stage = 0; phase ^= 1; }
+          for (int tap = 0; tap < taps; ++tap) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            const uint32_t fb = bar_full + 8 * stage;
+            mbar_expect_tx_elect(fb, b_bytes);
+            tma_load_2d_elect(b_base + uint32_t(stage) * b_slot, &tmB, fb, (mode == 3) ? tap * cin + bcol0 : bcol0, n0);
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
+          }
         }
+        continue;
+      }
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        const uint32_t fb = bar_full + 8 * stage;
+        const uint32_t sa = smem_base + uint32_t(stage) * stage_bytes;
+        const uint32_t sb = sa + a_part;
+        mbar_expect_tx_elect(fb, x3 ? 2u * (a_bytes + b_bytes) : a_bytes + b_bytes);
+        int bcol = kb * bk;
+        int tap = 0, c0 = 0, ky = 0, kx = 0;
+        if (mode != 0) {
+          tap = d_cinb.div(kb);
+          c0 = (kb - tap * cin_blocks) * bk;
+          ky = (tap * 11) >> 5; kx = tap - ky * 3;
+          bcol = tap * b_tap + c0;
+        }
+        for (int half = 0; half <= int(x3); ++half) {     // half 1 = the lo parts (fp16x3 operands only)
+          const uint32_t dst = sa + uint32_t(half) * kASlot;
+          const int ca = half * lo_a;
+          if (mode == 0) {
+            tma_load_2d_elect(dst, &tmA, fb, ca + kb * bk, mt * kTileM);
+          } else if (mode == 1) {
+            tma_load_4d_elect(dst, &tmA, fb, ca + c0, x0 + kx - 1, y0 + ky - 1, img);
+          } else {
+            // input row 2*oy + (ky-1): ky=0 -> (oy-1, odd), ky=1 -> (oy, even), ky=2 -> (oy, odd); same in x.
+            const int py = (ky != 1), px = (kx != 1);
+            const int yo = y0 - (ky == 0), xo = x0 - (kx == 0);
+            tma_load_5d_elect(dst, &tmA, fb, ca + c0 + px * ldpar, xo, py, yo, img);
+          }
+        }
+        tma_load_2d_elect(sb, &tmB, fb, bcol, n0);
+        if (x3) tma_load_2d_elect(sb + b_slot, &tmB, fb, bcol + lo_b, n0);
+        if constexpr (kTrace) { if (item == blockIdx.x && kb == kb0 && lane == 0) trace_stamp<kTrace>(g, kTrFirstTma); }
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -496,59 +529,93 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
     e.outf = reinterpret_cast<float*>(g.out);
     e.resh = reinterpret_cast<const __half*>(g.res);
     e.resf = reinterpret_cast<const float*>(g.res);
+    // this thread's row of the tile: its position inside the (tw x th [x nb images]) tile never changes
+    const int r = grp * 32 + lane;
+    const int e_mode = g.mode, e_ksplit = g.ksplit, e_bn = g.bn, e_th = g.th, e_twv = g.tw_valid, e_nb = g.nb;
+    const int e_Ho = g.Ho, e_Wo = g.Wo, e_batch = g.batch, e_tiles_x = g.tiles_x, e_per_img = g.tiles_x * g.tiles_y;
+    const bool e_mtfast = g.mt_fast != 0;
+    const FastDiv e_dks = g.d_ksplit, e_dnt = g.d_ntiles, e_dmt = g.d_mtiles, e_dpi = g.d_perimg, e_dtx = g.d_tilesx;
+    int r_sub = 0, r_ty = 0, r_tx = 0;
+    if (e_mode != 0) {
+      const int rows_img = g.tw * g.th;                  // rows of one image inside the tile
+      r_sub = (e_nb > 1) ? r / rows_img : 0;
+      const int rloc = r - r_sub * rows_img;
+      r_ty = rloc / g.tw;
+      r_tx = rloc - r_ty * g.tw;
+    }
+    const bool r_ok = (r_sub < e_nb) && (r_ty < e_th) && (r_tx < e_twv);
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const int ks = item % g.ksplit;
-      const int tile = item / g.ksplit;
-      const int nt = g.mt_fast ? tile / g.m_tiles : tile % g.n_tiles;
-      const int mt = g.mt_fast ? tile % g.m_tiles : tile / g.n_tiles;
-      const int n0 = nt * g.bn;
-      const int r = grp * 32 + lane;
+      const int tile = e_dks.div(item);
+      const int ks = item - tile * e_ksplit;
+      int nt, mt;
+      if (e_mtfast) { nt = e_dmt.div(tile); mt = tile - nt * g.m_tiles; }
+      else { mt = e_dnt.div(tile); nt = tile - mt * g.n_tiles; }
+      const int n0 = nt * e_bn;
       long long pix;
       bool valid;
-      if (g.mode == 0) {
+      if (e_mode == 0) {
         pix = (long long)mt * kTileM + r;
         valid = pix < g.M;
       } else {
-        const int per_img = g.tiles_x * g.tiles_y;
-        const int img0 = mt / per_img;
-        const int rr = mt - img0 * per_img;
-        const int rows_img = g.tw * g.th;                  // rows of one image inside the tile
-        const int sub = (g.nb > 1) ? r / rows_img : 0;
-        const int rloc = r - sub * rows_img;
-        const int img = img0 * g.nb + sub;
-        const int ty = rloc / g.tw, tx = rloc - ty * g.tw;
-        const int oy = (rr / g.tiles_x) * g.th + ty;
-        const int ox = (rr % g.tiles_x) * g.tw_valid + tx;
-        valid = (sub < g.nb) && (img < g.batch) && (ty < g.th) && (tx < g.tw_valid) && (oy < g.Ho) && (ox < g.Wo);
-        pix = ((long long)img * g.Ho + oy) * g.Wo + ox;
+        const int img0 = e_dpi.div(mt);
+        const int rr = mt - img0 * e_per_img;
+        const int img = img0 * e_nb + r_sub;
+        const int tyi = e_dtx.div(rr);
+        const int oy = tyi * e_th + r_ty;
+        const int ox = (rr - tyi * e_tiles_x) * e_twv + r_tx;
+        valid = r_ok && (img < e_batch) && (oy < e_Ho) && (ox < e_Wo);
+        pix = ((long long)img * e_Ho + oy) * e_Wo + ox;
       }
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       if constexpr (kTrace) { if (item == blockIdx.x && threadIdx.x == 64) trace_stamp<kTrace>(g, kTrFirstEpiStart); }
       const uint32_t t_row = tmem_base + (uint32_t(grp * 32) << 16) + uint32_t(acc * 256);
-      if (g.ksplit == 1) {
-        for (int c = cq * 16; c < g.bn; c += 64) {
-          uint32_t v[16];
-          tmem_ld16(t_row + c, v);
-          tmem_ld_wait();
-          if (n0 + c >= g.N) continue;   // warp-uniform
-          float x[16];
+      if (e_ksplit == 1) {
+        // software-pipelined: the TMEM load of this warp's next 16-column chunk is in flight while the current chunk runs its
+        // bias / activation / residual / store chain, and the accumulator goes back to the MMA warp as soon as the LAST chunk
+        // sits in registers (before it is processed).  r2_notes.md: N >= 128 SiLU / GELU tiles were epilogue-bound (5-6 us per
+        // 128x256 tile against ~2 us of MUFU work): every chunk paid the tcgen05.ld latency serially.
+        int c = cq * 16;
+        if (c < e_bn) {
+          uint32_t va[16], vb[16];
+          tmem_ld16(t_row + c, va);
+          tmem_ld_wait(va);
+          while (true) {
+            const int cn = c + 64;
+            const bool more = cn < e_bn;
+            if (more) {
+              tmem_ld16(t_row + cn, vb);
+            } else {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+            }
+            if (n0 + c < g.N) {   // warp-uniform
+              float x[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]);
-          epi_store16(g, e, x, n0 + c, pix, valid);
+              for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(va[j]);
+              epi_store16(g, e, x, n0 + c, pix, valid);
+            }
+            if (!more) break;
+            tmem_ld_wait(vb);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) va[j] = vb[j];
+            c = cn;
+          }
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
       } else {
-        // split-K (only launched when every work item owns a resident CTA, so spinning on the arrival counter is
-        // safe): park the raw partial tile; when all ksplit slices of this output tile have landed, each of the
-        // ksplit CTAs reduces its share of the 128 rows (slice order => deterministic sums) and runs the epilogue.
-        float* wsp = g.ws + ((size_t(tile) * g.ksplit + ks) * kTileM + r) * g.bn;
-        for (int c = cq * 16; c < g.bn; c += 64) {
+        // split-K: every slice parks its raw fp32 partial tile, then the partials are summed in slice order (deterministic) and
+        // the epilogue runs -- by the last CTA to arrive (sk_last: nobody waits for anybody, so partially resident grids cannot
+        // deadlock) or, by default, distributed over the tile's ksplit CTAs (faster, see below).
+        float* wsp = g.ws + ((size_t(tile) * e_ksplit + ks) * kTileM + r) * e_bn;
+        for (int c = cq * 16; c < e_bn; c += 64) {
           uint32_t v[16];
           tmem_ld16(t_row + c, v);
-          tmem_ld_wait();
+          tmem_ld_wait(v);
           float4* wp = reinterpret_cast<float4*>(wsp + c);
 #pragma unroll
           for (int q = 0; q < 4; ++q)
@@ -557,61 +624,122 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-        __threadfence();
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-        int* cnt = g.counters + 2 * tile;
-        if (threadIdx.x == 64) {
-          atomicAdd(cnt, 1);
-          long long t0 = clock64();
-          while (*reinterpret_cast<volatile int*>(cnt) < g.ksplit) {
-            if (clock64() - t0 > 4000000000LL) { printf("b2p: split-K arrival timeout (tile %d)\n", tile); __trap(); }
+        if (g.sk_last) {
+          __threadfence();
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+          volatile uint32_t* s_last = tmem_slot + 1;
+          if (threadIdx.x == 64) {
+            int* cnt = g.counters + 2 * tile;
+            const bool last = (atomicAdd(cnt, 1) == e_ksplit - 1);
+            if (last) *cnt = 0;   // every slice has arrived: the next user of this counter is a later launch / graph replay
+            *s_last = last ? 1u : 0u;
           }
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-        __threadfence();
-        const int rows_per = (kTileM + g.ksplit - 1) / g.ksplit;
-        const int row0 = ks * rows_per, row1 = min(kTileM, row0 + rows_per);
-        const int chunks = g.bn >> 4;
-        const float* base = g.ws + size_t(tile) * g.ksplit * kTileM * g.bn;
-        for (int w = (threadIdx.x - 64); w < (row1 - row0) * chunks; w += kEpiThreads) {
-          const int rr_ = row0 + w / chunks, c = (w % chunks) << 4;
-          if (n0 + c >= g.N) continue;
-          long long pix2;
-          bool valid2;
-          if (g.mode == 0) {
-            pix2 = (long long)mt * kTileM + rr_;
-            valid2 = pix2 < g.M;
-          } else {
-            const int per_img = g.tiles_x * g.tiles_y;
-            const int img0 = mt / per_img;
-            const int rr = mt - img0 * per_img;
-            const int rows_img = g.tw * g.th;
-            const int sub = (g.nb > 1) ? rr_ / rows_img : 0;
-            const int rloc = rr_ - sub * rows_img;
-            const int img = img0 * g.nb + sub;
-            const int ty = rloc / g.tw, tx = rloc - ty * g.tw;
-            const int oy = (rr / g.tiles_x) * g.th + ty;
-            const int ox = (rr % g.tiles_x) * g.tw_valid + tx;
-            valid2 = (sub < g.nb) && (img < g.batch) && (ty < g.th) && (tx < g.tw_valid) && (oy < g.Ho) && (ox < g.Wo);
-            pix2 = ((long long)img * g.Ho + oy) * g.Wo + ox;
-          }
-          float x[16];
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+          if (*s_last) {
+            __threadfence();
+            const int chunks = e_bn >> 4;
+            const float* base = g.ws + size_t(tile) * e_ksplit * kTileM * e_bn;
+            int img0 = 0, rr = 0, tyi = 0;
+            if (e_mode != 0) {
+              img0 = e_dpi.div(mt);
+              rr = mt - img0 * e_per_img;
+              tyi = e_dtx.div(rr);
+            }
+            const int rows_img = g.tw * g.th, tw_ = g.tw;
+            for (int w = (threadIdx.x - 64); w < kTileM * chunks; w += kEpiThreads) {
+              const int rr_ = w / chunks, c = (w - rr_ * chunks) << 4;
+              if (n0 + c >= g.N) continue;
+              long long pix2;
+              bool valid2;
+              if (e_mode == 0) {
+                pix2 = (long long)mt * kTileM + rr_;
+                valid2 = pix2 < g.M;
+              } else {
+                const int sub = (e_nb > 1) ? rr_ / rows_img : 0;
+                const int rloc = rr_ - sub * rows_img;
+                const int img = img0 * e_nb + sub;
+                const int ty = rloc / tw_, tx = rloc - ty * tw_;
+                const int oy = tyi * e_th + ty;
+                const int ox = (rr - tyi * e_tiles_x) * e_twv + tx;
+                valid2 = (sub < e_nb) && (img < e_batch) && (ty < e_th) && (tx < e_twv) && (oy < e_Ho) && (ox < e_Wo);
+                pix2 = ((long long)img * e_Ho + oy) * e_Wo + ox;
+              }
+              float x[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) x[j] = 0.f;
-          for (int sidx = 0; sidx < g.ksplit; ++sidx) {
-            const float4* pp = reinterpret_cast<const float4*>(base + (size_t(sidx) * kTileM + rr_) * g.bn + c);
+              for (int j = 0; j < 16; ++j) x[j] = 0.f;
+              for (int sidx = 0; sidx < e_ksplit; ++sidx) {
+                const float4* pp = reinterpret_cast<const float4*>(base + (size_t(sidx) * kTileM + rr_) * e_bn + c);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 t = __ldcg(pp + q);
-              x[4 * q] += t.x; x[4 * q + 1] += t.y; x[4 * q + 2] += t.z; x[4 * q + 3] += t.w;
+                for (int q = 0; q < 4; ++q) {
+                  const float4 t = __ldcg(pp + q);
+                  x[4 * q] += t.x; x[4 * q + 1] += t.y; x[4 * q + 2] += t.z; x[4 * q + 3] += t.w;
+                }
+              }
+              epi_store16(g, e, x, n0 + c, pix2, valid2);
             }
           }
-          epi_store16(g, e, x, n0 + c, pix2, valid2);
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-        if (threadIdx.x == 64) {
-          // the last CTA to finish its share resets both counters for the next launch / graph replay
-          if (atomicAdd(cnt + 1, 1) == g.ksplit - 1) { cnt[1] = 0; cnt[0] = 0; __threadfence(); }
+        } else {
+          // default: DISTRIBUTED reduction -- each of the ksplit CTAs of a tile waits for the tile's arrival counter and then
+          // reduces its share of the 128 rows (slice order => deterministic sums).  Measured 10-45 % faster per split-K launch
+          // than the wait-free variant above (one CTA re-reads all partials at the per-SM L2 rate), at the price of an
+          // inter-CTA wait: safe because the grid is at most one wave and the hardware dispatches the CTAs of an earlier
+          // launch before those of later ones (tools/coop_test, profiles/r2_notes.md 5); a wait longer than 2 s traps.
+          __threadfence();
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+          int* cnt = g.counters + 2 * tile;
+          if (threadIdx.x == 64) {
+            atomicAdd(cnt, 1);
+            long long t0 = clock64();
+            while (*reinterpret_cast<volatile int*>(cnt) < g.ksplit) {
+              if (clock64() - t0 > 4000000000LL) { printf("b2p: split-K arrival timeout (tile %d)\n", tile); __trap(); }
+            }
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+          __threadfence();
+          const int rows_per = (kTileM + g.ksplit - 1) / g.ksplit;
+          const int row0 = ks * rows_per, row1 = min(kTileM, row0 + rows_per);
+          const int chunks = g.bn >> 4;
+          const float* base = g.ws + size_t(tile) * g.ksplit * kTileM * g.bn;
+          for (int w = (threadIdx.x - 64); w < (row1 - row0) * chunks; w += kEpiThreads) {
+            const int rr_ = row0 + w / chunks, c = (w % chunks) << 4;
+            if (n0 + c >= g.N) continue;
+            long long pix2;
+            bool valid2;
+            if (g.mode == 0) {
+              pix2 = (long long)mt * kTileM + rr_;
+              valid2 = pix2 < g.M;
+            } else {
+              const int per_img = g.tiles_x * g.tiles_y;
+              const int img0 = mt / per_img;
+              const int rr = mt - img0 * per_img;
+              const int rows_img = g.tw * g.th;
+              const int sub = (g.nb > 1) ? rr_ / rows_img : 0;
+              const int rloc = rr_ - sub * rows_img;
+              const int img = img0 * g.nb + sub;
+              const int ty = rloc / g.tw, tx = rloc - ty * g.tw;
+              const int oy = (rr / g.tiles_x) * g.th + ty;
+              const int ox = (rr % g.tiles_x) * g.tw_valid + tx;
+              valid2 = (sub < g.nb) && (img < g.batch) && (ty < g.th) && (tx < g.tw_valid) && (oy < g.Ho) && (ox < g.Wo);
+              pix2 = ((long long)img * g.Ho + oy) * g.Wo + ox;
+            }
+            float x[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = 0.f;
+            for (int sidx = 0; sidx < g.ksplit; ++sidx) {
+              const float4* pp = reinterpret_cast<const float4*>(base + (size_t(sidx) * kTileM + rr_) * g.bn + c);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 t = __ldcg(pp + q);
+                x[4 * q] += t.x; x[4 * q + 1] += t.y; x[4 * q + 2] += t.z; x[4 * q + 3] += t.w;
+              }
+            }
+            epi_store16(g, e, x, n0 + c, pix2, valid2);
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+          if (threadIdx.x == 64) {
+            // the last CTA to finish its share resets both counters for the next launch / graph replay
+            if (atomicAdd(cnt + 1, 1) == g.ksplit - 1) { cnt[1] = 0; cnt[0] = 0; __threadfence(); }
+          }
         }
       }
       acc ^= 1;
@@ -739,6 +867,7 @@ static int device_setup() {
 static void pick_tiling(int N, int m_tiles, int num_kb, int bk, uint32_t a_bytes, int bn_max, bool allow_split, bool x3,
                         int* bn_out, int* ksplit_out) {
   static const int cand[] = {256, 192, 128, 96, 64, 48, 32, 16};
+  static const bool few_ctas = getenv("B2P_FEW_CTAS") != nullptr;
   const int n16 = (N + 15) / 16 * 16;
   double best_cost = -1;
   int best = 16, best_ks = 1;
@@ -758,7 +887,7 @@ static void pick_tiling(int N, int m_tiles, int num_kb, int bk, uint32_t a_bytes
     const double t_kb = t_mma > t_fill ? t_mma : t_fill;
     int max_ks = 1;
     if (allow_split && tiles * 2 <= g_num_sms && tiles * 2 <= kMaxCounterTiles) {
-      max_ks = int(g_num_sms / tiles);          // every (tile, slice) item must own a resident CTA (the kernel spins)
+      max_ks = int(g_num_sms / tiles);          // one wave of (tile, slice) items (a performance choice: nothing spins)
       if (max_ks > num_kb / 2) max_ks = num_kb / 2;
       if (max_ks > 32) max_ks = 32;
       if (max_ks < 1) max_ks = 1;
@@ -771,9 +900,19 @@ static void pick_tiling(int N, int m_tiles, int num_kb, int bk, uint32_t a_bytes
       const long items = tiles * ks;
       const long waves = (items + g_num_sms - 1) / g_num_sms;
       // split-K overhead: park one fp32 partial tile + read one tile's worth back (distributed reduce) at ~100 GB/s/SM
-      const double t_split = ks > 1 ? 2.0 + 2.0 * (128.0 * c * 4.0 / 100000.0) : 0.0;
-      const double per_item = 2.5 + kb_per * t_kb + 0.012 * c + t_split;
-      const double cost = waves * per_item;
+      double t_split = ks > 1 ? 2.0 + 2.0 * (128.0 * c * 4.0 / 100000.0) : 0.0;
+      double t_kb_ = t_kb;
+      double occupancy_penalty = 0.0;
+      if (few_ctas && waves == 1) {
+        // B2P_FEW_CTAS (experiment, profiles/r2_notes.md 2): measured constants for single-wave launches -- split-K's park /
+        // arrive / reduce costs ~6 us, a CTA of a sparse grid fills at ~100 GB/s -- plus a charge per occupied SM, so that
+        // equal-latency tilings resolve to the one that leaves more SMs to the other streams of the pipelined parser
+        if (ks > 1) t_split = 5.0 + double(ks) * (128.0 * c * 4.0 / 100000.0);
+        if (items < 128) t_kb_ = t_mma > t_fill * 0.7 ? t_mma : t_fill * 0.7;
+        occupancy_penalty = 0.04 * double(items);
+      }
+      const double per_item = 2.5 + kb_per * t_kb_ + 0.012 * c + t_split;
+      const double cost = waves * per_item + occupancy_penalty;
       if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = c; best_ks = ks; }
     }
   }
@@ -922,6 +1061,8 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
   g.sep = (halo || bres) ? 1 : 0;
   g.taps = halo ? 9 : 1;
   g.bn = bn;
+  static const bool sk_last = getenv("B2P_SPLITK_LAST") != nullptr;
+  g.sk_last = sk_last ? 1 : 0;
   g.ksplit = ksplit;
   g.kb_per = (g.num_kb + ksplit - 1) / ksplit;
   g.ws = slot >= 0 ? g_ws[slot] : nullptr;
@@ -938,6 +1079,9 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
     cuuint32_t box[2] = {cuuint32_t(bk), cuuint32_t(bn)};
     if (int e = encode(&tmB, d.bf16, 2, d.B, dims, str, box, bk)) return e;
   }
+  g.d_ksplit = FastDiv::make(g.ksplit); g.d_ntiles = FastDiv::make(g.n_tiles); g.d_mtiles = FastDiv::make(g.m_tiles);
+  g.d_perimg = FastDiv::make(d.mode != 0 ? g.tiles_x * g.tiles_y : 1); g.d_tilesx = FastDiv::make(d.mode != 0 ? g.tiles_x : 1);
+  g.d_cinb = FastDiv::make(d.mode != 0 ? g.cin_blocks : 1);
   const int stage_bytes = g.sep ? int(g.b_slot) : xk * (kASlot + int(g.b_slot));
   int stages, bar_space = 512;
   if (bres) {
