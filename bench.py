@@ -6,7 +6,7 @@
   python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores (oracle port)
 
 A "step" = one pass of the hot path over one batch of B synthetic screenshots per GPU: LANCZOS letterbox ->
-YOLOv9-E -> decode/NMS -> overlap filter (host) -> crop+resize -> Florence-2 greedy caption, results gathered to
+YOLOv9-E -> decode/NMS -> overlap filter (device) -> crop+resize -> Florence-2 greedy caption, results gathered to
 rank 0 with one NCCL gather.  `value` times it with the u8 screenshots already resident in HBM, `e2e` through the
 public API with host buffers (H2D of the screenshots and D2H of boxes/ids inside the timed region).
 Prints ONE JSON line on rank 0.
@@ -346,10 +346,14 @@ def run_b200(args):
     peak_tf, hbm, how = _peaks()
     achieved = plan.flops / (fwd_ms * 1e-3) / 1e12
     traffic = None
-    tp = ROOT / "profiles" / "r1_yolo_b8_traffic.json"
-    if tp.is_file() and B == 8:   # measured once under ncu for this exact forward (batch 8); not re-measured per run
-        tj = json.loads(tp.read_text())
-        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    # measured under ncu for this exact forward (batch 8: dram__bytes_read/write.sum of every launch, caches flushed per
+    # kernel), committed per round; not re-measured per run
+    for tp, key in ((ROOT / "profiles" / "r2_stage_traffic.json", "detect"), (ROOT / "profiles" / "r1_yolo_b8_traffic.json", None)):
+        if tp.is_file() and B == 8 and traffic is None:
+            tj = json.loads(tp.read_text())
+            tj = tj.get(key, {}) if key else tj
+            if "dram_bytes_read" in tj:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
 
     # p50 latency of one screenshot through the public batched entry point (host buffers)
     lat = []
@@ -406,7 +410,7 @@ def run_b200(args):
                                "executed_frac_of_peak": xk * cplan.flops_enc / enc_ms / 1e9 / peak_tf},
                     "decode_step": {"ms": dec_ms, "logical_tflops": cplan.flops_dec / dec_ms / 1e9, "executed_tflops": xk * cplan.flops_dec / dec_ms / 1e9,
                                     "executed_frac_of_peak": xk * cplan.flops_dec / dec_ms / 1e9 / peak_tf,
-                                    "note": "~70 launches per step at M = rows: launch/latency bound, see profiles/r1_gemm_notes.md"}}
+                                    "note": "~70 launches per step at M = rows: dependency-chain bound (~11 us per launch whatever the tiling), see profiles/r2_notes.md"}}
                 log(f"caption stages: encode {enc_ms:.2f} ms, decode step {dec_ms:.3f} ms")
     except Exception as exc:   # noqa: BLE001
         caption_stages = {"error": repr(exc)[:200]}

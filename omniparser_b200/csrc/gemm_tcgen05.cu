@@ -75,6 +75,7 @@ struct GemmArgs {
   const void* res;
   long long ldr;
   int act, vec_ok;
+  int vec32_ok;   // out / residual rows and the lo planes are 32-byte aligned: 256-bit accesses in the epilogue
   int split;   // > 0: fp16 output in the fp16x3 operand layout: hi at column n, lo at column split + n (lo-plane offset)
   int res_lo;  // > 0: the fp16 residual is a hi/lo pair too, lo at column res_lo + n
   // fp16x3 operands: A rows are [hi(K) | lo(K)] (conv: per pixel [hi(Cin) | lo(Cin)]), W rows [hi | lo] likewise.  Each
@@ -131,6 +132,18 @@ __device__ __forceinline__ float act_fn(float x, int act) {
   return x;
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per lane and instruction instead of two
+// 16-byte halves -- the epilogue's lane-per-row pattern touches 32 different lines per instruction, so halving the
+// instruction count halves its LSU / L2 transaction cost.  Addresses must be 32-byte aligned (GemmArgs::vec32_ok).
+__device__ __forceinline__ void st256(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+               "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void ld256(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]),
+               "=r"(v[6]), "=r"(v[7]) : "l"(p));
+}
+
 struct EpiCtx {
   __half* outh; float* outf; const __half* resh; const float* resf;
 };
@@ -154,18 +167,33 @@ __device__ __forceinline__ void epi_store16(const GemmArgs& g, const EpiCtx& e, 
     if (!valid) return;
     if (g.res) {
       if (g.out_f32) {
-        const float4* rp = reinterpret_cast<const float4*>(e.resf + pix * g.ldr + nb);
+        if (g.vec32_ok) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 t = rp[q];
-          x[4 * q] += t.x; x[4 * q + 1] += t.y; x[4 * q + 2] += t.z; x[4 * q + 3] += t.w;
+          for (int q = 0; q < 2; ++q) {
+            uint32_t t[8];
+            ld256(e.resf + pix * g.ldr + nb + 8 * q, t);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[8 * q + k] += __uint_as_float(t[k]);
+          }
+        } else {
+          const float4* rp = reinterpret_cast<const float4*>(e.resf + pix * g.ldr + nb);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 t = rp[q];
+            x[4 * q] += t.x; x[4 * q + 1] += t.y; x[4 * q + 2] += t.z; x[4 * q + 3] += t.w;
+          }
         }
       } else {
-        const uint4* rp = reinterpret_cast<const uint4*>(e.resh + pix * g.ldr + nb);
+        uint4 rr_[2];
+        if (g.vec32_ok) {
+          ld256(e.resh + pix * g.ldr + nb, *reinterpret_cast<uint32_t(*)[8]>(rr_));
+        } else {
+          const uint4* rp = reinterpret_cast<const uint4*>(e.resh + pix * g.ldr + nb);
+          rr_[0] = rp[0]; rr_[1] = rp[1];
+        }
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          const uint4 t = rp[q];
-          const __half2* hp = reinterpret_cast<const __half2*>(&t);
+          const __half2* hp = reinterpret_cast<const __half2*>(&rr_[q]);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const float2 f = __half22float2(hp[k]);
@@ -174,11 +202,15 @@ __device__ __forceinline__ void epi_store16(const GemmArgs& g, const EpiCtx& e, 
           }
         }
         if (g.res_lo) {
-          const uint4* rl = reinterpret_cast<const uint4*>(e.resh + pix * g.ldr + g.res_lo + nb);
+          if (g.vec32_ok) {
+            ld256(e.resh + pix * g.ldr + g.res_lo + nb, *reinterpret_cast<uint32_t(*)[8]>(rr_));
+          } else {
+            const uint4* rl = reinterpret_cast<const uint4*>(e.resh + pix * g.ldr + g.res_lo + nb);
+            rr_[0] = rl[0]; rr_[1] = rl[1];
+          }
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
-            const uint4 t = rl[q];
-            const __half2* hp = reinterpret_cast<const __half2*>(&t);
+            const __half2* hp = reinterpret_cast<const __half2*>(&rr_[q]);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const float2 f = __half22float2(hp[k]);
@@ -190,17 +222,31 @@ __device__ __forceinline__ void epi_store16(const GemmArgs& g, const EpiCtx& e, 
       }
     }
     if (g.out_f32) {
-      float4* op = reinterpret_cast<float4*>(e.outf + pix * g.ldc + nb);
+      if (g.vec32_ok) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) op[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+        for (int q = 0; q < 2; ++q) {
+          uint32_t t[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) t[k] = __float_as_uint(x[8 * q + k]);
+          st256(e.outf + pix * g.ldc + nb + 8 * q, t);
+        }
+      } else {
+        float4* op = reinterpret_cast<float4*>(e.outf + pix * g.ldc + nb);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) op[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+      }
     } else {
       uint4 pk[2];
       __half2* hp = reinterpret_cast<__half2*>(pk);
 #pragma unroll
       for (int k = 0; k < 8; ++k) hp[k] = __floats2half2_rn(x[2 * k], x[2 * k + 1]);
-      uint4* op = reinterpret_cast<uint4*>(e.outh + pix * g.ldc + nb);
-      op[0] = pk[0];
-      op[1] = pk[1];
+      if (g.vec32_ok) {
+        st256(e.outh + pix * g.ldc + nb, *reinterpret_cast<uint32_t(*)[8]>(pk));
+      } else {
+        uint4* op = reinterpret_cast<uint4*>(e.outh + pix * g.ldc + nb);
+        op[0] = pk[0];
+        op[1] = pk[1];
+      }
       if (g.split) {
         uint4 lo[2];
         __half2* lp = reinterpret_cast<__half2*>(lo);
@@ -209,9 +255,13 @@ __device__ __forceinline__ void epi_store16(const GemmArgs& g, const EpiCtx& e, 
           const float2 hf = __half22float2(hp[k]);
           lp[k] = __floats2half2_rn(x[2 * k] - hf.x, x[2 * k + 1] - hf.y);
         }
-        uint4* o3 = reinterpret_cast<uint4*>(e.outh + pix * g.ldc + g.split + nb);
-        o3[0] = lo[0];
-        o3[1] = lo[1];
+        if (g.vec32_ok) {
+          st256(e.outh + pix * g.ldc + g.split + nb, *reinterpret_cast<uint32_t(*)[8]>(lo));
+        } else {
+          uint4* o3 = reinterpret_cast<uint4*>(e.outh + pix * g.ldc + g.split + nb);
+          o3[0] = lo[0];
+          o3[1] = lo[1];
+        }
       }
     }
   } else {
@@ -571,38 +621,26 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       if constexpr (kTrace) { if (item == blockIdx.x && threadIdx.x == 64) trace_stamp<kTrace>(g, kTrFirstEpiStart); }
       const uint32_t t_row = tmem_base + (uint32_t(grp * 32) << 16) + uint32_t(acc * 256);
       if (e_ksplit == 1) {
-        // software-pipelined: the TMEM load of this warp's next 16-column chunk is in flight while the current chunk runs its
-        // bias / activation / residual / store chain, and the accumulator goes back to the MMA warp as soon as the LAST chunk
-        // sits in registers (before it is processed).  r2_notes.md: N >= 128 SiLU / GELU tiles were epilogue-bound (5-6 us per
-        // 128x256 tile against ~2 us of MUFU work): every chunk paid the tcgen05.ld latency serially.
-        int c = cq * 16;
-        if (c < e_bn) {
-          uint32_t va[16], vb[16];
-          tmem_ld16(t_row + c, va);
-          tmem_ld_wait(va);
-          while (true) {
-            const int cn = c + 64;
-            const bool more = cn < e_bn;
-            if (more) {
-              tmem_ld16(t_row + cn, vb);
-            } else {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-            }
-            if (n0 + c < g.N) {   // warp-uniform
-              float x[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(va[j]);
-              epi_store16(g, e, x, n0 + c, pix, valid);
-            }
-            if (!more) break;
-            tmem_ld_wait(vb);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) va[j] = vb[j];
-            c = cn;
+        // the accumulator goes back to the MMA warp as soon as this warp's LAST 16-column chunk sits in registers (before it
+        // is processed).  (A software-pipelined variant with two register buffers measured no faster and spilled.)
+        bool released = false;
+        for (int c = cq * 16; c < e_bn; c += 64) {
+          uint32_t v[16];
+          tmem_ld16(t_row + c, v);
+          tmem_ld_wait(v);
+          if (c + 64 >= e_bn) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+            released = true;
           }
-        } else {
+          if (n0 + c >= g.N) continue;   // warp-uniform
+          float x[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]);
+          epi_store16(g, e, x, n0 + c, pix, valid);
+        }
+        if (!released) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
@@ -867,7 +905,10 @@ static int device_setup() {
 static void pick_tiling(int N, int m_tiles, int num_kb, int bk, uint32_t a_bytes, int bn_max, bool allow_split, bool x3,
                         int* bn_out, int* ksplit_out) {
   static const int cand[] = {256, 192, 128, 96, 64, 48, 32, 16};
-  static const bool few_ctas = getenv("B2P_FEW_CTAS") != nullptr;
+  // single-wave launches: measured constants + a charge per occupied SM (B2P_DENSE_GRIDS=1 restores the round-1 model that
+  // spreads every launch over as many SMs as it can; B2P_CTA_PENALTY = microseconds charged per CTA, default 0.04)
+  static const bool few_ctas = getenv("B2P_DENSE_GRIDS") == nullptr;
+  static const double cta_penalty = getenv("B2P_CTA_PENALTY") ? atof(getenv("B2P_CTA_PENALTY")) : 0.04;
   const int n16 = (N + 15) / 16 * 16;
   double best_cost = -1;
   int best = 16, best_ks = 1;
@@ -904,12 +945,12 @@ static void pick_tiling(int N, int m_tiles, int num_kb, int bk, uint32_t a_bytes
       double t_kb_ = t_kb;
       double occupancy_penalty = 0.0;
       if (few_ctas && waves == 1) {
-        // B2P_FEW_CTAS (experiment, profiles/r2_notes.md 2): measured constants for single-wave launches -- split-K's park /
-        // arrive / reduce costs ~6 us, a CTA of a sparse grid fills at ~100 GB/s -- plus a charge per occupied SM, so that
-        // equal-latency tilings resolve to the one that leaves more SMs to the other streams of the pipelined parser
+        // measured (profiles/r2_notes.md 2): a single-wave launch takes ~11 us whatever its tiling (split-K's park / arrive /
+        // reduce costs ~6 us, a CTA of a sparse grid fills at ~100 GB/s), so equal-latency tilings are resolved by a charge per
+        // occupied SM: the sparser grid leaves SMs to the other streams of the pipelined parser (bench: 19.2 -> 18.1 ms/step)
         if (ks > 1) t_split = 5.0 + double(ks) * (128.0 * c * 4.0 / 100000.0);
         if (items < 128) t_kb_ = t_mma > t_fill * 0.7 ? t_mma : t_fill * 0.7;
-        occupancy_penalty = 0.04 * double(items);
+        occupancy_penalty = cta_penalty * double(items);
       }
       const double per_item = 2.5 + kb_per * t_kb_ + 0.012 * c + t_split;
       const double cost = waves * per_item + occupancy_penalty;
@@ -1112,10 +1153,18 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
   g.vec_ok = ((reinterpret_cast<uintptr_t>(d.out) & 15) == 0) && ((d.ldc * esz) % 16 == 0) &&
              (!d.res || (((reinterpret_cast<uintptr_t>(d.res) & 15) == 0) && ((d.ldr * esz) % 16 == 0))) &&
              (!d.bias || ((reinterpret_cast<uintptr_t>(d.bias) & 15) == 0));
+  {
+    static const bool no_v256 = getenv("B2P_NO_V256") != nullptr;
+    auto a32 = [](const void* p, long long ld, int es) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0 && (ld * es) % 32 == 0; };
+    g.vec32_ok = !no_v256 && g.vec_ok && a32(d.out, d.ldc, esz) && (!d.res || a32(d.res, d.ldr, esz)) &&
+                 (g.split * esz) % 32 == 0 && (g.res_lo * esz) % 32 == 0;
+  }
   static const bool dbg = getenv("B2P_DEBUG") != nullptr;
   static const bool no_pdl = getenv("B2P_NO_PDL") != nullptr;
   const int total = g.m_tiles * g.n_tiles * g.ksplit;
-  const int grid = total < g_num_sms ? total : g_num_sms;
+  static const int max_grid = getenv("B2P_MAX_GRID") ? atoi(getenv("B2P_MAX_GRID")) : 0;   // experiment: leave SMs to other streams
+  int grid = total < g_num_sms ? total : g_num_sms;
+  if (max_grid > 0 && grid > max_grid && ksplit == 1) grid = max_grid;
   if (grid <= 0) return 0;
   if (dbg)
     fprintf(stderr, "b2p_gemm mode=%d M=%d N=%d Ktot=%d bk=%d bn=%d tw=%d th=%d m_tiles=%d n_tiles=%d stages=%d grid=%d act=%d f32=%d res=%d ksplit=%d x3=%d bres=%d stagesA=%d\n",

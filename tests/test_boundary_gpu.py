@@ -141,15 +141,16 @@ def _overlay_pixels(png_b64, size):
     return np.asarray(im)
 
 
-def _overlay_close(png_b64, img, ref_elems, sha, cfg, size):
+def _overlay_close(png_b64, img, ref_elems, sha, cfg, size, events=0):
     """The reference's overlay is rebuilt from ITS boxes (sha256 pinned by the golden) and compared pixel by pixel: a
-    sub-millipixel coordinate difference may move one rectangle edge by a pixel, nothing more."""
+    sub-millipixel coordinate difference may move one rectangle edge by a pixel, nothing more; every tie-class order event
+    (two elements swapped, counted by _same_elements) renumbers two labels, which may also move them."""
     from omniparser_b200 import som_overlay as SO
     _, _, ref_frame = SO.som_outputs(img, [e["bbox"] for e in ref_elems], True, **cfg)
     assert hashlib.sha256(ref_frame.tobytes()).hexdigest() == sha
     got = _overlay_pixels(png_b64, size)
     frac = float((got != ref_frame).any(-1).mean())
-    assert frac <= 2e-3, f"{100 * frac:.3f} % of the overlay pixels differ"
+    assert frac <= 2e-3 * (1 + events), f"{100 * frac:.3f} % of the overlay pixels differ ({events} events)"
     return frac
 
 
@@ -166,8 +167,8 @@ def test_facade_reproduces_the_reference_facade_golden(artefacts):
     ev = _same_elements(parsed, g["parsed_content_list"], (w, h))
     r = max(w, h) / 3200                                              # ref:util/omniparser.py:21-27
     cfg = dict(text_scale=0.8 * r, text_thickness=max(int(2 * r), 1), text_padding=max(int(3 * r), 1), thickness=max(int(3 * r), 1))
-    frac = _overlay_close(png, img, g["parsed_content_list"], g["overlay_sha256"], cfg, (w, h))
-    print(f"facade: {len(parsed)} elements, {ev} integer-boundary events, {100 * frac:.4f} % overlay pixels differ")
+    frac = _overlay_close(png, img, g["parsed_content_list"], g["overlay_sha256"], cfg, (w, h), events=ev)
+    print(f"facade: {len(parsed)} elements, {ev} integer-boundary / order events, {100 * frac:.4f} % overlay pixels differ")
 
 
 @pytest.mark.parametrize("name", ["synth_seed0", "synth_seed3_odd", "synth_seed5_3240x2160"])
@@ -183,8 +184,8 @@ def test_get_som_labeled_img_reproduces_reference_golden_end_to_end(loaded, name
                                              iou_threshold=g["iou_threshold"], scale_img=False, batch_size=128)
     ev = _same_elements(elems, g["parsed_content_list"], (w, h), golden=g)
     dc = _label_coords_close(coords, g["label_coordinates"], (w, h))
-    frac = _overlay_close(png, np.asarray(img), g["parsed_content_list"], g["overlay_sha256"], dict(text_scale=0.4, text_padding=5), (w, h))
-    print(f"{name}: {len(elems)} elements, {ev} integer-boundary events, label coords within {dc:.1e} px, {100 * frac:.4f} % overlay pixels differ")
+    frac = _overlay_close(png, np.asarray(img), g["parsed_content_list"], g["overlay_sha256"], dict(text_scale=0.4, text_padding=5), (w, h), events=ev)
+    print(f"{name}: {len(elems)} elements, {ev} integer-boundary / order events, label coords within {dc:.1e} px, {100 * frac:.4f} % overlay pixels differ")
 
 
 @pytest.mark.parametrize("name", ["real_demo_image", "real_omni3", "real_excel_rgba", "real_header_bar_thin"])
@@ -204,8 +205,8 @@ def test_real_images_with_eval_call_site_parameters(loaded, name):
     ev = _same_elements(elems, g["parsed_content_list"], (w, h), golden=g)
     dc = _label_coords_close(coords, g["label_coordinates"], (w, h))
     img = np.asarray(Image.open(path).convert("RGB"))
-    frac = _overlay_close(png, img, g["parsed_content_list"], g["overlay_sha256"], cfg, (w, h))
-    print(f"{name}: {len(elems)} elements, {ev} integer-boundary events, label coords within {dc:.1e} px, {100 * frac:.4f} % overlay pixels differ")
+    frac = _overlay_close(png, img, g["parsed_content_list"], g["overlay_sha256"], cfg, (w, h), events=ev)
+    print(f"{name}: {len(elems)} elements, {ev} integer-boundary / order events, label coords within {dc:.1e} px, {100 * frac:.4f} % overlay pixels differ")
 
 
 def test_batching_server_equals_single_requests(loaded):
