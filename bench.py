@@ -504,7 +504,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--caption-lanes", type=int, default=2, help="caption batches in flight (own stream + plan each)")
+    ap.add_argument("--caption-lanes", type=int, default=3, help="caption batches in flight (own stream + plan each; 3 measured +3.4 % over 2 on B200, round 2)")
     ap.add_argument("--caption-group", type=int, default=1,
                     help="opt-in: caption the crops of this many consecutive steps in one Florence-2 pass (PipelinedParser caption_group)")
     ap.add_argument("--warmup", type=int, default=3)

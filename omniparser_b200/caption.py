@@ -158,7 +158,7 @@ class B200Florence2Model:
             plan.reset_decode(n)
             steps = 0
             while steps < plan.T:
-                plan.decode_step()
+                plan.decode_step(forced=plan.step_is_forced(steps))
                 steps += 1
                 if steps % sync_every == 0 and steps < plan.T and plan.unfinished() == 0:
                     break

@@ -49,6 +49,16 @@ struct ConvGemm {
 int gemm_launch(const ConvGemm& d, cudaStream_t st);
 int trace_read(unsigned long long* stamps, int* meta, int max_launches);   // B2P_TRACE=1 debugging aid
 
+// Round-2 SIMT kernels of the caption encoder (florence_simt.cu).  Return 0 = launched, 1 = shape not covered (the caller
+// falls back to the first-version kernel), < 0 = error (message recorded).
+int dwconv_ln_v3_launch(const float* x, int B, int H, int W, int C, const float* w9c, const float* bias, float* y,
+                        const float* gamma, const float* beta, float eps, void* out16, int split, cudaStream_t st);
+int window_attn_crop_launch(const float* qkv, const float* qkv_bias, int B, int H, int W, int C, int heads, int win, void* out,
+                            int split, cudaStream_t st);
+int channel_attn_v3_launch(const float* qkv, int B, int N, int C, int groups, void* out, int split, cudaStream_t st);
+int mha_short_launch(const float* q, long long ldq, const float* k, const float* v, long long ldk, int B, int Lq, int Lk, int heads,
+                     void* out, long long ldo, int split, cudaStream_t st);
+
 // Programmatic dependent launch for the small SIMT kernels: launched with the stream-serialization attribute they may
 // be scheduled while the preceding (persistent, early-triggering) GEMM drains; each such kernel calls pdl_wait() before
 // touching global memory.  They never trigger their own dependents early (their grids are not guaranteed resident).

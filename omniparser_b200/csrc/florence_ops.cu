@@ -677,6 +677,10 @@ int b2p_dwconv_ln(const float* x, int B, int H, int W, int C, const float* w9c, 
                   const float* gamma, const float* beta, float eps, void* out16, int split, cudaStream_t st) {
   if (C % 4 || C > 1024) return set_error("dwconv_ln: C must be a multiple of 4 and <= 1024");
   const long long T = (long long)B * H * W;
+  if (split & 4) {   // round-2 strip kernel (florence_simt.cu); shapes it does not cover fall through
+    const int r = dwconv_ln_v3_launch(x, B, H, W, C, w9c, bias, y, gamma, beta, eps, out16, split & 1, st);
+    if (r <= 0) return r;
+  }
   const size_t tile_bytes = size_t(H) * W * C * sizeof(float);
   if ((split & 2) && tile_bytes <= 200 * 1024 && B > 0) {   // opt-in tiled variant (see dwconv_ln_tile_kernel)
     static std::atomic<bool> attr{false};
@@ -707,6 +711,11 @@ int b2p_dwconv3x3_res(const float* x, int B, int H, int W, int C, const float* w
 int b2p_window_attn(const float* qkv, const float* qkv_bias, int B, int H, int W, int C, int heads, int win, void* out,
                     int split, cudaStream_t st) {
   if (C / heads != 32) return set_error("window_attn: head_dim must be 32");
+  if (split & 4) {   // one-window maps: CTA per (image, head group), florence_simt.cu
+    if (int e = bind_device()) return e;
+    const int r = window_attn_crop_launch(qkv, qkv_bias, B, H, W, C, heads, win, out, split & 1, st);
+    if (r <= 0) return r;
+  }
   const int nw = ((W + win - 1) / win) * ((H + win - 1) / win);
   // K/V staging sized by the REAL tokens of a window: the 4x4 / 2x2 maps of the 64x64-crop mode need 4 KB / 1 KB, not the
   // 36.9 KB of a full 12x12 window (which capped those launches at 6 one-warp CTAs per SM: ~100 us each, r1 step table)
@@ -722,13 +731,17 @@ int b2p_window_attn(const float* qkv, const float* qkv_bias, int B, int H, int W
   // one thread per query of the window: small maps (4x4, 8x8 in the 64x64-crop mode) get small CTAs so more of them fit per SM
   const int nq = kv_cap;
   const int threads = nq >= 160 ? 160 : ((nq + 31) / 32) * 32;
-  launch_pdl(window_attn_kernel<32>, dim3(B * nw * heads), dim3(threads), smem, st, qkv, qkv_bias, B, H, W, C, heads, win, (__half*)out, split ? C : 0, kv_cap);
+  launch_pdl(window_attn_kernel<32>, dim3(B * nw * heads), dim3(threads), smem, st, qkv, qkv_bias, B, H, W, C, heads, win, (__half*)out, (split & 1) ? C : 0, kv_cap);
   B2P_CHECK_LAUNCH();
   return 0;
 }
 
 int b2p_channel_attn(const float* qkv, int B, int N, int C, int groups, void* out, int split, cudaStream_t st) {
   if (C / groups != 32) return set_error("channel_attn: channels per group must be 32");
+  if (split & 4) {   // register-tiled kernel, florence_simt.cu
+    const int r = channel_attn_v3_launch(qkv, B, N, C, groups, out, split & 1, st);
+    if (r <= 0) return r;
+  }
   if ((split & 2) && N <= 16 && B > 0) {   // opt-in small-N variant (see channel_attn_small_kernel)
     launch_pdl(channel_attn_small_kernel, dim3((B * groups + 3) / 4), dim3(128), 0, st, qkv, B, N, C, groups, (__half*)out, (split & 1) ? C : 0);
     B2P_CHECK_LAUNCH();
@@ -742,9 +755,13 @@ int b2p_channel_attn(const float* qkv, int B, int N, int C, int groups, void* ou
 // Encoder self-attention / decoder cross-attention: explicit K, V.
 int b2p_mha(const float* q, long long ldq, const float* k, const float* v, long long ldk, int B, int Lq, int Lk, int heads,
             void* out, long long ldo, int split, cudaStream_t st) {
+  if (split & 4) {   // short sequences: warp per (batch, head) with K / V in registers, florence_simt.cu
+    const int r = mha_short_launch(q, ldq, k, v, ldk, B, Lq, Lk, heads, out, ldo, split & 1, st);
+    if (r <= 0) return r;
+  }
   MhaArgs a{};
   a.q = q; a.ldq = ldq; a.k = k; a.v = v; a.ldk = ldk;
-  a.B = B; a.Lq = Lq; a.Lk = Lk; a.heads = heads; a.out = (__half*)out; a.ldo = ldo; a.split = split ? heads * 64 : 0;
+  a.B = B; a.Lq = Lq; a.Lk = Lk; a.heads = heads; a.out = (__half*)out; a.ldo = ldo; a.split = (split & 1) ? heads * 64 : 0;
   const int total = B * heads * Lq;
   // (a thread-per-query variant measured 2.3x slower here: its per-thread 256-B rows are uncoalesced,
   // profiles/r1_step_table_v3.txt, and was removed)

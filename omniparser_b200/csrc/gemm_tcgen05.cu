@@ -115,21 +115,38 @@ __device__ __forceinline__ float fast_rcp(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float silu_fn(float x) {
+  return x * fast_rcp(1.0f + fast_ex2(x * -1.4426950408889634f));   // SiLU: 2 MUFU + 3 FP32, ~2 ulp
+}
+// exact (erf) GELU, Florence-2 parity: erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7) on MUFU rcp/ex2 instead
+// of the ~25-instruction libdevice erff: the GELU epilogues were instruction-bound
+__device__ __forceinline__ float gelu_fn(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * fast_ex2(z * z * -1.4426950408889634f);   // erf(|x|/sqrt2)
+  return 0.5f * x + 0.5f * fabsf(x) * e;                                      // 0.5 x (1 + sign(x) erf)
+}
 __device__ __forceinline__ float act_fn(float x, int act) {
-  if (act == 1) return x * fast_rcp(1.0f + fast_ex2(x * -1.4426950408889634f));   // SiLU: 2 MUFU + 3 FP32, ~2 ulp
-  if (act == 2) {
-    // exact (erf) GELU, Florence-2 parity: erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7) on MUFU rcp/ex2 instead
-    // of the ~25-instruction libdevice erff: the GELU epilogues were instruction-bound
-    const float z = fabsf(x) * 0.70710678118654752f;
-    const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    const float e = 1.0f - p * t * fast_ex2(z * z * -1.4426950408889634f);   // erf(|x|/sqrt2)
-    return 0.5f * x + 0.5f * fabsf(x) * e;                                      // 0.5 x (1 + sign(x) erf)
-  }
+  if (act == 1) return silu_fn(x);
+  if (act == 2) return gelu_fn(x);
   return x;
+}
+// Activation of 16 accumulator columns.  The switch on the (runtime) activation code sits OUTSIDE the element loop: with
+// act_fn(x[j], act) inside it the compiler kept one basic block per element (uniform branch, then the dependent
+// FMUL -> MUFU.EX2 -> FADD -> MUFU.RCP -> FMUL chain), so the 16 chains ran back to back at full MUFU latency instead of
+// interleaved -- the SiLU / GELU epilogues measured ~2.9x their MUFU-throughput bound (profiles/r2_notes.md 6).
+__device__ __forceinline__ void act16(float (&x)[16], int act) {
+  if (act == 1) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) x[j] = silu_fn(x[j]);
+  } else if (act == 2) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) x[j] = gelu_fn(x[j]);
+  }
 }
 
 // 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per lane and instruction instead of two
@@ -160,10 +177,7 @@ __device__ __forceinline__ void epi_store16(const GemmArgs& g, const EpiCtx& e, 
         x[4 * q + 0] += b.x; x[4 * q + 1] += b.y; x[4 * q + 2] += b.z; x[4 * q + 3] += b.w;
       }
     }
-    if (g.act) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) x[j] = act_fn(x[j], g.act);
-    }
+    act16(x, g.act);
     if (!valid) return;
     if (g.res) {
       if (g.out_f32) {

@@ -179,6 +179,9 @@ class FlorencePlan:
         # (tests/test_ops_gpu.py, validated on the B200 in round 2); B2P_NO_DWCONV_TILE / B2P_NO_CHATTN_SMALL select the old ones
         self.dw_tile = not os.environ.get("B2P_NO_DWCONV_TILE")
         self.ca_small = not os.environ.get("B2P_NO_CHATTN_SMALL")
+        # round-2 SIMT kernels (csrc/florence_simt.cu): strip dwconv+LN, per-image window attention, register-tiled channel
+        # attention, warp-per-head short attention; B2P_NO_SIMT_V3=1 selects the first versions (the checkers)
+        self.v3 = not os.environ.get("B2P_NO_SIMT_V3")
         self.warmed = False
         import threading
         self.lock = threading.Lock()
@@ -278,22 +281,22 @@ class FlorencePlan:
                     x1 = self._e(T, C)
                     h = self._act(T, C)
                     ops_.append(lambda x=x, x1=x1, h=h, e=e, H=H, C=C: ops.dwconv_ln(x, K, H, H, C, e["dw1_w"], e["dw1_b"], x1,
-                                                                                 e["n1"].g, e["n1"].b, h, split=x3, tile=self.dw_tile))
+                                                                                 e["n1"].g, e["n1"].b, h, split=x3, tile=self.dw_tile, v3=self.v3))
                     qkv = self._e(T, 3 * C)
                     self._gemm(ops_, h, e["qkv"], qkv)
                     a = self._act(T, C)
                     if kind == "spatial_block":
                         hd = w.heads[s]
-                        ops_.append(lambda qkv=qkv, a=a, e=e, H=H, C=C, hd=hd: ops.window_attn(qkv, e["qkv"].b, K, H, H, C, hd, a, split=x3))
+                        ops_.append(lambda qkv=qkv, a=a, e=e, H=H, C=C, hd=hd: ops.window_attn(qkv, e["qkv"].b, K, H, H, C, hd, a, split=x3, v3=self.v3))
                     else:
                         gr = w.groups[s]
-                        ops_.append(lambda qkv=qkv, a=a, H=H, C=C, gr=gr: ops.channel_attn(qkv, K, H * H, C, gr, a, split=x3, small=self.ca_small))
+                        ops_.append(lambda qkv=qkv, a=a, H=H, C=C, gr=gr: ops.channel_attn(qkv, K, H * H, C, gr, a, split=x3, small=self.ca_small, v3=self.v3))
                     x2 = self._e(T, C)
                     self._gemm(ops_, a, e["proj"], x2, res=x1)
                     x3_ = self._e(T, C)
                     h2 = self._act(T, C)
                     ops_.append(lambda x2=x2, x3_=x3_, h2=h2, e=e, H=H, C=C: ops.dwconv_ln(x2, K, H, H, C, e["dw2_w"], e["dw2_b"], x3_,
-                                                                                      e["n2"].g, e["n2"].b, h2, split=x3, tile=self.dw_tile))
+                                                                                      e["n2"].g, e["n2"].b, h2, split=x3, tile=self.dw_tile, v3=self.v3))
                     f = self._act(T, 4 * C)
                     self._gemm(ops_, h2, e["fc1"], f, act=ACT_GELU, split=x3)
                     x4 = self._e(T, C)
@@ -321,7 +324,7 @@ class FlorencePlan:
             qkv = self._e(TE, 3 * D)
             self._gemm(ops_, h, lay["qkv"], qkv)
             a = self._act(TE, D)
-            ops_.append(lambda qkv=qkv, a=a: ops.mha(qkv, 3 * D, qkv[:, D:], qkv[:, 2 * D:], 3 * D, K, L, L, self.HEADS, a, a.stride(0), split=x3))
+            ops_.append(lambda qkv=qkv, a=a: ops.mha(qkv, 3 * D, qkv[:, D:], qkv[:, 2 * D:], 3 * D, K, L, L, self.HEADS, a, a.stride(0), split=x3, v3=self.v3))
             y = self._e(TE, D)
             self._gemm(ops_, a, lay["o"], y, res=x)
             x = self._e(TE, D); h = self._act(TE, D)
@@ -407,8 +410,13 @@ class FlorencePlan:
                                                  g.get("no_repeat_ngram_size", 0) or 0, -1 if fb is None else fb,
                                                  -1 if fe is None else fe, g["eos_token_id"], g["pad_token_id"], self.max_len,
                                                  dump, n_unf)
-        return dict(idx=idx, r0=r0, r1=r1, ops=ops_, pick=pick, step=step, n_unf=n_unf, graph=None,
-                    stream=torch.cuda.Stream(device=self.dev), full=ops_ + [lambda: pick(None), lambda: ops.step_advance(step)])
+        # Steps whose token is forced by the generation config (forced BOS at length 1, forced EOS at the last length:
+        # hf:generation/logits_process.py:1552,1597) never look at the logits: the pick kernel writes the forced id without
+        # reading them, so those steps replay a graph WITHOUT the LM head (51290 x 768, the largest GEMM of the step).  The
+        # decoder layers still run: the KV cache of the step is needed by the following steps.
+        return dict(idx=idx, r0=r0, r1=r1, ops=ops_, pick=pick, step=step, n_unf=n_unf, graph=None, graph_forced=None,
+                    stream=torch.cuda.Stream(device=self.dev), full=ops_ + [lambda: pick(None), lambda: ops.step_advance(step)],
+                    full_forced=ops_[:-1] + [lambda: pick(None), lambda: ops.step_advance(step)])
 
     # ------------------------------------------------------------------ running
     def _run(self, lst, holder, key, tag, replay_after_capture=True):
@@ -453,10 +461,12 @@ class FlorencePlan:
 
     def _warm_decode(self):
         """Capture the decode-step graph(s) on scratch state (one eager step + capture), before any real decoding."""
-        if not self.use_graph or os.environ.get("B2P_EAGER_FIRST") or all(pt["graph"] is not None for pt in self.parts):
+        if not self.use_graph or os.environ.get("B2P_EAGER_FIRST") or all(pt["graph"] is not None and pt["graph_forced"] is not None for pt in self.parts):
             return
         self._reset_state(self.K)
         self.decode_step(_warm=True)
+        self.join()
+        self.decode_step(_warm=True, forced=True)     # the LM-head-free graph of the forced steps
         self.join()
         torch.cuda.current_stream().synchronize()
 
@@ -490,12 +500,21 @@ class FlorencePlan:
             tot += int(pt["n_unf"].item())
         return tot
 
-    def decode_step(self, dump=None, force_tokens=None, _warm=False):
-        """one token for every row; ``force_tokens`` [K] (teacher forcing) overwrites the picked ids."""
+    def step_is_forced(self, t: int) -> bool:
+        """True if the token of decode step t (0-based) is fixed by the generation config whatever the logits are."""
+        g = self.w.gen
+        if os.environ.get("B2P_NO_FORCED_SKIP"):
+            return False
+        return (t == 0 and g.get("forced_bos_token_id") is not None) or (t == self.T - 1 and g.get("forced_eos_token_id") is not None)
+
+    def decode_step(self, dump=None, force_tokens=None, _warm=False, forced=False):
+        """one token for every row; ``force_tokens`` [K] (teacher forcing) overwrites the picked ids.  forced: this step's
+        token is forced by the generation config (``step_is_forced``): run the step without the LM head."""
         if dump is None and force_tokens is None:
             cur = torch.cuda.current_stream()
+            lst, key = ("full_forced", "graph_forced") if forced else ("full", "graph")
             if len(self.parts) == 1:
-                self._run(self.parts[0]["full"], self.parts[0], "graph", self.tag + "_dec0", replay_after_capture=False)
+                self._run(self.parts[0][lst], self.parts[0], key, self.tag + "_dec0", replay_after_capture=False)
                 return
             if not self._forked:
                 for pt in self.parts:
@@ -503,7 +522,7 @@ class FlorencePlan:
                 self._forked = True
             for pt in self.parts:
                 with torch.cuda.stream(pt["stream"]):
-                    self._run(pt["full"], pt, "graph", f"{self.tag}_dec{pt['idx']}", replay_after_capture=False)
+                    self._run(pt[lst], pt, key, f"{self.tag}_dec{pt['idx']}", replay_after_capture=False)
             return
         for pt in self.parts:   # eager path used by the parity tests
             for f in pt["ops"]:

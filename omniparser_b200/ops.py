@@ -242,24 +242,30 @@ def dwconv3x3_res(x, B, H, W, C, w9c, bias, y):
     _lib.check(_lib.lib().b2p_dwconv3x3_res(_p(x), B, H, W, C, _p(w9c), _p(bias), _p(y), _stream()))
 
 
-def dwconv_ln(x, B, H, W, C, w9c, bias, y, gamma, beta, out16, eps=1e-5, split=False, tile=False):
-    """y = dwconv3x3(x) + bias + x (fp32) and out16 = LayerNorm(y) as the next GEMM operand, one kernel.  tile: opt-in
-    smem-tiled variant (one CTA per image, maps up to 200 KB; not yet validated on hardware)."""
+def dwconv_ln(x, B, H, W, C, w9c, bias, y, gamma, beta, out16, eps=1e-5, split=False, tile=False, v3=False):
+    """y = dwconv3x3(x) + bias + x (fp32) and out16 = LayerNorm(y) as the next GEMM operand, one kernel.  tile: smem-tiled
+    variant (one CTA per image, maps up to 200 KB); v3: strip kernel with register-resident weights (csrc/florence_simt.cu;
+    shapes it does not cover fall back to the tile / per-token kernels)."""
     _lib.check(_lib.lib().b2p_dwconv_ln(_p(x), B, H, W, C, _p(w9c), _p(bias), _p(y), _p(gamma), _p(beta), eps, _p(out16),
-                                        int(bool(split)) | (2 if tile else 0), _stream()))
+                                        int(bool(split)) | (2 if tile else 0) | (4 if v3 else 0), _stream()))
 
 
-def window_attn(qkv32, qkv_bias, B, H, W, C, heads, out, win=12, split=False):
-    _lib.check(_lib.lib().b2p_window_attn(_p(qkv32), _p(qkv_bias), B, H, W, C, heads, win, _p(out), int(split), _stream()))
+def window_attn(qkv32, qkv_bias, B, H, W, C, heads, out, win=12, split=False, v3=False):
+    """v3: maps no larger than one window run one CTA per (image, head group) (csrc/florence_simt.cu)."""
+    _lib.check(_lib.lib().b2p_window_attn(_p(qkv32), _p(qkv_bias), B, H, W, C, heads, win, _p(out),
+                                          int(bool(split)) | (4 if v3 else 0), _stream()))
 
 
-def channel_attn(qkv32, B, N, C, groups, out, split=False, small=False):
-    """small: opt-in warp-per-(batch, group) variant for N <= 16 tokens (not yet validated on hardware)."""
-    _lib.check(_lib.lib().b2p_channel_attn(_p(qkv32), B, N, C, groups, _p(out), int(bool(split)) | (2 if small else 0), _stream()))
+def channel_attn(qkv32, B, N, C, groups, out, split=False, small=False, v3=False):
+    """small: warp-per-(batch, group) variant for N <= 16 tokens; v3: register-tiled kernel (csrc/florence_simt.cu)."""
+    _lib.check(_lib.lib().b2p_channel_attn(_p(qkv32), B, N, C, groups, _p(out),
+                                           int(bool(split)) | (2 if small else 0) | (4 if v3 else 0), _stream()))
 
 
-def mha(q, ldq, k, v, ldk, B, Lq, Lk, heads, out, ldo, split=False):
-    _lib.check(_lib.lib().b2p_mha(_p(q), ldq, _p(k), _p(v), ldk, B, Lq, Lk, heads, _p(out), ldo, int(split), _stream()))
+def mha(q, ldq, k, v, ldk, B, Lq, Lk, heads, out, ldo, split=False, v3=False):
+    """v3: sequences of <= 16 keys run one warp per (batch, head) with K / V in registers (csrc/florence_simt.cu)."""
+    _lib.check(_lib.lib().b2p_mha(_p(q), ldq, _p(k), _p(v), ldk, B, Lq, Lk, heads, _p(out), ldo,
+                                  int(bool(split)) | (4 if v3 else 0), _stream()))
 
 
 def mha_cached(q, ldq, knew, vnew, ldnew, kcache, vcache, tmax, step, B, heads, out, ldo, split=False):

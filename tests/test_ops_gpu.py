@@ -365,6 +365,121 @@ def test_channel_attn_small_variant_bit_identical(B, N, C, split):
     assert torch.equal(outs[0], outs[1])
 
 
+# ---------------------------------------------------------------------------------------------- round-2 SIMT kernels (csrc/florence_simt.cu)
+def _pair_val(o, C, split):
+    """fp16 activation buffer -> float64 values ([hi | lo] pairs summed)."""
+    o = o.double()
+    return o[:, :C] + o[:, C:2 * C] if split else o
+
+
+def _act_close(a, b, C, split):
+    va, vb = _pair_val(a.cpu(), C, split), _pair_val(b.cpu(), C, split)
+    tol = (4e-6 if split else 1.5e-3) * max(1.0, vb.abs().max().item())     # pairs carry ~22 bits, plain fp16 11
+    err = (va - vb).abs().max().item()
+    assert err <= tol, (err, tol)
+
+
+@pytest.mark.parametrize("B,H,C", [(5, 4, 512), (3, 2, 1024), (4, 8, 256), (3, 16, 128), (2, 5, 256), (2, 3, 128)])
+@pytest.mark.parametrize("split", [False, True])
+def test_dwconv_ln_v3_equals_first_version(B, H, C, split):
+    """strip kernel with register-resident weights: y bit-identical (same tap order), LayerNorm output within rounding."""
+    g = torch.Generator().manual_seed(B * H + C + 1)
+    x = torch.randn(B, H, H, C, generator=g).to(DEV)
+    w9c = (torch.randn(9, C, generator=g) * 0.2).to(DEV)
+    bias = torch.randn(C, generator=g).to(DEV)
+    gam = torch.randn(C, generator=g).to(DEV)
+    bet = torch.randn(C, generator=g).to(DEV)
+    outs = []
+    for v3 in (False, True):
+        y = torch.zeros(B * H * H, C, device=DEV)
+        o16 = torch.zeros(B * H * H, (2 if split else 1) * C, dtype=torch.float16, device=DEV)
+        ops.dwconv_ln(x, B, H, H, C, w9c, bias, y, gam, bet, o16, split=split, v3=v3)
+        torch.cuda.synchronize()
+        outs.append((y.cpu(), o16))
+    assert torch.equal(outs[0][0], outs[1][0])
+    _act_close(outs[1][1], outs[0][1], C, split)
+    # and against torch (fp64) directly
+    xr = x.cpu().double().permute(0, 3, 1, 2)
+    yr = F.conv2d(xr, w9c.cpu().double().t().reshape(C, 1, 3, 3), bias.cpu().double(), padding=1, groups=C) + xr
+    yr = yr.permute(0, 2, 3, 1).reshape(-1, C)
+    assert (outs[1][0].double() - yr).abs().max().item() < 1e-5 * max(1.0, yr.abs().max().item())
+    hr = F.layer_norm(yr, (C,), gam.cpu().double(), bet.cpu().double(), 1e-5)
+    tol = (2e-5 if split else 1.5e-3) * max(1.0, hr.abs().max().item())
+    assert (_pair_val(outs[1][1].cpu(), C, split) - hr).abs().max().item() < tol
+
+
+def _window_attn_ref(qkv, bias, B, H, W, C, heads, win=12):
+    """torch fp64 restatement of hf:models/florence2/modeling_florence2.py:346-383 for a map inside ONE window: the map is
+    zero-padded to win x win AFTER the qkv projection's input norm, so padded tokens have qkv = bias."""
+    qkv = qkv.double().reshape(B, H, W, 3 * C)
+    full = bias.double().reshape(1, 1, 1, 3 * C).repeat(B, win, win, 1).clone()
+    full[:, :H, :W] = qkv
+    full = full.reshape(B, win * win, 3, heads, C // heads).permute(2, 0, 3, 1, 4)
+    q, k, v = full[0] * (C // heads) ** -0.5, full[1], full[2]
+    a = torch.softmax(q @ k.transpose(-2, -1), -1) @ v                       # [B, heads, win*win, d]
+    a = a.transpose(1, 2).reshape(B, win, win, C)[:, :H, :W]
+    return a.reshape(B * H * W, C)
+
+
+@pytest.mark.parametrize("B,H,C,heads", [(7, 4, 512, 16), (5, 2, 1024, 32), (3, 8, 256, 8), (2, 3, 128, 4), (2, 12, 128, 4)])
+@pytest.mark.parametrize("split", [False, True])
+def test_window_attn_v3_equals_first_version_and_torch(B, H, C, heads, split):
+    g = torch.Generator().manual_seed(B * H + C + 2)
+    qkv = torch.randn(B * H * H, 3 * C, generator=g).to(DEV)
+    bias = torch.randn(3 * C, generator=g).to(DEV)
+    outs = []
+    for v3 in (False, True):
+        o = torch.zeros(B * H * H, (2 if split else 1) * C, dtype=torch.float16, device=DEV)
+        ops.window_attn(qkv, bias, B, H, H, C, heads, o, split=split, v3=v3)
+        torch.cuda.synchronize()
+        outs.append(o)
+    _act_close(outs[1], outs[0], C, split)
+    ref = _window_attn_ref(qkv.cpu(), bias.cpu(), B, H, H, C, heads)
+    tol = (2e-5 if split else 1.5e-3) * max(1.0, ref.abs().max().item())
+    assert (_pair_val(outs[1].cpu(), C, split) - ref).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("B,N,C", [(7, 16, 512), (5, 4, 1024), (3, 9, 256), (3, 64, 256), (2, 256, 128), (2, 100, 128)])
+@pytest.mark.parametrize("split", [False, True])
+def test_channel_attn_v3_equals_first_version_and_torch(B, N, C, split):
+    g = torch.Generator().manual_seed(B * N + C + 3)
+    qkv = torch.randn(B * N, 3 * C, generator=g).to(DEV)
+    outs = []
+    for v3 in (False, True):
+        o = torch.zeros(B * N, (2 if split else 1) * C, dtype=torch.float16, device=DEV)
+        ops.channel_attn(qkv, B, N, C, C // 32, o, split=split, v3=v3)
+        torch.cuda.synchronize()
+        outs.append(o)
+    _act_close(outs[1], outs[0], C, split)
+    # hf:models/florence2/modeling_florence2.py:228-264
+    t = qkv.cpu().double().reshape(B, N, 3, C // 32, 32).permute(2, 0, 3, 1, 4)
+    q, k, v = t[0] * N ** -0.5, t[1], t[2]
+    a = torch.softmax(q.transpose(-1, -2) @ k, -1)
+    ref = (a @ v.transpose(-1, -2)).transpose(-1, -2).transpose(1, 2).reshape(B * N, C)
+    tol = (2e-5 if split else 1.5e-3) * max(1.0, ref.abs().max().item())
+    assert (_pair_val(outs[1].cpu(), C, split) - ref).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("B,L", [(9, 13), (3, 16), (4, 5), (2, 3)])
+@pytest.mark.parametrize("split", [False, True])
+def test_mha_short_equals_first_version(B, L, split):
+    """warp-per-(batch, head) attention with K / V in registers == the warp-per-query kernel."""
+    D, heads = 768, 12
+    g = torch.Generator().manual_seed(B * L + 4)
+    qkv = torch.randn(B * L, 3 * D, generator=g).to(DEV)
+    outs = []
+    for v3 in (False, True):
+        o = torch.zeros(B * L, (2 if split else 1) * D, dtype=torch.float16, device=DEV)
+        ops.mha(qkv, 3 * D, qkv[:, D:], qkv[:, 2 * D:], 3 * D, B, L, L, heads, o, o.stride(0), split=split, v3=v3)
+        torch.cuda.synchronize()
+        outs.append(o)
+    _act_close(outs[1], outs[0], D, split)
+    t = qkv.cpu().double().reshape(B, L, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    ref = (torch.softmax(t[0] * 0.125 @ t[1].transpose(-1, -2), -1) @ t[2]).transpose(1, 2).reshape(B * L, D)
+    tol = (2e-5 if split else 1.5e-3) * max(1.0, ref.abs().max().item())
+    assert (_pair_val(outs[1].cpu(), D, split) - ref).abs().max().item() < tol
+
+
 # ---------------------------------------------------------------------------------------------- overlap filter (8f-2)
 def _overlap_device(px_list, ocr_px_list, W, H, thr, max_det=300, max_ocr=256):
     """b2p_overlap_filter on a batch: px_list[b] fp32 [n_b,4] pixel boxes (NMS output format), ocr_px_list[b] (texts, int boxes)

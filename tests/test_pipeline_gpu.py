@@ -101,7 +101,7 @@ def test_get_som_labeled_img_api():
     assert texts2 == [e["content"] for e in elems if e["source"] == "box_yolo_content_yolo"]
 
 
-@pytest.mark.parametrize("lanes", [1, 2])
+@pytest.mark.parametrize("lanes", [1, 2, 3])
 def test_pipelined_parser_equals_sequential(lanes):
     """The pipelined schedule (detect of batch i+1 | host list logic of batch i | `lanes` caption batches in flight, each
     on its own stream and plan instance) returns exactly what the one-batch-at-a-time path returns, including the first

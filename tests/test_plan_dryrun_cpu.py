@@ -91,7 +91,7 @@ def _check(name, a):
         assert ldx >= Cc and (o16 is None or ld16 >= (2 if split else 1) * Cc) and (o32 is None or ld32 >= Cc)
     elif name in ("b2p_dwconv_ln", "b2p_channel_attn", "b2p_window_attn", "b2p_mha", "b2p_mha_cached", "b2p_projector_prep"):
         split = a[-2]
-        assert split in (0, 1, 2, 3)
+        assert 0 <= split <= 7            # bit 0: [hi | lo] output, bit 1: round-2 tile/small variants, bit 2: florence_simt.cu kernels
 
 
 @pytest.fixture()
@@ -130,6 +130,12 @@ def test_florence_plan_64(rec, florence, prec):
     assert names[-3:] == ["b2p_gemm", "b2p_greedy_pick", "b2p_step_advance"]
     lm = rec.calls[-3][1]
     assert lm[4] == 51290 and lm[7] % 8 == 0 and lm[7] >= 51290
+    # steps whose token the generation config forces (BOS at length 1, EOS at the last length) run without the LM head
+    assert p.step_is_forced(0) and p.step_is_forced(p.T - 1) and not any(p.step_is_forced(t) for t in range(1, p.T - 1))
+    n0 = len(rec.calls)
+    p.decode_step(forced=True)
+    forced = [c[0] for c in rec.calls[n0:]]
+    assert len(forced) == n_dec - 1 and forced[-3:] == ["b2p_layernorm", "b2p_greedy_pick", "b2p_step_advance"]
 
 
 def test_florence_plan_768(rec, florence):
@@ -150,11 +156,19 @@ def test_kernel_variant_flags_are_forwarded(rec, florence, monkeypatch):
     from omniparser_b200.florence_engine import FlorencePlan, FlorenceWeights
     monkeypatch.delenv("B2P_NO_DWCONV_TILE", raising=False)
     monkeypatch.delenv("B2P_NO_CHATTN_SMALL", raising=False)
+    monkeypatch.delenv("B2P_NO_SIMT_V3", raising=False)
     w = FlorenceWeights(florence.state_dict(), torch.device("cpu"), FS.GEN, "fp16x3")
     p = FlorencePlan(w, 2, 2, FS.PROMPT_IDS, use_graph=False, size=64)
     p.encode()
-    assert {c[1][-2] for c in rec.calls if c[0] == "b2p_dwconv_ln"} == {3}        # default: smem-tiled / warp-per-group variants
-    assert {c[1][-2] for c in rec.calls if c[0] == "b2p_channel_attn"} == {3}
+    assert {c[1][-2] for c in rec.calls if c[0] == "b2p_dwconv_ln"} == {7}        # default: florence_simt.cu kernels, tile / small as fall-backs
+    assert {c[1][-2] for c in rec.calls if c[0] == "b2p_channel_attn"} == {7}
+    assert {c[1][-2] for c in rec.calls if c[0] in ("b2p_window_attn", "b2p_mha")} == {5}
+    rec.calls.clear()
+    monkeypatch.setenv("B2P_NO_SIMT_V3", "1")
+    p = FlorencePlan(w, 2, 2, FS.PROMPT_IDS, use_graph=False, size=64)
+    p.encode()
+    assert {c[1][-2] for c in rec.calls if c[0] in ("b2p_dwconv_ln", "b2p_channel_attn")} == {3}   # smem-tiled / warp-per-group variants
+    assert {c[1][-2] for c in rec.calls if c[0] in ("b2p_window_attn", "b2p_mha")} == {1}
     rec.calls.clear()
     monkeypatch.setenv("B2P_NO_DWCONV_TILE", "1")
     monkeypatch.setenv("B2P_NO_CHATTN_SMALL", "1")
@@ -211,9 +225,10 @@ def test_graph_paths(rec, florence, monkeypatch):
     p = FlorencePlan(w, 2, 3, FS.PROMPT_IDS, use_graph=True, size=64)
     assert p.use_graph and not p.warmed
     p.warm()                                            # encode: eager + capture + replay; decode: eager + capture, then one replay
-    assert p.warmed and p.g_enc is not None and all(pt["graph"] is not None for pt in p.parts)
+    assert p.warmed and p.g_enc is not None and all(pt["graph"] is not None and pt["graph_forced"] is not None for pt in p.parts)
     n_eager = len(rec.calls)
-    assert n_eager == 2 * (232 + 71)                    # every op ran once eagerly and once inside the (stubbed) capture
+    assert n_eager == 2 * (232 + 71 + 70)               # every op ran once eagerly and once inside the (stubbed) capture; the
+                                                        # decode step exists with and without the LM head (forced tokens)
     p.encode(); p.reset_decode(2); p.decode_step(); p.decode_step()
     assert _Graph.replays == 2 + 3 and ops.GRAPH_LAUNCHES[0] - g0 == 2 * 232 + 3 * 71
     assert sum(1 for c in rec.calls[n_eager:] if c[0].startswith("b2p_")) == 0     # steady state: graph replays only
