@@ -105,6 +105,94 @@ __global__ void adown_pool_kernel(const __half* __restrict__ x, long long ldx, i
   }
 }
 
+// Plain fp16 maps (the fast detector mode): the two halves of adown_pool_kernel as separate launches, one item per thread,
+// 32-bit index arithmetic.  The x2 item of the combined kernel walks nine 2x2 windows one after the other (nine dependent
+// L2 round trips, and its register count sets the occupancy of the x1 items); here its 4x4 input patch (16 vector loads) is
+// requested at once.  hs = horizontal pair sums of a patch row; an average is (hs[row] + hs[row + 1]) * 0.25 =
+// ((a + b) + (c + d)) * 0.25: the same association as the combined kernel => identical results.
+__global__ void __launch_bounds__(256) adown_avg_kernel(const __half* __restrict__ x, long long ldx, int B, int H, int W, int C,
+                                                        __half* __restrict__ x1, long long ld1) {
+  pdl_wait();
+  const unsigned c8n = unsigned(C) / 16u;
+  const unsigned n1 = unsigned(B) * H * W * c8n;
+  const unsigned i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= n1) return;
+  const unsigned cv = i % c8n;
+  unsigned p = i / c8n;
+  const unsigned xx = p % unsigned(W); p /= unsigned(W);
+  const unsigned yy = p % unsigned(H);
+  const unsigned b = p / unsigned(H);
+  float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (yy < unsigned(H - 1) && xx < unsigned(W - 1)) {
+    const __half* s = x + (((long long)b * H + yy) * W + xx) * ldx + cv * 8;
+    const uint4 ra = ld8(s), rb = ld8(s + ldx), rc = ld8(s + (long long)W * ldx), rd = ld8(s + (long long)(W + 1) * ldx);
+    float a[8], bq[8], c[8], d[8];
+    unpack8(ra, a); unpack8(rb, bq); unpack8(rc, c); unpack8(rd, d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = ((a[k] + bq[k]) + (c[k] + d[k])) * 0.25f;
+  }
+  st8(x1 + (((long long)b * H + yy) * W + xx) * ld1 + cv * 8, pack8(o));
+}
+
+__global__ void __launch_bounds__(256) adown_max_kernel(const __half* __restrict__ x, long long ldx, int B, int H, int W, int C,
+                                                        __half* __restrict__ x2, long long ld2) {
+  pdl_wait();
+  const unsigned c8n = unsigned(C) / 16u;
+  const int Ho = H / 2, Wo = W / 2;
+  const unsigned n2 = unsigned(B) * Ho * Wo * c8n;
+  const unsigned i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= n2) return;
+  const unsigned cv = i % c8n;
+  unsigned p = i / c8n;
+  const int ox = int(p % unsigned(Wo)); p /= unsigned(Wo);
+  const int oy = int(p % unsigned(Ho));
+  const int b = int(p / unsigned(Ho));
+  uint4 raw[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int yy = 2 * oy - 1 + r;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int xx = 2 * ox - 1 + c;
+      raw[r][c] = (yy >= 0 && yy < H && xx >= 0 && xx < W)
+                      ? ld8(x + (((long long)b * H + yy) * W + xx) * ldx + C / 2 + cv * 8) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  float m[8], hp[3][8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float pr[4][8], hs[3][8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) unpack8(raw[r][c], pr[c]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) hs[c][k] = pr[c][k] + pr[c + 1][k];
+    }
+    if (r > 0) {
+      const int ay = 2 * oy - 2 + r;               // average row: inputs ay, ay + 1
+      if (ay >= 0 && ay < H - 1) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int ax = 2 * ox - 1 + c;
+          if (ax >= 0 && ax < W - 1) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], (hp[c][k] + hs[c][k]) * 0.25f);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) hp[c][k] = hs[c][k];
+    }
+  }
+  st8(x2 + (((long long)b * Ho + oy) * Wo + ox) * ld2 + cv * 8, pack8(m));
+}
+
 // MaxPool2d(k, stride 1, pad k/2) on a channel slice (SPPELAN, k = 5).
 __global__ void maxpool_s1_kernel(const __half* __restrict__ x, long long ldx, int B, int H, int W, int C, int k,
                                   __half* __restrict__ y, long long ldy, long long lox, long long loy) {
@@ -271,6 +359,14 @@ int b2p_adown_pool_x3(const void* x, long long ldx, int B, int H, int W, int C, 
   if ((H & 1) || (W & 1) || (C % 16)) return set_error("adown_pool: H, W must be even and C a multiple of 16");
   if ((lox != 0) != (lo1 != 0) || (lox != 0) != (lo2 != 0) || (lox | lo1 | lo2) % 8) return set_error("adown_pool: lo planes must be all set (8-aligned) or all 0");
   const long long n = (long long)B * H * W * (C / 16) + (long long)B * (H / 2) * (W / 2) * (C / 16);
+  if (lox == 0 && n < (1LL << 31) - 256) {
+    const long long n1 = (long long)B * H * W * (C / 16), n2 = n - n1;
+    launch_pdl(adown_avg_kernel, dim3(unsigned((n1 + 255) / 256)), dim3(256), 0, st, (const __half*)x, ldx, B, H, W, C, (__half*)x1, ld1);
+    B2P_CHECK_LAUNCH();
+    launch_pdl(adown_max_kernel, dim3(unsigned((n2 + 255) / 256)), dim3(256), 0, st, (const __half*)x, ldx, B, H, W, C, (__half*)x2, ld2);
+    B2P_CHECK_LAUNCH();
+    return 0;
+  }
   launch_pdl(adown_pool_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, (const __half*)x, ldx, B, H, W, C, (__half*)x1, ld1, (__half*)x2, ld2,
              lox, lo1, lo2);
   B2P_CHECK_LAUNCH();

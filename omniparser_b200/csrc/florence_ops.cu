@@ -72,6 +72,70 @@ __global__ void layernorm_kernel(const float* __restrict__ x, long long ldx, con
   }
 }
 
+// Split-K reduction + bias + residual + LayerNorm in one pass over the partial tiles a park-only GEMM left in the split-K
+// workspace (gemm_tcgen05.cu, GemmArgs::park): the decoder's out-proj / cross out-proj / fc2 GEMMs (N = 768, M = crops) are
+// split-K launches followed by a LayerNorm; inside the GEMM the slices had to wait for each other and re-read the partials
+// (5.8 of 10.8 us), and the LayerNorm was one more 4 us launch.  One warp per row.  Same arithmetic in the same order as
+// the GEMM epilogue (slices in order, + bias, + residual) and layernorm_kernel => bit-identical results.
+__global__ void splitk_ln_kernel(ParkInfo pk, int M, int N, const float* __restrict__ bias, const float* __restrict__ res, long long ldr,
+                                 const float* __restrict__ g, const float* __restrict__ b, float eps, __half* __restrict__ o16,
+                                 long long ld16, float* __restrict__ o32, long long ld32, int split) {
+  pdl_wait();
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const int mt = row >> 7, r = row & 127;
+  const int C4 = N >> 2;
+  const size_t sl_stride = size_t(128) * pk.bn;     // floats between consecutive k slices of a tile
+  float4 v[8];   // N <= 1024
+  float s = 0.f;
+  int n = 0;
+  for (int c = lane; c < C4; c += 32, ++n) {
+    const int col = 4 * c;
+    const int nt = col / pk.bn, cc = col - nt * pk.bn;
+    const int tile = pk.mt_fast ? nt * pk.m_tiles + mt : mt * pk.n_tiles + nt;
+    const float* p = pk.ws + (size_t(tile) * pk.ksplit * 128 + r) * pk.bn + cc;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    int sidx = 0;
+    for (; sidx + 2 <= pk.ksplit; sidx += 2) {       // two slices in flight; adds in slice order
+      const float4 t0 = __ldcg(reinterpret_cast<const float4*>(p + size_t(sidx) * sl_stride));
+      const float4 t1 = __ldcg(reinterpret_cast<const float4*>(p + size_t(sidx + 1) * sl_stride));
+      a.x += t0.x; a.y += t0.y; a.z += t0.z; a.w += t0.w;
+      a.x += t1.x; a.y += t1.y; a.z += t1.z; a.w += t1.w;
+    }
+    if (sidx < pk.ksplit) {
+      const float4 t0 = __ldcg(reinterpret_cast<const float4*>(p + size_t(sidx) * sl_stride));
+      a.x += t0.x; a.y += t0.y; a.z += t0.z; a.w += t0.w;
+    }
+    if (bias) {
+      const float4 bb = reinterpret_cast<const float4*>(bias)[c];
+      a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+    }
+    if (res) {
+      const float4 rr = reinterpret_cast<const float4*>(res + (long long)row * ldr)[c];
+      a.x += rr.x; a.y += rr.y; a.z += rr.z; a.w += rr.w;
+    }
+    v[n] = a;
+    s += (a.x + a.y) + (a.z + a.w);
+  }
+  const float mean = warp_sum(s) / float(N);
+  float q = 0.f;
+  for (int i = 0; i < n; ++i) {
+    const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+    q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / float(N) + eps);
+  n = 0;
+  for (int c = lane; c < C4; c += 32, ++n) {
+    const float4 gg = reinterpret_cast<const float4*>(g)[c], bb = reinterpret_cast<const float4*>(b)[c];
+    float4 y;
+    y.x = (v[n].x - mean) * rstd * gg.x + bb.x; y.y = (v[n].y - mean) * rstd * gg.y + bb.y;
+    y.z = (v[n].z - mean) * rstd * gg.z + bb.z; y.w = (v[n].w - mean) * rstd * gg.w + bb.w;
+    if (o16) store_act4(o16 + (long long)row * ld16, 4 * c, split, y);
+    if (o32) reinterpret_cast<float4*>(o32 + (long long)row * ld32)[c] = y;
+  }
+}
+
 // Fused DaViT pre-block: y = dwconv3x3(x) + bias + x (fp32, the new residual stream) and h = LayerNorm(y) as the next
 // GEMM operand.  One warp per token; channels in float4 lanes (C <= 1024).
 __global__ void dwconv_ln_kernel(const float* __restrict__ x, int B, int H, int W, int C, const float* __restrict__ w9c,
@@ -593,16 +657,27 @@ __global__ void __launch_bounds__(1024) greedy_pick_kernel(PickArgs a) {
       // plain scan; the (<= 19-entry) ban list is only consulted when a value would become the running maximum
       const float2* lp = reinterpret_cast<const float2*>(lg);
       const int V2 = a.V >> 1;
-      for (int v2 = threadIdx.x; v2 < V2; v2 += blockDim.x) {
-        const float2 t2 = lp[v2];
+      // four strided loads in flight per thread before the compares (one load per iteration left every thread waiting on an
+      // L2 round trip 25 times per row); the compares stay in ascending index order
+      for (int v0 = threadIdx.x; v0 < V2; v0 += 4 * blockDim.x) {
+        float2 t4[4];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float sv = e ? t2.y : t2.x;
-          const int v = 2 * v2 + e;
-          if (sv > best) {   // ascending v within a thread: ties keep the earlier index
-            bool ban = false;
-            for (int k = 0; k < nbanned; ++k) ban = ban || (banned[k] == v);
-            if (!ban) { best = sv; besti = v; }
+        for (int u = 0; u < 4; ++u) {
+          const int v2 = v0 + u * blockDim.x;
+          t4[u] = (v2 < V2) ? lp[v2] : make_float2(-INFINITY, -INFINITY);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int v2 = v0 + u * blockDim.x;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float sv = e ? t4[u].y : t4[u].x;
+            const int v = 2 * v2 + e;
+            if (sv > best) {   // ascending v within a thread: ties keep the earlier index
+              bool ban = false;
+              for (int k = 0; k < nbanned; ++k) ban = ban || (banned[k] == v);
+              if (!ban) { best = sv; besti = v; }
+            }
           }
         }
       }
@@ -669,6 +744,28 @@ int b2p_layernorm(const float* x, long long ldx, const float* gamma, const float
   if (C % 4 || C > 1024 || (ldx % 4) || (ld32 % 4) || (ld16 % 4)) return set_error("layernorm: C, ld must be multiples of 4, C <= 1024");
   const int wpb = 8;
   launch_pdl(layernorm_kernel, dim3((T + wpb - 1) / wpb), dim3(wpb * 32), 0, st, x, ldx, gamma, beta, eps, T, C, (__half*)out16, ld16, out32, ld32, split ? C : 0);
+  B2P_CHECK_LAUNCH();
+  return 0;
+}
+
+// out = LayerNorm(A * B^T + bias + residual): a park-only GEMM (raw partial accumulators of every (tile, k slice) in the
+// split-K workspace) followed by splitk_ln_kernel.  A, B as b2p_gemm (flags & 8: fp16x3 operands); residual fp32 [M][ldr];
+// out16: fp16 (flags & 4: [hi | lo], ld16 >= 2N) and / or out32: fp32.  Replaces b2p_gemm(+residual) + b2p_layernorm.
+int b2p_gemm_ln(const void* A, long long lda, const void* B, int M, int N, int K, const float* bias, const float* residual,
+                long long ldr, const float* gamma, const float* beta, float eps, void* out16, long long ld16, float* out32,
+                long long ld32, int flags, cudaStream_t st) {
+  if (M <= 0) return 0;
+  if (N % 16 || N > 1024 || (ldr % 4) || (ld32 % 4) || (ld16 % 4)) return set_error("gemm_ln: N must be a multiple of 16 and <= 1024, ld multiples of 4");
+  ParkInfo pk{};
+  ConvGemm d{};
+  d.mode = 0; d.bf16 = 0; d.A = A; d.lda = lda; d.B = B; d.M = M; d.N = N; d.K = K;
+  d.out = nullptr; d.ldc = N; d.out_f32 = 1; d.bias = nullptr; d.res = nullptr; d.ldr = 0; d.act = 0;
+  d.bn_max = (flags >> 8) & 0x1ff; d.x3 = (flags >> 3) & 1;
+  d.park = 1; d.park_info = &pk;
+  if (int e = gemm_launch(d, st)) return e;
+  const int wpb = 8;
+  launch_pdl(splitk_ln_kernel, dim3((M + wpb - 1) / wpb), dim3(wpb * 32), 0, st, pk, M, N, bias, residual, ldr, gamma, beta, eps,
+             (__half*)out16, ld16, out32, ld32, (flags & 4) ? N : 0);
   B2P_CHECK_LAUNCH();
   return 0;
 }

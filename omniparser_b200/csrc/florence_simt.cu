@@ -537,14 +537,17 @@ int channel_attn_v3_launch(const float* qkv, int B, int N, int C, int groups, vo
 // warp re-reads the head's K and V rows (430 MB of L2 -> SM traffic per launch).  Here one warp owns a (batch, head): K and V
 // (<= 16 keys, 2 values per lane per key) stay in registers and the queries are processed in turn with exactly the
 // arithmetic of mha_kernel (four keys per step, then the tail) => bit-identical outputs.
-constexpr int kMhaLmax = 16;
+constexpr int kMhaLmax = 16, kMhaQSplit = 1;   // > 1 deals the queries of a head to several warps: measured slower (4: 48 us vs 38)
 __global__ void __launch_bounds__(128) mha_short_kernel(const float* __restrict__ qp, long long ldq, const float* __restrict__ kp,
                                                         const float* __restrict__ vp, long long ldk, int B, int Lq, int Lk, int heads,
                                                         __half* __restrict__ out, long long ldo, int split) {
   pdl_wait();
-  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int wid0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (wid >= B * heads) return;
+  if (wid0 >= B * heads * kMhaQSplit) return;
+  // the queries of one (batch, head) are dealt to kMhaQSplit warps (each query is a long dependent chain of butterfly
+  // reductions: one warp per head left the SM latency-bound at 38 us per launch); K / V re-loads hit L1 / L2
+  const int part = wid0 % kMhaQSplit, wid = wid0 / kMhaQSplit;
   const int h = wid % heads, b = wid / heads;
   const float* kb = kp + (long long)b * Lk * ldk + h * 64;
   const float* vb = vp + (long long)b * Lk * ldk + h * 64;
@@ -562,11 +565,12 @@ __global__ void __launch_bounds__(128) mha_short_kernel(const float* __restrict_
   // the query loop stays ROLLED (fully unrolled it is ~11k instructions and thrashes the instruction cache: 112 us per launch
   // against 40); the next query's row is fetched one iteration ahead so its L2 round trip overlaps this query's arithmetic
   const float* qrow = qp + (long long)b * Lq * ldq + h * 64 + 2 * lane;
-  float2 qn = *reinterpret_cast<const float2*>(qrow);
+  if (part >= Lq) return;
+  float2 qn = *reinterpret_cast<const float2*>(qrow + (long long)part * ldq);
 #pragma unroll 1
-  for (int qi = 0; qi < Lq; ++qi) {
+  for (int qi = part; qi < Lq; qi += kMhaQSplit) {
     float2 q = qn;
-    if (qi + 1 < Lq) qn = *reinterpret_cast<const float2*>(qrow + (long long)(qi + 1) * ldq);
+    if (qi + kMhaQSplit < Lq) qn = *reinterpret_cast<const float2*>(qrow + (long long)(qi + kMhaQSplit) * ldq);
     q.x *= 0.125f; q.y *= 0.125f;
     float m = -INFINITY, l = 0.f;
     float2 acc = make_float2(0.f, 0.f);
@@ -621,7 +625,7 @@ __global__ void __launch_bounds__(128) mha_short_kernel(const float* __restrict_
 int mha_short_launch(const float* q, long long ldq, const float* k, const float* v, long long ldk, int B, int Lq, int Lk, int heads,
                      void* out, long long ldo, int split, cudaStream_t st) {
   if (Lk > kMhaLmax || Lq > kMhaLmax || Lq < 2 || B <= 0) return 1;
-  const int total = B * heads;
+  const int total = B * heads * kMhaQSplit;
   launch_pdl(mha_short_kernel, dim3((total + 3) / 4), dim3(128), 0, st, q, ldq, k, v, ldk, B, Lq, Lk, heads, (__half*)out, ldo,
              split ? heads * 64 : 0);
   cudaError_t e = cudaGetLastError();

@@ -86,6 +86,8 @@ struct GemmArgs {
   float* ws;   // split-K partial tiles [tile][slice][128][bn] fp32
   int* counters;   // split-K {arrived, finished} counters per output tile (self-resetting)
   int sk_last;     // split-K variant: 1 = last arriver reduces (wait-free, B2P_SPLITK_LAST=1), 0 = distributed reduction
+  int park;        // 1 = park-only: every (tile, k slice) leaves its raw fp32 accumulators in ws and the kernel ends; the
+                   // following kernel (splitk_ln_kernel) sums the slices, adds bias + residual and applies LayerNorm
   unsigned long long* trace;   // B2P_TRACE build of the kernel only: [CTA][16] globaltimer stamps (see trace_stamp)
 };
 
@@ -634,7 +636,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       tc_fence_after();
       if constexpr (kTrace) { if (item == blockIdx.x && threadIdx.x == 64) trace_stamp<kTrace>(g, kTrFirstEpiStart); }
       const uint32_t t_row = tmem_base + (uint32_t(grp * 32) << 16) + uint32_t(acc * 256);
-      if (e_ksplit == 1) {
+      if (e_ksplit == 1 && !g.park) {
         // the accumulator goes back to the MMA warp as soon as this warp's LAST 16-column chunk sits in registers (before it
         // is processed).  (A software-pipelined variant with two register buffers measured no faster and spilled.)
         bool released = false;
@@ -676,7 +678,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-        if (g.sk_last) {
+        if (g.park) {
+          // park-only: nothing to wait for, nothing to reduce here (the consumer kernel starts after this grid has completed)
+        } else if (g.sk_last) {
           __threadfence();
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
           volatile uint32_t* s_last = tmem_slot + 1;
@@ -777,8 +781,24 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
             float x[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) x[j] = 0.f;
-            for (int sidx = 0; sidx < g.ksplit; ++sidx) {
-              const float4* pp = reinterpret_cast<const float4*>(base + (size_t(sidx) * kTileM + rr_) * g.bn + c);
+            // two slices per round trip: the loads of both are in flight before the first add (one slice at a time cost one L2
+            // latency per slice: 4 us of the 8.8 us fc2 epilogue at split 6); the adds keep the slice order
+            const size_t sl_stride = size_t(kTileM) * g.bn;
+            const float* pbase = base + size_t(rr_) * g.bn + c;
+            int sidx = 0;
+            for (; sidx + 2 <= g.ksplit; sidx += 2) {
+              const float4* p0 = reinterpret_cast<const float4*>(pbase + size_t(sidx) * sl_stride);
+              const float4* p1 = reinterpret_cast<const float4*>(pbase + size_t(sidx + 1) * sl_stride);
+              float4 t0[4], t1[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { t0[q] = __ldcg(p0 + q); t1[q] = __ldcg(p1 + q); }
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { x[4 * q] += t0[q].x; x[4 * q + 1] += t0[q].y; x[4 * q + 2] += t0[q].z; x[4 * q + 3] += t0[q].w; }
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { x[4 * q] += t1[q].x; x[4 * q + 1] += t1[q].y; x[4 * q + 2] += t1[q].z; x[4 * q + 3] += t1[q].w; }
+            }
+            if (sidx < g.ksplit) {
+              const float4* pp = reinterpret_cast<const float4*>(pbase + size_t(sidx) * sl_stride);
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const float4 t = __ldcg(pp + q);
@@ -1112,6 +1132,12 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
       if (res_stagesA > 8) res_stagesA = 8;
     }
   }
+  if (d.park) {
+    if (d.mode != 0 || slot < 0) return set_error("gemm (park-only): needs mode 0 and a split-K workspace slot for this stream");
+    if (size_t(g.m_tiles) * ((d.N + bn - 1) / bn) * ksplit * 128 * bn * 4 > kWsBytes) return set_error("gemm (park-only): partial tiles exceed the workspace");
+    bres = false;
+  }
+  g.park = d.park ? 1 : 0;
   g.bres = bres ? 1 : 0;
   g.sep = (halo || bres) ? 1 : 0;
   g.taps = halo ? 9 : 1;
@@ -1210,6 +1236,10 @@ int gemm_launch(const ConvGemm& d, cudaStream_t st) {
   if (ce == cudaSuccess) ce = cudaGetLastError();
   if (ce != cudaSuccess) return set_error(cudaGetErrorString(ce));
   count_launch();
+  if (d.park_info) {
+    d.park_info->ws = g.ws; d.park_info->bn = bn; d.park_info->ksplit = g.ksplit; d.park_info->n_tiles = g.n_tiles;
+    d.park_info->m_tiles = g.m_tiles; d.park_info->mt_fast = g.mt_fast;
+  }
   return 0;
 }
 

@@ -182,6 +182,10 @@ class FlorencePlan:
         # round-2 SIMT kernels (csrc/florence_simt.cu): strip dwconv+LN, per-image window attention, register-tiled channel
         # attention, warp-per-head short attention; B2P_NO_SIMT_V3=1 selects the first versions (the checkers)
         self.v3 = not os.environ.get("B2P_NO_SIMT_V3")
+        # B2P_GEMM_LN=1: decoder out-proj / cross out-proj / fc2 as park-only split-K GEMM + one reduce/LayerNorm kernel
+        # (b2p_gemm_ln) instead of GEMM with in-kernel split-K reduction + LayerNorm launch.  Bit-identical; measured neutral
+        # on B200 (decode step 0.84 vs 0.82 ms: the kernel boundary costs what the in-kernel wait cost), so it stays opt-in.
+        self.fuse_ln = bool(os.environ.get("B2P_GEMM_LN"))
         self.warmed = False
         import threading
         self.lock = threading.Lock()
@@ -230,6 +234,21 @@ class FlorencePlan:
         lst.append(lambda: ops.gemm(a, a.stride(0), lin.w, M, lin.N, lin.K, out, out.stride(0), lin.b, res,
                                     res.stride(0) if res is not None else 0, act, out_f32=(out.dtype == torch.float32),
                                     split=split, x3=self.x3))
+
+    def _gemm_ln(self, lst, a, lin, res, ln, o16, o32, enc=False):
+        """o16 / o32 = LayerNorm(a @ W^T + b + res): one park-only GEMM + the split-K-reduce / LayerNorm kernel (b2p_gemm_ln)
+        instead of GEMM (+ in-kernel split-K reduction) + LayerNorm.  Same sums in the same order."""
+        M = a.shape[0]
+        assert a.shape[1] == self.KX * lin.K and res.dtype == torch.float32
+        f = 2 * M * lin.N * lin.Klog
+        if enc:
+            self.flops_enc += f
+        else:
+            self.flops_dec += f
+        f_ = lambda: ops.gemm_ln(a, a.stride(0), lin.w, M, lin.N, lin.K, lin.b, res, res.stride(0), ln.g, ln.b,
+                                 o16, o16.stride(0), o32, o32.stride(0), split=self.x3, x3=self.x3)
+        f_.n_kernels = 2        # launch accounting of graph replays (ops.count_graph_launches)
+        lst.append(f_)
 
     def _ln(self, lst, x, ln, T, C, o16=None, o32=None):
         lst.append(lambda: ops.layernorm(x, ln.g, ln.b, T, C, o16, o32, split=self.x3))
@@ -382,25 +401,40 @@ class FlorencePlan:
             a = self._act(R, D)
             ops_.append(lambda qkv=qkv, kc=kc, vc=vc, a=a: ops.mha_cached(qkv, 3 * D, qkv[:, D:], qkv[:, 2 * D:], 3 * D, kc, vc, tmax,
                                                                        step, R, self.HEADS, a, a.stride(0), split=x3))
-            y = self._e(R, D)
-            self._gemm(ops_, a, lay["o"], y, res=x, enc=False)
-            x = self._e(R, D); h = self._act(R, D)
-            self._ln(ops_, y, lay["ln1"], R, D, h, x)
+            if self.fuse_ln:
+                xn = self._e(R, D); h = self._act(R, D)
+                self._gemm_ln(ops_, a, lay["o"], x, lay["ln1"], h, xn)
+                x = xn
+            else:
+                y = self._e(R, D)
+                self._gemm(ops_, a, lay["o"], y, res=x, enc=False)
+                x = self._e(R, D); h = self._act(R, D)
+                self._ln(ops_, y, lay["ln1"], R, D, h, x)
             q = self._e(R, D)
             self._gemm(ops_, h, lay["cq"], q, enc=False)
             kv = self.cross_kv[li][r0 * self.L:r1 * self.L]
             a2 = self._act(R, D)
             ops_.append(lambda q=q, kv=kv, a2=a2: ops.mha(q, D, kv, kv[:, D:], 2 * D, R, 1, self.L, self.HEADS, a2, a2.stride(0), split=x3))
-            y = self._e(R, D)
-            self._gemm(ops_, a2, lay["co"], y, res=x, enc=False)
-            x = self._e(R, D); h = self._act(R, D)
-            self._ln(ops_, y, lay["ln2"], R, D, h, x)
+            if self.fuse_ln:
+                xn = self._e(R, D); h = self._act(R, D)
+                self._gemm_ln(ops_, a2, lay["co"], x, lay["ln2"], h, xn)
+                x = xn
+            else:
+                y = self._e(R, D)
+                self._gemm(ops_, a2, lay["co"], y, res=x, enc=False)
+                x = self._e(R, D); h = self._act(R, D)
+                self._ln(ops_, y, lay["ln2"], R, D, h, x)
             f = self._act(R, 4 * D)
             self._gemm(ops_, h, lay["fc1"], f, act=ACT_GELU, enc=False, split=x3)
-            y = self._e(R, D)
-            self._gemm(ops_, f, lay["fc2"], y, res=x, enc=False)
-            x = self._e(R, D); h = self._act(R, D)
-            self._ln(ops_, y, lay["ln3"], R, D, h, x)
+            if self.fuse_ln:
+                xn = self._e(R, D); h = self._act(R, D)
+                self._gemm_ln(ops_, f, lay["fc2"], x, lay["ln3"], h, xn)
+                x = xn
+            else:
+                y = self._e(R, D)
+                self._gemm(ops_, f, lay["fc2"], y, res=x, enc=False)
+                x = self._e(R, D); h = self._act(R, D)
+                self._ln(ops_, y, lay["ln3"], R, D, h, x)
         lm = type("W", (), {})()
         lm.w, lm.b, lm.N, lm.K, lm.Klog = w.E16, None, w.vocab, D, D
         self._gemm(ops_, h, lm, logits, enc=False)
@@ -444,7 +478,7 @@ class FlorencePlan:
             if not replay_after_capture or os.environ.get("B2P_EAGER_FIRST"):
                 return
         g.replay()
-        ops.count_graph_launches(len(lst))
+        ops.count_graph_launches(sum(getattr(f, "n_kernels", 1) for f in lst))
 
     def warm(self):
         """Build every CUDA graph of this plan on scratch inputs (call with the GPU otherwise idle: see

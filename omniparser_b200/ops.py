@@ -101,6 +101,13 @@ def gemm(a_ptr, lda, w, M, N, K, out_ptr, ldc, bias=None, res_ptr=None, ldr=0, a
                                    flags, _stream()))
 
 
+def gemm_ln(a_ptr, lda, w, M, N, K, bias, res, ldr, gamma, beta, out16, ld16, out32, ld32, eps=1e-5, split=False, x3=False):
+    """out = LayerNorm(A @ w^T + bias + res): park-only GEMM + split-K-reduce/LayerNorm kernel (decoder out-proj / fc2)."""
+    flags = (FLAG_SPLIT if split else 0) | (FLAG_X3 if x3 else 0)
+    _lib.check(_lib.lib().b2p_gemm_ln(_p(a_ptr), lda, _p(w), M, N, K, _p(bias), _p(res), ldr, _p(gamma), _p(beta), eps,
+                                      _p(out16), ld16, _p(out32), ld32, flags, _stream()))
+
+
 def linear(x: torch.Tensor, w: torch.Tensor, bias=None, res=None, act=ACT_NONE, out_dtype=torch.float16, out=None,
            bn_max=0):
     """out[M,N] = act(x[M,K] @ w[N,K]^T + bias) + res ; x, w fp16 row-major (x may be a strided row view)."""

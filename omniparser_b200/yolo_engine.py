@@ -277,7 +277,9 @@ class YoloPlan:
     def _adown(self, name, x: Map, out: Map):
         x1 = self._fm(x.C // 2, x.H, x.W)
         x2 = self._fm(x.C // 2, x.H // 2, x.W // 2)
-        self.ops.append(lambda: ops.adown_pool(x, x1, x2))
+        f_ = lambda: ops.adown_pool(x, x1, x2)
+        f_.n_kernels = 1 if self.x3 else 2      # plain fp16 maps: separate average / max kernels (csrc/detect_ops.cu)
+        self.ops.append(f_)
         half = out.C // 2
         self._c3(x1, name + ".cv1", out.slice(0, half), stride=2)
         self._c1(x2, name + ".cv2", out.slice(half, half))
@@ -364,7 +366,7 @@ class YoloPlan:
             self.cls_out.append(co.buf); self.box_out.append(bo.buf); self.hw.append((x.H, x.W))
         self.taps.update(x1=x1, x2=x2, x3=x3, x5=x5, x7=x7, x9=x9, x16=x16, x18=x18, x19=x19, x22=x22, x25=x25,
                          x28=x28, x29=x29, x32=x32, x35=x35, x38=x38, x41=x41)
-        self.n_launches = len(self.ops)
+        self.n_launches = sum(getattr(f, "n_kernels", 1) for f in self.ops)
 
     def run(self):
         """Run the recorded launches on the current stream (canvas -> head tensors)."""

@@ -480,6 +480,37 @@ def test_mha_short_equals_first_version(B, L, split):
     assert (_pair_val(outs[1].cpu(), D, split) - ref).abs().max().item() < tol
 
 
+@pytest.mark.parametrize("M,N,K", [(416, 768, 768), (416, 768, 3072), (100, 256, 512), (37, 1024, 64), (700, 512, 2048)])
+@pytest.mark.parametrize("x3", [False, True])
+def test_gemm_ln_equals_gemm_then_layernorm(M, N, K, x3):
+    """b2p_gemm_ln (park-only split-K GEMM + reduce / bias / residual / LayerNorm kernel) == b2p_gemm (+bias, +residual, fp32)
+    followed by b2p_layernorm, bit for bit (same sums in the same order), and close to torch fp64."""
+    g = torch.Generator().manual_seed(M + N + K)
+    a32 = torch.randn(M, K, generator=g)
+    w32 = torch.randn(N, K, generator=g) * 0.05
+    if x3:
+        a = torch.cat(_hilo(a32), 1).contiguous().to(DEV)
+        w = torch.cat(_hilo(w32), 1).contiguous().to(DEV)
+        aref, wref = a32.double(), w32.double()
+    else:
+        a, w = a32.half().to(DEV), w32.half().to(DEV)
+        aref, wref = a.cpu().double(), w.cpu().double()
+    bias = torch.randn(N, generator=g).to(DEV)
+    res = torch.randn(M, N, generator=g).to(DEV)
+    gam = torch.randn(N, generator=g).to(DEV)
+    bet = torch.randn(N, generator=g).to(DEV)
+    y = torch.zeros(M, N, device=DEV)
+    ops.gemm(a, a.stride(0), w, M, N, K, y, N, bias, res, N, ops.ACT_NONE, out_f32=True, x3=x3)
+    o16a = torch.zeros(M, 2 * N, dtype=torch.float16, device=DEV); o32a = torch.zeros(M, N, device=DEV)
+    ops.layernorm(y, gam, bet, M, N, o16a, o32a, split=True)
+    o16b = torch.zeros(M, 2 * N, dtype=torch.float16, device=DEV); o32b = torch.zeros(M, N, device=DEV)
+    ops.gemm_ln(a, a.stride(0), w, M, N, K, bias, res, N, gam, bet, o16b, 2 * N, o32b, N, split=True, x3=x3)
+    torch.cuda.synchronize()
+    assert torch.equal(o32a, o32b) and torch.equal(o16a, o16b)
+    ref = F.layer_norm(aref @ wref.t() + bias.cpu().double() + res.cpu().double(), (N,), gam.cpu().double(), bet.cpu().double(), 1e-5)
+    assert (o32b.cpu().double() - ref).abs().max().item() < (2e-4 if x3 else 2e-3) * max(1.0, ref.abs().max().item())
+
+
 # ---------------------------------------------------------------------------------------------- overlap filter (8f-2)
 def _overlap_device(px_list, ocr_px_list, W, H, thr, max_det=300, max_ocr=256):
     """b2p_overlap_filter on a batch: px_list[b] fp32 [n_b,4] pixel boxes (NMS output format), ocr_px_list[b] (texts, int boxes)

@@ -138,6 +138,20 @@ def test_florence_plan_64(rec, florence, prec):
     assert len(forced) == n_dec - 1 and forced[-3:] == ["b2p_layernorm", "b2p_greedy_pick", "b2p_step_advance"]
 
 
+def test_gemm_ln_opt_in(rec, florence, monkeypatch):
+    """B2P_GEMM_LN=1: the 18 (split-K GEMM + residual, LayerNorm) pairs of the decode step become b2p_gemm_ln calls"""
+    from omniparser_b200.florence_engine import FlorencePlan, FlorenceWeights
+    monkeypatch.setenv("B2P_GEMM_LN", "1")
+    w = FlorenceWeights(florence.state_dict(), torch.device("cpu"), FS.GEN, "fp16x3")
+    p = FlorencePlan(w, 2, 4, FS.PROMPT_IDS, use_graph=False, size=64)
+    p.encode()
+    n_enc = len(rec.calls)
+    p.reset_decode(2)
+    p.decode_step()
+    names = [c[0] for c in rec.calls[n_enc:]]
+    assert len(names) == 71 - 18 and names.count("b2p_gemm_ln") == 18 and names.count("b2p_layernorm") == 1
+
+
 def test_florence_plan_768(rec, florence):
     from omniparser_b200.florence_engine import FlorencePlan, FlorenceWeights
     w = FlorenceWeights(florence.state_dict(), torch.device("cpu"), FS.GEN, "fp16x3")
@@ -184,7 +198,7 @@ def test_yolo_plan(rec):
     plan = YoloPlan(w, 2, 384, 640, use_graph=False)
     plan.run()
     names = [c[0] for c in rec.calls]
-    assert len(names) == plan.n_launches == 252
+    assert len(names) == 252 and plan.n_launches == 260                  # 8 b2p_adown_pool calls launch an average and a max kernel each
     assert names.count("b2p_gemm") + names.count("b2p_conv3x3") == 233   # the figure quoted in bench.py / DESIGN.md
     assert all(not (c[1][12] & 8) for c in rec.calls if c[0] == "b2p_gemm")      # detector: plain fp16 operands
 
@@ -230,10 +244,10 @@ def test_graph_paths(rec, florence, monkeypatch):
     assert n_eager == 2 * (232 + 71 + 70)               # every op ran once eagerly and once inside the (stubbed) capture; the
                                                         # decode step exists with and without the LM head (forced tokens)
     p.encode(); p.reset_decode(2); p.decode_step(); p.decode_step()
-    assert _Graph.replays == 2 + 3 and ops.GRAPH_LAUNCHES[0] - g0 == 2 * 232 + 3 * 71
+    assert _Graph.replays == 2 + 3 and ops.GRAPH_LAUNCHES[0] - g0 == 2 * 232 + 3 * 71      # kernels, not calls
     assert sum(1 for c in rec.calls[n_eager:] if c[0].startswith("b2p_")) == 0     # steady state: graph replays only
     yw = YoloWeights(yolo_standin(0).state_dict(), torch.device("cpu"))
     yp = YoloPlan(yw, 1, 384, 640, use_graph=True)
     g1 = ops.GRAPH_LAUNCHES[0]
     yp.run(); yp.run()
-    assert ops.GRAPH_LAUNCHES[0] - g1 == 2 * 252
+    assert ops.GRAPH_LAUNCHES[0] - g1 == 2 * 260
