@@ -412,6 +412,7 @@ def run_b200(args):
                                     "executed_frac_of_peak": xk * cplan.flops_dec / dec_ms / 1e9 / peak_tf,
                                     "note": "~70 launches per step at M = rows: dependency-chain bound (~11 us per launch whatever the tiling), see profiles/r2_notes.md"}}
                 log(f"caption stages: encode {enc_ms:.2f} ms, decode step {dec_ms:.3f} ms")
+                log(f"device memory: peak allocated {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB, reserved {torch.cuda.memory_reserved() / 2**30:.1f} GiB")
     except Exception as exc:   # noqa: BLE001
         caption_stages = {"error": repr(exc)[:200]}
 
@@ -422,7 +423,7 @@ def run_b200(args):
     tpf = ROOT / "profiles" / "r2_stage_traffic.json"
     if tpf.is_file() and B == 8:
         stage_traffic = json.loads(tpf.read_text())
-    roofline_stages = [{"stage": "detect: YOLOv9-E forward (gemm_tcgen05_kernel x233 + 19 HBM kernels)", "bound": "tensor", "ms": fwd_ms,
+    roofline_stages = [{"stage": "detect: YOLOv9-E forward (gemm_tcgen05_kernel x233 + 27 HBM kernels)", "bound": "tensor", "ms": fwd_ms,
                         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                         "traffic": (stage_traffic.get("detect") or {}).get("dram_bytes", traffic)}]
     if caption_stages and "encode" in caption_stages:
@@ -458,7 +459,7 @@ def run_b200(args):
                         "d2h_bytes_per_step": B * (4 + 300 * 16) + st["crops"] // max(args.steps, 1) * (args.max_new_tokens + 1) * 8,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clocks,
-                "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (YOLOv9-E forward, batch %d: 233 GEMM/conv launches + 19 im2col/pooling/upsample/CBFuse launches)" % B,
+                "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (YOLOv9-E forward, batch %d: 233 GEMM/conv launches + 27 im2col/pooling/upsample/CBFuse launches)" % B,
                              "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
                              "traffic_note": "DRAM bytes per forward from the committed ncu launch list (caches flushed per kernel), not from this run",
                              "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})", "forward_ms": fwd_ms,

@@ -284,7 +284,9 @@ __global__ void dwconv3x3_res_kernel(const float* __restrict__ x, int B, int H, 
 // window; padded tokens have qkv = bias and take part as keys/values unmasked
 // (hf:models/florence2/modeling_florence2.py:346-350,377-383).  Exact shortcut: one "pad key" (k = bias_k,
 // v = bias_v) with multiplicity n_pad = 144 - n_real.  One CTA per (batch, window, head); one thread per query.
-template <int D>
+// QB queries per thread (t, t + ceil(nreal / QB), ...): every K / V row read from shared memory feeds QB independent
+// online-softmax chains.  Only QB = 1 is instantiated (see b2p_window_attn).
+template <int D, int QB>
 __global__ void window_attn_kernel(const float* __restrict__ qkv, const float* __restrict__ qkv_bias, int B, int H,
                                    int W, int C, int heads, int win, __half* __restrict__ out, int split, int kv_cap) {
   pdl_wait();   // PDL: inputs come from the previous kernel in the stream
@@ -309,58 +311,84 @@ __global__ void window_attn_kernel(const float* __restrict__ qkv, const float* _
   }
   __syncthreads();
   const float scale = rsqrtf(float(D));
-  for (int t = threadIdx.x; t < nreal; t += blockDim.x) {
-    const long long tok = ((long long)b * H + y0 + t / nx) * W + x0 + t % nx;
-    float4 q[D4], acc[D4];
+  const int nq = (nreal + QB - 1) / QB;
+  for (int t0 = threadIdx.x; t0 < nq; t0 += blockDim.x) {
+    long long tok[QB];
+    bool live[QB];
+    float4 q[QB][D4], acc[QB][D4];
+    float m[QB], l[QB];
 #pragma unroll
-    for (int d = 0; d < D4; ++d) {
-      q[d] = reinterpret_cast<const float4*>(qkv + tok * 3 * C + head * D)[d];
-      q[d].x *= scale; q[d].y *= scale; q[d].z *= scale; q[d].w *= scale;
-      acc[d] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    float m = -INFINITY, l = 0.f;
-    if (npad > 0) {
-      float s = 0.f;
+    for (int u = 0; u < QB; ++u) {
+      const int t = t0 + u * nq;
+      live[u] = t < nreal;
+      const int tc = live[u] ? t : t0;      // a dead slot recomputes query t0 and stores nothing
+      tok[u] = ((long long)b * H + y0 + tc / nx) * W + x0 + tc % nx;
 #pragma unroll
       for (int d = 0; d < D4; ++d) {
-        const float4 kb = reinterpret_cast<const float4*>(qkv_bias + C + head * D)[d];
-        s += (q[d].x * kb.x + q[d].y * kb.y) + (q[d].z * kb.z + q[d].w * kb.w);
+        q[u][d] = reinterpret_cast<const float4*>(qkv + tok[u] * 3 * C + head * D)[d];
+        q[u][d].x *= scale; q[u][d].y *= scale; q[u][d].z *= scale; q[u][d].w *= scale;
+        acc[u][d] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      m = s;
-      l = float(npad);
+      m[u] = -INFINITY; l[u] = 0.f;
+    }
+    if (npad > 0) {
 #pragma unroll
-      for (int d = 0; d < D4; ++d) {
-        const float4 vb = reinterpret_cast<const float4*>(qkv_bias + 2 * C + head * D)[d];
-        acc[d] = make_float4(l * vb.x, l * vb.y, l * vb.z, l * vb.w);
+      for (int u = 0; u < QB; ++u) {
+        float s = 0.f;
+#pragma unroll
+        for (int d = 0; d < D4; ++d) {
+          const float4 kb = reinterpret_cast<const float4*>(qkv_bias + C + head * D)[d];
+          s += (q[u][d].x * kb.x + q[u][d].y * kb.y) + (q[u][d].z * kb.z + q[u][d].w * kb.w);
+        }
+        m[u] = s;
+        l[u] = float(npad);
+#pragma unroll
+        for (int d = 0; d < D4; ++d) {
+          const float4 vb = reinterpret_cast<const float4*>(qkv_bias + 2 * C + head * D)[d];
+          acc[u][d] = make_float4(l[u] * vb.x, l[u] * vb.y, l[u] * vb.z, l[u] * vb.w);
+        }
       }
     }
     for (int j = 0; j < nreal; ++j) {
-      float s = 0.f;
+      float s[QB], p[QB];
+#pragma unroll
+      for (int u = 0; u < QB; ++u) s[u] = 0.f;
 #pragma unroll
       for (int d = 0; d < D4; ++d) {
         const float4 kk = Ks[j * D4 + d];
-        s += (q[d].x * kk.x + q[d].y * kk.y) + (q[d].z * kk.z + q[d].w * kk.w);
-      }
-      if (s > m) {
-        const float r = __expf(m - s);
-        l *= r;
 #pragma unroll
-        for (int d = 0; d < D4; ++d) { acc[d].x *= r; acc[d].y *= r; acc[d].z *= r; acc[d].w *= r; }
-        m = s;
+        for (int u = 0; u < QB; ++u) s[u] += (q[u][d].x * kk.x + q[u][d].y * kk.y) + (q[u][d].z * kk.z + q[u][d].w * kk.w);
       }
-      const float p = __expf(s - m);
-      l += p;
+#pragma unroll
+      for (int u = 0; u < QB; ++u) {
+        if (s[u] > m[u]) {
+          const float r = __expf(m[u] - s[u]);
+          l[u] *= r;
+#pragma unroll
+          for (int d = 0; d < D4; ++d) { acc[u][d].x *= r; acc[u][d].y *= r; acc[u][d].z *= r; acc[u][d].w *= r; }
+          m[u] = s[u];
+        }
+        p[u] = __expf(s[u] - m[u]);
+        l[u] += p[u];
+      }
 #pragma unroll
       for (int d = 0; d < D4; ++d) {
         const float4 vv = Vs[j * D4 + d];
-        acc[d].x += p * vv.x; acc[d].y += p * vv.y; acc[d].z += p * vv.z; acc[d].w += p * vv.w;
+#pragma unroll
+        for (int u = 0; u < QB; ++u) {
+          acc[u][d].x += p[u] * vv.x; acc[u][d].y += p[u] * vv.y; acc[u][d].z += p[u] * vv.z; acc[u][d].w += p[u] * vv.w;
+        }
       }
     }
-    const float inv = 1.f / l;
-    __half* orow = out + tok * (split ? 2 * C : C);
 #pragma unroll
-    for (int d = 0; d < D4; ++d)
-      store_act4(orow, head * D + 4 * d, split, make_float4(acc[d].x * inv, acc[d].y * inv, acc[d].z * inv, acc[d].w * inv));
+    for (int u = 0; u < QB; ++u) {
+      if (!live[u]) continue;
+      const float inv = 1.f / l[u];
+      __half* orow = out + tok[u] * (split ? 2 * C : C);
+#pragma unroll
+      for (int d = 0; d < D4; ++d)
+        store_act4(orow, head * D + 4 * d, split, make_float4(acc[u][d].x * inv, acc[u][d].y * inv, acc[u][d].z * inv, acc[u][d].w * inv));
+    }
   }
 }
 
@@ -821,14 +849,16 @@ int b2p_window_attn(const float* qkv, const float* qkv_bias, int B, int H, int W
   if (int e = bind_device()) return e;
   static std::atomic<bool> attr{false};
   if (!attr) {
-    cudaFuncSetAttribute(window_attn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(window_attn_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr = true;
   }
   if (smem > 64 * 1024) return set_error("window_attn: window too large");
+  // (two queries per thread, QB = 2, measured SLOWER on the 16x16 map: 479 us against 357 -- 168 registers leave 12 warps per SM;
+  //  the one-window maps do use QB = 2, in window_attn_crop_kernel)
   // one thread per query of the window: small maps (4x4, 8x8 in the 64x64-crop mode) get small CTAs so more of them fit per SM
   const int nq = kv_cap;
   const int threads = nq >= 160 ? 160 : ((nq + 31) / 32) * 32;
-  launch_pdl(window_attn_kernel<32>, dim3(B * nw * heads), dim3(threads), smem, st, qkv, qkv_bias, B, H, W, C, heads, win, (__half*)out, (split & 1) ? C : 0, kv_cap);
+  launch_pdl(window_attn_kernel<32, 1>, dim3(B * nw * heads), dim3(threads), smem, st, qkv, qkv_bias, B, H, W, C, heads, win, (__half*)out, (split & 1) ? C : 0, kv_cap);
   B2P_CHECK_LAUNCH();
   return 0;
 }

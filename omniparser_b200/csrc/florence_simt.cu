@@ -178,10 +178,13 @@ int dwconv_ln_v3_launch(const float* x, int B, int H, int W, int C, const float*
 // (image, group of HPC heads): K and V of those heads for all tokens are staged once (coalesced float4 rows), thread =
 // (head, query) runs the same online-softmax recurrence as window_attn_kernel (bit-identical results), and the outputs
 // leave through a shared-memory transpose as whole [hi | lo] row segments.
-// shared memory: [token][K seg (HPC*32) | V seg (HPC*32)] fp32 (re-used as the output stage), then the mbarrier
-__global__ void __launch_bounds__(256, 3) window_attn_crop_kernel(const float* __restrict__ qkv, const float* __restrict__ qkv_bias,
-                                                                  int nreal, int npad, int C, int heads, int HPC,
-                                                                  __half* __restrict__ out, int split) {
+// shared memory: [token][K seg (HPC*32) | V seg (HPC*32)] fp32 (re-used as the output stage), then the mbarrier.
+// QB queries per thread (t, t + nreal / QB, ...): every K / V row read from shared memory feeds QB independent online-softmax
+// chains (the one-query loop was bound by the latency of its LDS -> FMA -> MUFU chain at 30 % occupancy, ncu short_scoreboard).
+template <int QB>
+__global__ void __launch_bounds__(256 / QB, 3) window_attn_crop_kernel(const float* __restrict__ qkv, const float* __restrict__ qkv_bias,
+                                                                       int nreal, int npad, int C, int heads, int HPC,
+                                                                       __half* __restrict__ out, int split) {
   pdl_wait();
   extern __shared__ float4 wsm4[];
   constexpr int D = 32, D4 = 8;
@@ -208,71 +211,91 @@ __global__ void __launch_bounds__(256, 3) window_attn_crop_kernel(const float* _
       }
     }
   }
-  const int hh = threadIdx.x / nreal, t = threadIdx.x - hh * nreal;   // blockDim.x == HPC * nreal
+  const int nq = nreal / QB;                                         // queries per (head, thread slot); nreal % QB == 0
+  const int hh = threadIdx.x / nq, t0 = threadIdx.x - hh * nq;       // blockDim.x == HPC * nq
   const int head = h0 + hh;
-  float4 q[D4], acc[D4];
+  float4 q[QB][D4], acc[QB][D4];
+  float m[QB], l[QB];
   const float scale = rsqrtf(float(D));
-  {
-    const float4* qp = reinterpret_cast<const float4*>(qkv + (tok0 + t) * 3 * C + head * D);
 #pragma unroll
-    for (int d = 0; d < D4; ++d) q[d] = qp[d];
+  for (int u = 0; u < QB; ++u) {
+    const float4* qp = reinterpret_cast<const float4*>(qkv + (tok0 + t0 + u * nq) * 3 * C + head * D);
 #pragma unroll
-    for (int d = 0; d < D4; ++d) {
-      q[d].x *= scale; q[d].y *= scale; q[d].z *= scale; q[d].w *= scale;
-      acc[d] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    for (int d = 0; d < D4; ++d) q[u][d] = qp[d];
   }
-  float m = -INFINITY, l = 0.f;
-  if (npad > 0) {
-    float s = 0.f;
+#pragma unroll
+  for (int u = 0; u < QB; ++u) {
 #pragma unroll
     for (int d = 0; d < D4; ++d) {
-      const float4 kb = reinterpret_cast<const float4*>(qkv_bias + C + head * D)[d];
-      s += (q[d].x * kb.x + q[d].y * kb.y) + (q[d].z * kb.z + q[d].w * kb.w);
+      q[u][d].x *= scale; q[u][d].y *= scale; q[u][d].z *= scale; q[u][d].w *= scale;
+      acc[u][d] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    m = s;
-    l = float(npad);
+    m[u] = -INFINITY; l[u] = 0.f;
+  }
+  if (npad > 0) {
 #pragma unroll
-    for (int d = 0; d < D4; ++d) {
-      const float4 vb = reinterpret_cast<const float4*>(qkv_bias + 2 * C + head * D)[d];
-      acc[d] = make_float4(l * vb.x, l * vb.y, l * vb.z, l * vb.w);
+    for (int u = 0; u < QB; ++u) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < D4; ++d) {
+        const float4 kb = reinterpret_cast<const float4*>(qkv_bias + C + head * D)[d];
+        s += (q[u][d].x * kb.x + q[u][d].y * kb.y) + (q[u][d].z * kb.z + q[u][d].w * kb.w);
+      }
+      m[u] = s;
+      l[u] = float(npad);
+#pragma unroll
+      for (int d = 0; d < D4; ++d) {
+        const float4 vb = reinterpret_cast<const float4*>(qkv_bias + 2 * C + head * D)[d];
+        acc[u][d] = make_float4(l[u] * vb.x, l[u] * vb.y, l[u] * vb.z, l[u] * vb.w);
+      }
     }
   }
   mbar_wait(bar, 0);
   for (int j = 0; j < nreal; ++j) {
     const float4* kr = wsm4 + j * row4 + hh * D4;
-    float s = 0.f;
+    float s[QB], p[QB];
+#pragma unroll
+    for (int u = 0; u < QB; ++u) s[u] = 0.f;
 #pragma unroll
     for (int d = 0; d < D4; ++d) {
       const float4 kk = kr[d];
-      s += (q[d].x * kk.x + q[d].y * kk.y) + (q[d].z * kk.z + q[d].w * kk.w);
-    }
-    if (s > m) {
-      const float r = __expf(m - s);
-      l *= r;
 #pragma unroll
-      for (int d = 0; d < D4; ++d) { acc[d].x *= r; acc[d].y *= r; acc[d].z *= r; acc[d].w *= r; }
-      m = s;
+      for (int u = 0; u < QB; ++u) s[u] += (q[u][d].x * kk.x + q[u][d].y * kk.y) + (q[u][d].z * kk.z + q[u][d].w * kk.w);
     }
-    const float p = __expf(s - m);
-    l += p;
+#pragma unroll
+    for (int u = 0; u < QB; ++u) {
+      if (s[u] > m[u]) {
+        const float r = __expf(m[u] - s[u]);
+        l[u] *= r;
+#pragma unroll
+        for (int d = 0; d < D4; ++d) { acc[u][d].x *= r; acc[u][d].y *= r; acc[u][d].z *= r; acc[u][d].w *= r; }
+        m[u] = s[u];
+      }
+      p[u] = __expf(s[u] - m[u]);
+      l[u] += p[u];
+    }
     const float4* vr = kr + HPC * D4;
 #pragma unroll
     for (int d = 0; d < D4; ++d) {
       const float4 vv = vr[d];
-      acc[d].x += p * vv.x; acc[d].y += p * vv.y; acc[d].z += p * vv.z; acc[d].w += p * vv.w;
+#pragma unroll
+      for (int u = 0; u < QB; ++u) {
+        acc[u][d].x += p[u] * vv.x; acc[u][d].y += p[u] * vv.y; acc[u][d].z += p[u] * vv.z; acc[u][d].w += p[u] * vv.w;
+      }
     }
   }
-  const float inv = 1.f / l;
   __syncthreads();                                  // everyone is done reading K / V: reuse the buffer as the output stage
   // stage: [plane (hi, lo)][token][HPC*32 halves]
   __half* stg = reinterpret_cast<__half*>(wsm4);
   const int seg = HPC * D;                          // halves per token per plane
-  {
-    __half* rh = stg + t * seg;
+#pragma unroll
+  for (int u = 0; u < QB; ++u) {
+    const float inv = 1.f / l[u];
+    __half* rh = stg + (t0 + u * nq) * seg;
 #pragma unroll
     for (int d = 0; d < D4; ++d)
-      put4(rh, hh * D + 4 * d, split ? nreal * seg : 0, make_float4(acc[d].x * inv, acc[d].y * inv, acc[d].z * inv, acc[d].w * inv));
+      put4(rh, hh * D + 4 * d, split ? nreal * seg : 0,
+           make_float4(acc[u][d].x * inv, acc[u][d].y * inv, acc[u][d].z * inv, acc[u][d].w * inv));
   }
   __syncthreads();
   const int planes = split ? 2 : 1;
@@ -294,18 +317,24 @@ int window_attn_crop_launch(const float* qkv, const float* qkv_bias, int B, int 
   int HPC = 256 / nreal;
   if (HPC > heads) HPC = heads;
   while (HPC > 1 && heads % HPC) --HPC;
-  const int threads = HPC * nreal;
-  if (threads > 256 || threads < 1) return 1;
+  const int QB = (nreal % 2 == 0) ? 2 : 1;          // two queries per thread whenever the token count is even
+  const int threads = HPC * (nreal / QB);
+  if (threads > 256 / QB || threads < 1) return 1;
   const size_t smem = size_t(2) * nreal * HPC * 32 * sizeof(float) + 16;
   static std::atomic<bool> attr{false};
   if (!attr) {
-    if (cudaFuncSetAttribute(window_attn_crop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(window_attn_crop_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(window_attn_crop_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65 * 1024) != cudaSuccess)
       return set_error("window_attn: cudaFuncSetAttribute failed");
     attr = true;
   }
   if (smem > 65 * 1024) return 1;
-  launch_pdl(window_attn_crop_kernel, dim3(B * (heads / HPC)), dim3(threads), smem, st, qkv, qkv_bias, nreal, win * win - nreal, C,
-             heads, HPC, (__half*)out, split ? 1 : 0);
+  if (QB == 2)
+    launch_pdl(window_attn_crop_kernel<2>, dim3(B * (heads / HPC)), dim3(threads), smem, st, qkv, qkv_bias, nreal, win * win - nreal, C,
+               heads, HPC, (__half*)out, split ? 1 : 0);
+  else
+    launch_pdl(window_attn_crop_kernel<1>, dim3(B * (heads / HPC)), dim3(threads), smem, st, qkv, qkv_bias, nreal, win * win - nreal, C,
+               heads, HPC, (__half*)out, split ? 1 : 0);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
   count_launch();

@@ -162,6 +162,9 @@ class FlorenceWeights:
         return _f(pos.reshape(h * w, -1) + temporal[None], self.device)
 
 
+POOL_DEFAULT = "0"     # flipped to "1" once the pooled layout has passed the GPU parity tests
+
+
 class FlorencePlan:
     """Buffers + launch sequences for a fixed number of crop rows K (64x64 crops)."""
 
@@ -207,6 +210,9 @@ class FlorencePlan:
         self._logits_buf = torch.zeros((K, (w.vocab + 7) // 8 * 8), dtype=torch.float32, device=dev)
         self.logits = self._logits_buf[:, :w.vocab]
         self.enc_ops, self.dec_ops = [], []
+        self._pools = {}
+        # B2P_BUFFER_POOL=1: re-use intermediates across blocks / layers (see _pool); 0 = one buffer per intermediate
+        self.pool = os.environ.get("B2P_BUFFER_POOL", POOL_DEFAULT) != "0"
         self.flops_enc = 0   # logical (useful) FLOPs; the fp16x3 mode executes 3x this on the tensor cores
         self.flops_dec = 0
         self._build_vision_encoder()
@@ -222,6 +228,18 @@ class FlorencePlan:
     def _act(self, T, C):
         """fp16 GEMM-operand buffer for T rows of logical width C ([hi(C) | lo(C)] in fp16x3 mode)."""
         return torch.zeros((T, self.KX * C), dtype=torch.float16, device=self.dev)
+
+    def _pool(self, role, T, C, act=False):
+        """One buffer per (role, shape) for the whole plan: the blocks of a DaViT stage / the BART encoder layers run one after
+        the other, so block i+1 re-uses the intermediates of block i (a plan at 416 crops drops from ~7.5 GB to ~1.5 GB, and
+        caption grouping / a third lane / many crop-count buckets stop exhausting HBM).  Roles are chosen so that no kernel
+        reads a buffer it writes: see the liveness notes at the call sites."""
+        if not self.pool:
+            return self._act(T, C) if act else self._e(T, C)
+        key = (role, T, C, act)
+        if key not in self._pools:
+            self._pools[key] = self._act(T, C) if act else self._e(T, C)
+        return self._pools[key]
 
     def _gemm(self, lst, a, lin, out, act=ACT_NONE, res=None, enc=True, split=False):
         M = a.shape[0]
@@ -294,31 +312,35 @@ class FlorencePlan:
                     self.flops_enc += 2 * T * C * 9 * Cp
                     ops_.append(lambda hmap=hmap, xo=xo, ce=ce: ops.conv3x3(hmap, ce.w, xo, 2, ce.b, None, ACT_NONE, out_f32=True, x3=x3))
                 x = xo.buf.view(T, C)
+            # Buffer roles of a stage (fp32 [T, C] unless noted); every block re-uses them:
+            #   xA: x1 = x + dw1(x), x3 = x2 + dw2(x2)      xB: x2 = proj(a) + x1, x4 = fc2(f) + x3 (the block output)
+            #   act (fp16 operand): h = LN(x1) -> a = attention(qkv) -> h2 = LN(x3)      qkv [T, 3C]      f (fp16 operand, 4C)
+            # Liveness: dw1 reads the block input (xB or the stage's fresh patch-embed output) and writes xA; the proj GEMM reads
+            # a + residual xA and writes xB; dw2 reads xB, writes xA (x1 is dead: proj consumed it) and act (a is dead); fc2
+            # reads f + residual xA and writes xB (x2 is dead: dw2 consumed it).  h dies at the qkv GEMM, before attention writes a.
             for blk in w.blocks[s]:
                 for kind in ("spatial_block", "channel_block"):
                     e = blk[kind]
-                    x1 = self._e(T, C)
-                    h = self._act(T, C)
+                    xA, xB = self._pool("xA", T, C), self._pool("xB", T, C)      # without pooling: fresh buffers per block
+                    act_, qkv, f = self._pool("act", T, C, act=True), self._pool("qkv", T, 3 * C), self._pool("f", T, 4 * C, act=True)
+                    x1, h = xA, act_
                     ops_.append(lambda x=x, x1=x1, h=h, e=e, H=H, C=C: ops.dwconv_ln(x, K, H, H, C, e["dw1_w"], e["dw1_b"], x1,
                                                                                  e["n1"].g, e["n1"].b, h, split=x3, tile=self.dw_tile, v3=self.v3))
-                    qkv = self._e(T, 3 * C)
                     self._gemm(ops_, h, e["qkv"], qkv)
-                    a = self._act(T, C)
+                    a = act_
                     if kind == "spatial_block":
                         hd = w.heads[s]
                         ops_.append(lambda qkv=qkv, a=a, e=e, H=H, C=C, hd=hd: ops.window_attn(qkv, e["qkv"].b, K, H, H, C, hd, a, split=x3, v3=self.v3))
                     else:
                         gr = w.groups[s]
                         ops_.append(lambda qkv=qkv, a=a, H=H, C=C, gr=gr: ops.channel_attn(qkv, K, H * H, C, gr, a, split=x3, small=self.ca_small, v3=self.v3))
-                    x2 = self._e(T, C)
+                    x2 = xB
                     self._gemm(ops_, a, e["proj"], x2, res=x1)
-                    x3_ = self._e(T, C)
-                    h2 = self._act(T, C)
+                    x3_, h2 = xA, act_
                     ops_.append(lambda x2=x2, x3_=x3_, h2=h2, e=e, H=H, C=C: ops.dwconv_ln(x2, K, H, H, C, e["dw2_w"], e["dw2_b"], x3_,
                                                                                       e["n2"].g, e["n2"].b, h2, split=x3, tile=self.dw_tile, v3=self.v3))
-                    f = self._act(T, 4 * C)
                     self._gemm(ops_, h2, e["fc1"], f, act=ACT_GELU, split=x3)
-                    x4 = self._e(T, C)
+                    x4 = xB
                     self._gemm(ops_, f, e["fc2"], x4, res=x3_)
                     x = x4
         self.vision_out = x                     # [K*HW, 1024] fp32, H = 2
@@ -339,20 +361,24 @@ class FlorencePlan:
         x = self._e(TE, D)
         h = self._act(TE, D)
         self._ln(ops_, e0, w.enc_ln_emb, TE, D, h, x)
+        # encoder layers re-use five buffers: qkv; a (the fp16 operand buffer h: h dies at the qkv GEMM, before attention writes
+        # a, and a dies at the out-proj GEMM, before LayerNorm writes the next h); y (GEMM + residual output, consumed by the
+        # LayerNorm that follows); x (the LayerNorm output overwrites the residual the GEMM has already consumed); f
         for lay in w.enc_layers:
-            qkv = self._e(TE, 3 * D)
+            qkv, f = self._pool("eqkv", TE, 3 * D), self._pool("ef", TE, 4 * D, act=True)
             self._gemm(ops_, h, lay["qkv"], qkv)
-            a = self._act(TE, D)
+            a = h if self.pool else self._act(TE, D)
             ops_.append(lambda qkv=qkv, a=a: ops.mha(qkv, 3 * D, qkv[:, D:], qkv[:, 2 * D:], 3 * D, K, L, L, self.HEADS, a, a.stride(0), split=x3, v3=self.v3))
-            y = self._e(TE, D)
+            y = self._pool("ey", TE, D)
             self._gemm(ops_, a, lay["o"], y, res=x)
-            x = self._e(TE, D); h = self._act(TE, D)
+            if not self.pool:
+                x, h = self._e(TE, D), self._act(TE, D)
             self._ln(ops_, y, lay["ln1"], TE, D, h, x)
-            f = self._act(TE, 4 * D)
             self._gemm(ops_, h, lay["fc1"], f, act=ACT_GELU, split=x3)
-            y = self._e(TE, D)
+            y = self._pool("ey", TE, D)
             self._gemm(ops_, f, lay["fc2"], y, res=x)
-            x = self._e(TE, D); h = self._act(TE, D)
+            if not self.pool:
+                x, h = self._e(TE, D), self._act(TE, D)
             self._ln(ops_, y, lay["ln2"], TE, D, h, x)
         self.enc_out32, self.enc_out16 = x, h
         # cross-attention K/V of every decoder layer, once per batch (fp32: read by the attention kernel)

@@ -439,6 +439,23 @@ def test_window_attn_v3_equals_first_version_and_torch(B, H, C, heads, split):
     assert (_pair_val(outs[1].cpu(), C, split) - ref).abs().max().item() < tol
 
 
+@pytest.mark.parametrize("B,H,C,heads", [(3, 16, 128, 4), (2, 20, 128, 4), (2, 13, 256, 8)])
+@pytest.mark.parametrize("split", [False, True])
+def test_window_attn_multi_window_maps_v3_flag(B, H, C, heads, split):
+    """maps larger than one 12x12 window (16x16 in the 64x64-crop mode: windows of 144 / 48 / 48 / 16 real tokens) are not
+    covered by the one-window kernel: with the v3 flag the call must fall through to the per-window kernel, same results."""
+    g = torch.Generator().manual_seed(B * H + C + 5)
+    qkv = torch.randn(B * H * H, 3 * C, generator=g).to(DEV)
+    bias = torch.randn(3 * C, generator=g).to(DEV)
+    outs = []
+    for v3 in (False, True):
+        o = torch.zeros(B * H * H, (2 if split else 1) * C, dtype=torch.float16, device=DEV)
+        ops.window_attn(qkv, bias, B, H, H, C, heads, o, split=split, v3=v3)
+        torch.cuda.synchronize()
+        outs.append(o)
+    _act_close(outs[1], outs[0], C, split)
+
+
 @pytest.mark.parametrize("B,N,C", [(7, 16, 512), (5, 4, 1024), (3, 9, 256), (3, 64, 256), (2, 256, 128), (2, 100, 128)])
 @pytest.mark.parametrize("split", [False, True])
 def test_channel_attn_v3_equals_first_version_and_torch(B, N, C, split):
