@@ -6,7 +6,7 @@ packs weights K-major fp16, lays every feature map out as an NHWC fp16 channel s
 graph.  All arithmetic runs in ``libb200parse.so``: tcgen05 implicit-GEMM convs with fused bias+SiLU(+residual)
 epilogues plus the HBM-bound pooling / upsample / CBFuse kernels.
 
-Topology: WongKinYiu/yolov9 ``yolov9-e.yaml`` (restated in oracle/yolov9e.py).
+Topology: WongKinYiu/yolov9 ``yolov9-e.yaml`` (restated in standin/yolov9e.py).
 """
 from __future__ import annotations
 
@@ -114,7 +114,7 @@ class _W:
 
 
 class YoloWeights:
-    """Folded + packed parameters, from a state_dict in oracle/yolov9e.py naming (``l{N}.…``, ``detect.…``);
+    """Folded + packed parameters, from a state_dict in standin/yolov9e.py naming (``l{N}.…``, ``detect.…``);
     upstream archives name the same tensors ``model.{N}.…`` / ``model.42.…`` (see :func:`rename_upstream`)."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], device, nc: int | None = None, precision: str = "fp16"):

@@ -19,10 +19,10 @@ from PIL import Image
 
 from omniparser_b200 import synth
 
-from . import florence_standin as FS
+from standin import florence as FS
 from .shims import import_reference
-from .standin import GOLDEN, yolo_standin
-from .yolov9e import export_torchscript
+from standin.yolo_weights import GOLDEN, yolo_standin
+from standin.yolov9e import export_torchscript
 
 CASES = [dict(name="synth_seed0", seed=0, size=(1920, 1080)), dict(name="synth_seed3_odd", seed=3, size=(1919, 1079)),
          dict(name="synth_seed5_3240x2160", seed=5, size=(3240, 2160))]   # geometry of ref:imgs/demo_image.jpg (BASELINE configs[0])

@@ -17,7 +17,7 @@ from typing import List, Sequence
 import numpy as np
 import torch
 
-from . import florence_standin as FS
+from standin import florence as FS
 from . import ref_restate as R
 
 
@@ -77,7 +77,7 @@ def build_elements(xyxy_ratio, ocr_ratio, ocr_text, w, h, iou_threshold):
 # --------------------------------------------------------------------------- the pipeline
 class OraclePipeline:
     def __init__(self, yolo=None, florence=None):
-        from .standin import yolo_standin
+        from standin.yolo_weights import yolo_standin
         self.yolo = yolo if yolo is not None else yolo_standin(0)
         self.florence = florence if florence is not None else FS.florence_standin(0)
 

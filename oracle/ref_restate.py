@@ -9,7 +9,7 @@ independently.  ``tests/test_oracle_cpu.py`` checks every function here against
 the unmodified reference (when ``/root/reference`` is present) and against
 Pillow / OpenCV / torchvision themselves.  parity: pinned on Pillow 12.2,
 OpenCV 4.13, torchvision 0.26 (the versions in this image); the network
-arithmetic itself is "parity unpinned" (see oracle/yolov9e.py).
+arithmetic itself is "parity unpinned" (see standin/yolov9e.py).
 """
 from __future__ import annotations
 

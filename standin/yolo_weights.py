@@ -94,7 +94,7 @@ def yolo_standin(seed: int = 0, nc: int = 1) -> YOLOv9E:
         stats = np.load(BN_CALIB)
     else:
         if seed == 0:
-            raise FileNotFoundError(f"{BN_CALIB} missing; run `python -m oracle.standin` where it can be regenerated")
+            raise FileNotFoundError(f"{BN_CALIB} missing; run `python -m standin.yolo_weights` where it can be regenerated")
         stats = _calibrate_bn(m)
     bns = [b for b in m.modules() if isinstance(b, nn.BatchNorm2d)]
     with torch.no_grad():

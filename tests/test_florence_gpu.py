@@ -1,4 +1,4 @@
-"""GPU parity of the Florence-2 engine against the fp32 HF oracle (oracle/florence_standin.py), 64x64-crop mode.
+"""GPU parity of the Florence-2 engine against the fp32 HF oracle (standin/florence.py), 64x64-crop mode.
 
 Checks, in order of the data flow: image tokens, encoder states, teacher-forced logits at every decode step
 (tolerance stated below), processed scores / forced tokens, and the free-running greedy ids (must be identical)."""
@@ -9,7 +9,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from omniparser_b200.florence_engine import FlorencePlan, FlorenceWeights  # noqa: E402
-from oracle import florence_standin as FS  # noqa: E402
+from standin import florence as FS  # noqa: E402
 
 DEV = "cuda:0"
 K = 6

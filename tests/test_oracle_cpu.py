@@ -74,8 +74,8 @@ def test_restatement_equals_reference_wrapper(tmp_path):
     """End-to-end: unmodified YOLOv9Detector.predict (ref:util/yolov9.py:115-136) vs the restated pipeline."""
     from PIL import Image
     from oracle.shims import import_reference
-    from oracle.standin import yolo_standin
-    from oracle.yolov9e import export_torchscript
+    from standin.yolo_weights import yolo_standin
+    from standin.yolov9e import export_torchscript
     _, ry = import_reference()
     m = yolo_standin(0)
     path = tmp_path / "icon_detect_v3" / "model.pt"

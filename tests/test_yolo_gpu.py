@@ -1,4 +1,4 @@
-"""GPU parity of the YOLOv9-E engine against the fp32 PyTorch oracle (oracle/yolov9e.py) on seeded weights.
+"""GPU parity of the YOLOv9-E engine against the fp32 PyTorch oracle (standin/yolov9e.py) on seeded weights.
 
 The engine computes in fp16 with fp32 accumulation (the reference's own CUDA path is fp16 autocast,
 ref:util/yolov9.py:110-113); tolerances below are for fp16-vs-fp32 drift through ~100 conv layers and are
@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 from omniparser_b200 import synth  # noqa: E402
 from omniparser_b200.detector import B200YOLOv9Detector  # noqa: E402
 from oracle import ref_restate as R  # noqa: E402
-from oracle.standin import yolo_standin  # noqa: E402
+from standin.yolo_weights import yolo_standin  # noqa: E402
 
 DEV = "cuda:0"
 TAP_LAYERS = {"x3": "l3", "x5": "l5", "x7": "l7", "x9": "l9", "x19": "l19", "x22": "l22", "x25": "l25", "x28": "l28",

@@ -3,7 +3,7 @@ import sys, time
 import torch
 sys.path.insert(0, ".")
 from omniparser_b200.yolo_engine import YoloPlan, YoloWeights
-from oracle.standin import yolo_standin
+from standin.yolo_weights import yolo_standin
 
 dev = torch.device("cuda:0")
 w = YoloWeights(yolo_standin(0).state_dict(), dev)
