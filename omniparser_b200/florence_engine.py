@@ -162,7 +162,7 @@ class FlorenceWeights:
         return _f(pos.reshape(h * w, -1) + temporal[None], self.device)
 
 
-POOL_DEFAULT = "0"     # flipped to "1" once the pooled layout has passed the GPU parity tests
+POOL_DEFAULT = "1"     # pooled layout: validated against the GPU parity tests (round 2); B2P_BUFFER_POOL=0 restores one buffer per intermediate
 
 
 class FlorencePlan:
