@@ -161,41 +161,41 @@ __global__ void lanczos_v_paste_kernel(const unsigned char* __restrict__ tmp, in
 }
 
 // ----------------------------------------------------------------------------------------- im2col
-// One thread per (output pixel, 8-element chunk of its row): consecutive threads write consecutive 16-byte chunks (the first
-// version gave a thread a whole row: 64-320 bytes per thread at a row-pitch stride, ~1 TB/s).
+// One thread per output pixel writes the whole row.  (One thread per 8-element chunk -- coalesced 16-byte stores across the
+// warp -- was measured in round 2: 59 -> 78 us on the detector stem, 8x640x640, Kpad 32; the per-element index arithmetic is the
+// bound, not the store pattern.)
 __global__ void im2col_u8_kernel(const unsigned char* __restrict__ img, int B, int H, int W, int k, int s, int p,
                                  int Ho, int Wo, int Kpad, const float* __restrict__ lut /*[3][256]*/,
                                  __half* __restrict__ out, int split) {
   pdl_wait();   // PDL: inputs come from the previous kernel in the stream
-  const int chunks = Kpad >> 3;
-  const long long n = (long long)B * Ho * Wo * chunks;
+  const long long n = (long long)B * Ho * Wo;
   const int K = k * k * 3;
-  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < n; it += (long long)gridDim.x * blockDim.x) {
-    const int k0 = int(it % chunks) << 3;
-    const long long i = it / chunks;            // output pixel
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int ox = int(i % Wo);
     const int oy = int((i / Wo) % Ho);
     const int b = int(i / ((long long)Wo * Ho));
     __half* o = out + i * (split ? 2 * Kpad : Kpad);
-    __align__(16) __half v[8];
-    __align__(16) __half lo[8];
+    for (int k0 = 0; k0 < Kpad; k0 += 8) {
+      __align__(16) __half v[8];
+      __align__(16) __half lo[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int kk = k0 + j;
-      float f = 0.f;
-      if (kk < K) {
-        const int c = kk % 3;
-        const int tap = kk / 3;
-        const int ky = tap / k, kx = tap - ky * k;
-        const int y = oy * s - p + ky, x = ox * s - p + kx;
-        if (y >= 0 && y < H && x >= 0 && x < W) f = lut[c * 256 + img[(((long long)b * H + y) * W + x) * 3 + c]];
+      for (int j = 0; j < 8; ++j) {
+        const int kk = k0 + j;
+        float f = 0.f;
+        if (kk < K) {
+          const int c = kk % 3;
+          const int tap = kk / 3;
+          const int ky = tap / k, kx = tap - ky * k;
+          const int y = oy * s - p + ky, x = ox * s - p + kx;
+          if (y >= 0 && y < H && x >= 0 && x < W) f = lut[c * 256 + img[(((long long)b * H + y) * W + x) * 3 + c]];
+        }
+        v[j] = __float2half_rn(f);
+        lo[j] = __float2half_rn(f - __half2float(v[j]));
       }
-      v[j] = __float2half_rn(f);
-      lo[j] = __float2half_rn(f - __half2float(v[j]));
+      *reinterpret_cast<uint4*>(o + k0) = *reinterpret_cast<const uint4*>(v);
+      if (split)   // fp16x3 operand layout [hi | lo], see florence_ops.cu::store_act
+        *reinterpret_cast<uint4*>(o + Kpad + k0) = *reinterpret_cast<const uint4*>(lo);
     }
-    *reinterpret_cast<uint4*>(o + k0) = *reinterpret_cast<const uint4*>(v);
-    if (split)   // fp16x3 operand layout [hi | lo], see florence_ops.cu::store_act
-      *reinterpret_cast<uint4*>(o + Kpad + k0) = *reinterpret_cast<const uint4*>(lo);
   }
 }
 
@@ -341,9 +341,7 @@ int b2p_im2col_u8(const unsigned char* img, int B, int H, int W, int k, int s, i
                   void* out, int split, cudaStream_t st) {
   if (Kpad % 8 || Kpad < k * k * 3) return set_error("im2col_u8: Kpad must be a multiple of 8 and >= 3*k*k");
   const int Ho = (H + 2 * p - k) / s + 1, Wo = (W + 2 * p - k) / s + 1;
-  const long long n_items = (long long)B * Ho * Wo * (Kpad / 8);
-  const long long n_ctas = (n_items + 255) / 256;
-  launch_pdl(im2col_u8_kernel, dim3(unsigned(n_ctas < 1 ? 1 : (n_ctas > (1LL << 20) ? (1LL << 20) : n_ctas))), dim3(256), 0, st, img, B, H, W, k, s, p, Ho, Wo, Kpad, lut, (__half*)out, split);
+  launch_pdl(im2col_u8_kernel, dim3(grid_for((long long)B * Ho * Wo, 128)), dim3(128), 0, st, img, B, H, W, k, s, p, Ho, Wo, Kpad, lut, (__half*)out, split);
   B2P_CHECK_LAUNCH();
   return 0;
 }
