@@ -943,9 +943,11 @@ static void pick_tiling(int N, int m_tiles, int num_kb, int bk, uint32_t a_bytes
                         int* bn_out, int* ksplit_out) {
   static const int cand[] = {256, 192, 128, 96, 64, 48, 32, 16};
   // single-wave launches: measured constants + a charge per occupied SM (B2P_DENSE_GRIDS=1 restores the round-1 model that
-  // spreads every launch over as many SMs as it can; B2P_CTA_PENALTY = microseconds charged per CTA, default 0.04)
+  // spreads every launch over as many SMs as it can; B2P_CTA_PENALTY = microseconds charged per CTA, default 0.02: with the
+  // grouped caption schedule of the second half of round 2, 0.02 / 0.04 / 0.08 / dense grids measured 14.42 / 14.54 / 14.82 /
+  // 14.63 ms per step and 4.47 / 4.73 / 4.90 / 4.43 ms per stand-alone detector forward)
   static const bool few_ctas = getenv("B2P_DENSE_GRIDS") == nullptr;
-  static const double cta_penalty = getenv("B2P_CTA_PENALTY") ? atof(getenv("B2P_CTA_PENALTY")) : 0.04;
+  static const double cta_penalty = getenv("B2P_CTA_PENALTY") ? atof(getenv("B2P_CTA_PENALTY")) : 0.02;
   const int n16 = (N + 15) / 16 * 16;
   double best_cost = -1;
   int best = 16, best_ks = 1;
