@@ -191,6 +191,76 @@ def test_kernel_variant_flags_are_forwarded(rec, florence, monkeypatch):
     assert {c[1][-2] for c in rec.calls if c[0] in ("b2p_dwconv_ln", "b2p_channel_attn")} == {1}   # the round-1 kernels
 
 
+# ---- data flow of the pooled caption-encoder plan -------------------------------------------------------------------
+_ROLES = {   # op -> (indices of tensor inputs, indices of tensor outputs) in the positional arguments of ops.<op>
+    "im2col_u8": ((0,), (9,)), "gemm": ((0, 9), (6,)), "layernorm": ((0,), (5, 6)), "dwconv_ln": ((0,), (7, 10)),
+    "window_attn": ((0,), (7,)), "channel_attn": ((0,), (5,)), "mha": ((0, 2, 3), (9,)), "conv3x3": ((0, 5), (2,)),
+    "im2col3x3": ((0,), (2,)), "projector_prep": ((0,), (5,)), "encoder_embed": ((0,), (8,)), "resize_u8": ((0,), (7, 8)),
+}
+
+
+def _storage(t):
+    if t is None:
+        return None
+    if isinstance(t, ops.Map):
+        t = t.buf
+    return t.untyped_storage().data_ptr() if isinstance(t, torch.Tensor) else None
+
+
+def _trace_ops(monkeypatch):
+    """wrap the ops.* front ends of the encode launches: (name, storages read, storages written) per call"""
+    trace = []
+
+    def wrap(name, fn):
+        ins, outs = _ROLES[name]
+
+        def w(*a, **k):
+            full = list(a) + [None] * 12
+            if name == "gemm" and "res" in k:
+                full[9] = k["res"]
+            if name == "conv3x3" and "res" in k:
+                full[5] = k["res"]
+            if name == "layernorm":
+                full[5], full[6] = k.get("out16", full[5]), k.get("out32", full[6])
+            trace.append((name, [_storage(full[i]) for i in ins], [_storage(full[i]) for i in outs]))
+            return fn(*a, **k)
+        return w
+    for name in _ROLES:
+        monkeypatch.setattr(ops, name, wrap(name, getattr(ops, name)))
+    return trace
+
+
+def _dataflow(trace, monkeypatch, florence, pool):
+    """[(op, producers of its inputs)]: for every input tensor of every encode launch, the index of the launch that last wrote
+    the buffer it lives in (-1 = never written by the plan: crops, weights)."""
+    from omniparser_b200.florence_engine import FlorencePlan, FlorenceWeights
+    monkeypatch.setenv("B2P_BUFFER_POOL", "1" if pool else "0")
+    del trace[:]
+    w = FlorenceWeights(florence.state_dict(), torch.device("cpu"), FS.GEN, "fp16x3")
+    p = FlorencePlan(w, 2, 2, FS.PROMPT_IDS, use_graph=False, size=64)
+    p.encode()
+    last_writer, flow = {}, []
+    for i, (name, ins, outs) in enumerate(trace):
+        flow.append((name, [last_writer.get(s, -1) if s is not None else None for s in ins]))
+        assert not (set(s for s in ins if s is not None) & set(s for s in outs if s is not None)), (i, name, "reads a buffer it writes")
+        for s in outs:
+            if s is not None:
+                last_writer[s] = i
+    return flow, len(last_writer), p     # the plan is returned so that its buffers stay alive (storage pointers stay unique)
+
+
+def test_buffer_pool_preserves_dataflow(rec, florence, monkeypatch):
+    """The pooled caption-encoder plan (five buffers per DaViT stage / BART encoder instead of one per intermediate) must have
+    the SAME data flow as the one-buffer-per-intermediate plan: every input of every launch is produced by the same launch."""
+    trace = _trace_ops(monkeypatch)
+    flow_pool, n_pool, keep1 = _dataflow(trace, monkeypatch, florence, True)
+    flow_flat, n_flat, keep2 = _dataflow(trace, monkeypatch, florence, False)
+    assert len(flow_pool) == len(flow_flat) == 232
+    for i, (a, b) in enumerate(zip(flow_pool, flow_flat)):
+        assert a == b, (i, a, b)
+    assert n_pool < n_flat / 4, (n_pool, n_flat)        # and it really is pooled
+
+
 def test_yolo_plan(rec):
     from omniparser_b200.yolo_engine import YoloPlan, YoloWeights
     from standin.yolo_weights import yolo_standin
